@@ -1,0 +1,147 @@
+/* nlt_b200.h -- C ABI of the B200-native NLT UV-space hot path.
+ *
+ * The reference (google/neural-light-transport) has NO native/FFI boundary:
+ * its numerics live in pip wheels (tensorflow 2.2 / tensorflow-addons 0.10)
+ * called from Keras layers.  Each entry point below therefore cites the
+ * reference *call site* it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to fp32, NHWC contiguous, owned by the
+ *    caller (the library never allocates; workspace is queried, then passed)
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*)
+ *  - return 0 on success; <0 on error, message via nlt_last_error()
+ *      NLT_ERR_INVALID      bad shape / argument      (reference: ValueError/AssertionError)
+ *      NLT_ERR_UNSUPPORTED  unsupported configuration (reference: NotImplementedError)
+ *      NLT_ERR_CUDA         CUDA runtime failure
+ *  - re-entrant for distinct streams; no global mutable state
+ */
+#ifndef NLT_B200_H_
+#define NLT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NLT_MAX_SEG 4
+
+#define NLT_OK 0
+#define NLT_ERR_INVALID (-1)
+#define NLT_ERR_UNSUPPORTED (-2)
+#define NLT_ERR_CUDA (-3)
+
+/* activation codes -- nlt/networks/elements.py:69-78 */
+#define NLT_ACT_NONE 0
+#define NLT_ACT_RELU 1
+#define NLT_ACT_LEAKYRELU 2 /* alpha = 0.3 */
+#define NLT_ACT_ELU 3       /* alpha = 1.0 */
+
+/* One generalised convolution  out[p, n] = sum_{tap, c} A[map(p, tap), c] * W[tap, c, n]
+ * over a *virtual channel concat* A of up to NLT_MAX_SEG NHWC tensors (the
+ * tf.concat calls of nlt/models/nlt.py:95, :174, :190 are never materialised).
+ *
+ *   transposed == 0 : map(p,d) = p*stride + d - pad      (Conv2D 'same',          elements.py:26-31)
+ *   transposed == 1 : map(p,d) = (p + pad - d) / stride  (Conv2DTranspose 'same', elements.py:34-39;
+ *                     taps with a non-integer quotient are skipped)
+ *
+ * pad_t/pad_l are the TF-SAME pad_before of the underlying strided forward conv.
+ * Weight element (tap=dy*kw+dx, c, n) lives at w[tap*w_tap_stride + c*w_c_stride + n*w_n_stride],
+ * so that Keras Conv2D kernels (kh,kw,Ci,Co) and Conv2DTranspose kernels
+ * (kh,kw,Co,Ci) are both consumed in place, and the adjoint (dgrad) of either
+ * op is the other op on the same buffer with swapped strides.
+ */
+typedef struct nlt_gconv_desc {
+  int32_t N;          /* batch */
+  int32_t Hin, Win;   /* spatial size of the gathered operand A */
+  int32_t Hout, Wout; /* spatial size of the output lattice */
+  int32_t kh, kw, stride;
+  int32_t pad_t, pad_l;
+  int32_t transposed;
+  int32_t nseg;                      /* 1..NLT_MAX_SEG */
+  const float* seg_ptr[NLT_MAX_SEG]; /* [N or 1, Hin, Win, seg_C] */
+  const float* seg_sub[NLT_MAX_SEG]; /* optional: A = seg_ptr - seg_sub (nn_rgb - nn_base, models/nlt.py:96) */
+  int32_t seg_C[NLT_MAX_SEG];
+  int32_t seg_bcast[NLT_MAX_SEG];    /* 1: tensor has batch 1 and is broadcast (tf.tile in nlt_test.py:84) */
+  int32_t Cout;
+  const float* w;
+  int64_t w_tap_stride, w_c_stride, w_n_stride;
+} nlt_gconv_desc;
+
+const char* nlt_version(void);
+const char* nlt_last_error(void);
+/* number of CUDA kernels this library has launched so far in this process (diagnostic counter) */
+uint64_t nlt_launch_count(void);
+
+/* out = act(A*W + bias);   then  out = beta*out_old + out;  then out *= act'(mask_y)
+ * Replaces Conv2D / Conv2DTranspose + LeakyReLU (elements.py:26-39, 69-78) and,
+ * with the adjoint descriptor, their input-gradients (tape.gradient,
+ * nlt/trainvali.py:279).  bias, mask_y may be NULL; beta is 0 or 1. */
+int nlt_gconv_fwd(const nlt_gconv_desc* d, const float* bias, int act,
+                  float beta, const float* mask_y, int mask_act,
+                  float* out, void* stream);
+
+/* Weight/bias gradient of the op described by d:
+ *   dW[tap,c,n] (+)= sum_p A[map(p,tap),c] * G[p,n],   db[n] (+)= sum_p G[p,n]
+ * written with the same strides as d->w.  Deterministic (two-stage split
+ * reduction through `workspace`).  accumulate: 0 overwrite, 1 add.
+ * Replaces tape.gradient w.r.t. trainable_variables (nlt/trainvali.py:279). */
+int64_t nlt_gconv_wgrad_workspace_bytes(const nlt_gconv_desc* d);
+int nlt_gconv_wgrad(const nlt_gconv_desc* d, const float* G, float* dW,
+                    float* db, int accumulate, void* workspace,
+                    int64_t workspace_bytes, void* stream);
+
+/* mean over K observations: out[b] = (1/K) sum_k w[b,k] * in[k*B + b]
+ * (tf.reduce_mean over the stacked observation axis, models/nlt.py:161-164).
+ * weights may be NULL.  per_sample = H*W*C elements. */
+int nlt_kmean_fwd(const float* in, const float* weights, int32_t K, int32_t B,
+                  int64_t per_sample, float* out, void* stream);
+/* d_in[k*B+b] = beta*d_in + w[b,k]/K * d_out[b]; then *= act'(mask_y) */
+int nlt_kmean_bwd(const float* d_out, const float* weights, int32_t K,
+                  int32_t B, int64_t per_sample, float beta,
+                  const float* mask_y, int mask_act, float* d_in, void* stream);
+
+/* UV -> camera tail of Model.call (nlt/models/nlt.py:99-120, 132-133):
+ *   pred_uv = net_out (+ base if skip_connect_base); texel (0,0) of pred/base/fg zeroed;
+ *   {fg,base,pred}_camspc = resampler(., warp * (uvw,uvh));  gt_camspc = rgb_camspc * fg_camspc.
+ * warp [B,ih,iw,2] in [0,1].  Any output pointer may be NULL (skipped).
+ * pred_uv [B,H,W,3] is always written. */
+int nlt_uv2cam_fwd(const float* net_out, const float* base, const float* warp,
+                   const float* rgb_camspc, int32_t B, int32_t H, int32_t W,
+                   int32_t ih, int32_t iw, int32_t skip_connect_base,
+                   float* pred_uv, float* pred_camspc, float* base_camspc,
+                   float* fg_camspc, float* gt_camspc, void* stream);
+/* d_net_out [B,H,W,3] = scatter-add of d_pred_camspc through the 4 bilinear
+ * taps, texel (0,0) zeroed (gradient of tfa.image.resampler w.r.t. data).
+ * d_net_out is fully overwritten. */
+int nlt_uv2cam_bwd(const float* d_pred_camspc, const float* warp, int32_t B,
+                   int32_t H, int32_t W, int32_t ih, int32_t iw,
+                   float* d_net_out, void* stream);
+
+/* tf.image.resize bilinear, half-pixel centres (nlt/util/img.py:113-116) */
+int nlt_resize_bilinear_fwd(const float* in, int32_t B, int32_t H, int32_t W,
+                            int32_t C, int32_t oh, int32_t ow, float* out,
+                            void* stream);
+int nlt_resize_bilinear_bwd(const float* d_out, int32_t B, int32_t H, int32_t W,
+                            int32_t C, int32_t oh, int32_t ow, float* d_in,
+                            void* stream);
+
+/* losses.L2 with keep_batch (nlt/losses.py:39-53) fused with its gradient:
+ *   loss[b] = mean_{h,w,c} (gt-pred)^2 ;  d_pred = 2*(pred-gt)*loss_scale/(h*w*c)
+ * loss_scale = 1/global_bs (tf.nn.compute_average_loss, trainvali.py:277-278).
+ * d_pred may be NULL.  partial: >= nlt_l2_loss_workspace_bytes(). */
+int64_t nlt_l2_loss_workspace_bytes(int32_t B, int64_t per_sample);
+int nlt_l2_loss(const float* pred, const float* gt, int32_t B,
+                int64_t per_sample, float loss_scale, float* loss,
+                float* d_pred, void* workspace, void* stream);
+
+/* tf.keras.optimizers.Adam(lr, amsgrad=True) dense update over a flat bucket
+ * (nlt/trainvali.py:122-127, 280); step is 1-based; grad_scale multiplies g. */
+int nlt_amsgrad_step(float* p, const float* g, float* m, float* v, float* vhat,
+                     int64_t n, int32_t step, float lr, float beta1,
+                     float beta2, float eps, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NLT_B200_H_ */

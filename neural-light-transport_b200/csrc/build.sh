@@ -1,0 +1,16 @@
+#!/bin/bash
+# Builds libnlt_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU).
+set -e
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -I../../include"
+OBJS=""
+for f in nlt_gconv nlt_ops ${NLT_EXTRA_SRCS}; do
+  if [ ! -f $f.o ] || [ $f.cu -nt $f.o ] || [ nlt_common.cuh -nt $f.o ] || [ ../../include/nlt_b200.h -nt $f.o ]; then
+    echo "nvcc $f.cu"
+    $NVCC $FLAGS ${NLT_PTXAS_V:+-Xptxas -v} -c $f.cu -o $f.o
+  fi
+  OBJS="$OBJS $f.o"
+done
+$NVCC -shared -o libnlt_b200.so $OBJS -lcudart
+echo "built $(pwd)/libnlt_b200.so"

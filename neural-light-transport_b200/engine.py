@@ -1,0 +1,307 @@
+"""Host-side execution engine for the NLT UV-space hot path.
+
+A small explicit tape (no torch.autograd): every fused op records its own
+backward closure; gradient buffers are accumulated in place by the dgrad
+kernels (beta) and the activation-derivative mask is applied by the LAST
+contributor, so no separate add / mask passes ever run.  All arithmetic is
+done by the CUDA library behind include/nlt_b200.h; torch is used only for
+device memory and streams.
+"""
+import ctypes as C
+import math
+
+import torch
+
+import nlt_native as nat
+
+
+def same_pad(n, k, s):
+    """TF 'SAME' (pad_before, pad_after) -- see SURVEY.md section 8c."""
+    out = -(-n // s)
+    total = max((out - 1) * s + k - n, 0)
+    return total // 2, total - total // 2
+
+
+class Act:
+    """An activation tensor [N,H,W,C] plus the bookkeeping of its gradient."""
+    __slots__ = ('t', 'act', 'grad', 'n_cons', 'n_contrib', 'needs_grad')
+
+    def __init__(self, t, act=None, needs_grad=False):
+        self.t = t
+        self.act = act            # activation that produced t (mask source)
+        self.grad = None
+        self.n_cons = 0           # consumers that will contribute a gradient
+        self.n_contrib = 0
+        self.needs_grad = needs_grad
+
+
+class Seg:
+    """One source of a virtual channel concat."""
+    __slots__ = ('a', 'sub', 'bcast')
+
+    def __init__(self, a, sub=None, bcast=False):
+        self.a = a if isinstance(a, Act) else Act(a)
+        self.sub = sub
+        self.bcast = bcast
+
+    @property
+    def C(self):
+        return self.a.t.shape[3]
+
+
+class Tape:
+    def __init__(self):
+        self.ops = []
+
+    def record(self, fn):
+        self.ops.append(fn)
+
+    def backward(self):
+        for fn in reversed(self.ops):
+            fn()
+        self.ops = []
+
+
+class Workspace:
+    """Grow-only device scratch shared by all wgrad calls on one stream."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes, device):
+        if self.buf is None or self.buf.numel() * 4 < nbytes or self.buf.device != device:
+            self.buf = torch.empty((max(nbytes, 1 << 20) + 3) // 4, dtype=torch.float32, device=device)
+        return self.buf
+
+
+_WS = Workspace()
+
+
+def contribute(target, write_fn):
+    """Adds one gradient contribution into target.grad.
+    write_fn(out, beta, mask_y, mask_act) launches the producing kernel."""
+    if target.grad is None:
+        target.grad = torch.empty_like(target.t)
+        beta = 0.0
+    else:
+        beta = 1.0
+    target.n_contrib += 1
+    last = target.n_contrib == target.n_cons
+    mask = target.t if (last and target.act is not None) else None
+    write_fn(target.grad, beta, mask, nat.ACT_CODES[target.act] if mask is not None else 0)
+
+
+class ConvLayer:
+    """One Conv2D / Conv2DTranspose ('same', bias) with a fused activation.
+    Reference: nlt/networks/elements.py:26-39 (+ :69-78 for the activation).
+    Kernel layouts are Keras': conv (kh,kw,Ci,Co), deconv (kh,kw,Co,Ci)."""
+
+    def __init__(self, kind, k, s, cout, act=None):
+        assert kind in ('conv', 'deconv')
+        self.kind, self.k, self.s, self.cout, self.act = kind, k, s, cout, act
+        self.cin = None
+        self.kernel = self.bias = self.gkernel = self.gbias = None
+        self.grad_written = False
+
+    # ---- parameters -------------------------------------------------------
+    def kernel_shape(self, cin):
+        k = self.k
+        return (k, k, cin, self.cout) if self.kind == 'conv' else (k, k, self.cout, cin)
+
+    @property
+    def built(self):
+        return self.kernel is not None
+
+    def build(self, cin, device, generator=None):
+        """Keras defaults: Glorot-uniform kernel, zero bias."""
+        self.cin = cin
+        shape = self.kernel_shape(cin)
+        limit = math.sqrt(6.0 / (self.k * self.k * (cin + self.cout)))
+        w = (torch.rand(shape, generator=generator, dtype=torch.float32) * 2 - 1) * limit
+        self.kernel = w.to(device)
+        self.bias = torch.zeros(self.cout, dtype=torch.float32, device=device)
+        self.gkernel = torch.zeros_like(self.kernel)
+        self.gbias = torch.zeros_like(self.bias)
+
+    # ---- descriptors ------------------------------------------------------
+    def _geometry(self, Hin, Win):
+        k, s = self.k, self.s
+        if self.kind == 'conv':
+            Hout, Wout = -(-Hin // s), -(-Win // s)
+            pt, pl = same_pad(Hin, k, s)[0], same_pad(Win, k, s)[0]
+        else:
+            Hout, Wout = Hin * s, Win * s
+            pt, pl = same_pad(Hout, k, s)[0], same_pad(Wout, k, s)[0]
+        return Hout, Wout, pt, pl
+
+    def _fwd_desc(self, segs, N, Hin, Win):
+        Hout, Wout, pt, pl = self._geometry(Hin, Win)
+        d = nat.GConvDesc()
+        d.N, d.Hin, d.Win, d.Hout, d.Wout = N, Hin, Win, Hout, Wout
+        d.kh = d.kw = self.k
+        d.stride, d.pad_t, d.pad_l = self.s, pt, pl
+        d.transposed = 0 if self.kind == 'conv' else 1
+        d.nseg = len(segs)
+        for i, sg in enumerate(segs):
+            d.seg_ptr[i] = nat.ptr(sg.a.t)
+            d.seg_sub[i] = nat.ptr(sg.sub)
+            d.seg_C[i] = sg.C
+            d.seg_bcast[i] = 1 if sg.bcast else 0
+        d.Cout = self.cout
+        d.w = nat.ptr(self.kernel)
+        ci, co = self.cin, self.cout
+        if self.kind == 'conv':
+            d.w_tap_stride, d.w_c_stride, d.w_n_stride = ci * co, co, 1
+        else:
+            d.w_tap_stride, d.w_c_stride, d.w_n_stride = ci * co, 1, ci
+        return d
+
+    def _dgrad_desc(self, dz, N, Hin, Win, coff, cseg):
+        """Adjoint op producing d(input segment) from dz = d(pre-activation out)."""
+        Hout, Wout, pt, pl = self._geometry(Hin, Win)
+        d = nat.GConvDesc()
+        d.N, d.Hin, d.Win, d.Hout, d.Wout = N, Hout, Wout, Hin, Win
+        d.kh = d.kw = self.k
+        d.stride, d.pad_t, d.pad_l = self.s, pt, pl
+        d.transposed = 1 if self.kind == 'conv' else 0
+        d.nseg = 1
+        d.seg_ptr[0] = nat.ptr(dz)
+        d.seg_sub[0] = None
+        d.seg_C[0] = self.cout
+        d.seg_bcast[0] = 0
+        d.Cout = cseg
+        ci, co = self.cin, self.cout
+        base = self.kernel.data_ptr()
+        if self.kind == 'conv':      # (kh,kw,Ci,Co): contraction over Co, output over Ci
+            d.w = base + 4 * coff * co
+            d.w_tap_stride, d.w_c_stride, d.w_n_stride = ci * co, 1, co
+        else:                        # (kh,kw,Co,Ci)
+            d.w = base + 4 * coff
+            d.w_tap_stride, d.w_c_stride, d.w_n_stride = ci * co, ci, 1
+        return d
+
+    # ---- execution --------------------------------------------------------
+    def forward(self, segs, tape=None):
+        lib = nat.lib()
+        ref = next(sg for sg in segs if not sg.bcast).a.t
+        N, Hin, Win = ref.shape[0], ref.shape[1], ref.shape[2]
+        cin = sum(sg.C for sg in segs)
+        if not self.built:
+            self.build(cin, ref.device)
+        if cin != self.cin:
+            raise ValueError('layer built for %d input channels, got %d' % (self.cin, cin))
+        for sg in segs:
+            t = sg.a.t
+            if t.shape[1] != Hin or t.shape[2] != Win or (not sg.bcast and t.shape[0] != N) \
+                    or (sg.bcast and t.shape[0] != 1):
+                raise ValueError('segment shape %s incompatible with %s' % (tuple(t.shape), tuple(ref.shape)))
+        d = self._fwd_desc(segs, N, Hin, Win)
+        out = torch.empty((N, d.Hout, d.Wout, self.cout), dtype=torch.float32, device=ref.device)
+        nat.check(lib.nlt_gconv_fwd(C.byref(d), nat.ptr(self.bias), nat.ACT_CODES[self.act], 0.0, None, 0,
+                                    nat.ptr(out), nat.stream()))
+        y = Act(out, act=self.act, needs_grad=tape is not None)
+        if tape is not None:
+            for sg in segs:
+                if sg.a.needs_grad:
+                    sg.a.n_cons += 1
+            tape.record(lambda: self._backward(segs, y, N, Hin, Win))
+        return y
+
+    def _backward(self, segs, y, N, Hin, Win):
+        lib = nat.lib()
+        dz = y.grad
+        if dz is None:
+            return
+        # weight / bias gradient (same descriptor as forward, G = dz)
+        d = self._fwd_desc(segs, N, Hin, Win)
+        need = lib.nlt_gconv_wgrad_workspace_bytes(C.byref(d))
+        if need < 0:
+            nat.check(-1)
+        ws = _WS.get(need, dz.device)
+        nat.check(lib.nlt_gconv_wgrad(C.byref(d), nat.ptr(dz), nat.ptr(self.gkernel), nat.ptr(self.gbias),
+                                      1 if self.grad_written else 0, nat.ptr(ws), ws.numel() * 4, nat.stream()))
+        self.grad_written = True
+        # input gradients, one adjoint launch per differentiable segment
+        coff = 0
+        for sg in segs:
+            if sg.a.needs_grad:
+                dd = self._dgrad_desc(dz, N, Hin, Win, coff, sg.C)
+
+                def write(out, beta, mask, mask_act, dd=dd):
+                    nat.check(lib.nlt_gconv_fwd(C.byref(dd), None, 0, beta, nat.ptr(mask), mask_act,
+                                                nat.ptr(out), nat.stream()))
+                contribute(sg.a, write)
+            coff += sg.C
+        y.grad = None   # dz is dead: release it
+
+
+def kmean(obs_y, K, tape=None, weights=None):
+    """mean over the K stacked observations (nlt/models/nlt.py:161-164).
+    obs_y: Act [K*B,H,W,C] (k-major).  K == 1 aliases (no kernel, no copy)."""
+    if K == 1 and weights is None:
+        return obs_y
+    lib = nat.lib()
+    t = obs_y.t
+    B = t.shape[0] // K
+    per = t.shape[1] * t.shape[2] * t.shape[3]
+    out = torch.empty((B,) + tuple(t.shape[1:]), dtype=torch.float32, device=t.device)
+    nat.check(lib.nlt_kmean_fwd(nat.ptr(t), nat.ptr(weights), K, B, per, nat.ptr(out), nat.stream()))
+    agg = Act(out, act=None, needs_grad=tape is not None and obs_y.needs_grad)
+    if tape is not None and obs_y.needs_grad:
+        obs_y.n_cons += 1
+
+        def bwd():
+            if agg.grad is None:
+                return
+
+            def write(o, beta, mask, mask_act):
+                nat.check(lib.nlt_kmean_bwd(nat.ptr(agg.grad), nat.ptr(weights), K, B, per, beta, nat.ptr(mask),
+                                            mask_act, nat.ptr(o), nat.stream()))
+            contribute(obs_y, write)
+            agg.grad = None
+        tape.record(bwd)
+    return agg
+
+
+class ParamBucket:
+    """All trainable parameters of a model in ONE contiguous fp32 buffer (and
+    one gradient buffer), so that the data-parallel step is a single
+    all-reduce and a single fused AMSGrad launch (nlt/trainvali.py:279-280)."""
+
+    def __init__(self, layers, device):
+        self.layers = list(layers)
+        n = 0
+        self.slices = []
+        for L in self.layers:
+            assert L.built
+            ks, bs = L.kernel.numel(), L.bias.numel()
+            n_al = (n + 3) // 4 * 4          # keep every kernel 16B aligned
+            self.slices.append((n_al, ks, n_al + ks, bs))
+            n = n_al + ks + bs
+        self.n = (n + 3) // 4 * 4
+        self.flat = torch.zeros(self.n, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(self.n, dtype=torch.float32, device=device)
+        for L, (ko, ks, bo, bs) in zip(self.layers, self.slices):
+            kshape, bshape = L.kernel.shape, L.bias.shape
+            self.flat[ko:ko + ks].copy_(L.kernel.reshape(-1))
+            self.flat[bo:bo + bs].copy_(L.bias.reshape(-1))
+            L.kernel = self.flat[ko:ko + ks].view(kshape)
+            L.bias = self.flat[bo:bo + bs].view(bshape)
+            L.gkernel = self.grad[ko:ko + ks].view(kshape)
+            L.gbias = self.grad[bo:bo + bs].view(bshape)
+
+    def variables(self):
+        out = []
+        for L in self.layers:
+            out += [L.kernel, L.bias]
+        return out
+
+    def gradients(self):
+        out = []
+        for L in self.layers:
+            out += [L.gkernel, L.gbias]
+        return out
+
+    def begin_step(self):
+        for L in self.layers:
+            L.grad_written = False

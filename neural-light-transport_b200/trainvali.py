@@ -1,0 +1,147 @@
+"""Data-parallel training step -- host mirror of nlt/trainvali.py:254-325.
+
+The reference replicates in-graph with tf.distribute.MirroredStrategy; here it
+is one process per GPU (torchrun), the batch sharded along the view x light
+axis, and ONE all-reduce(SUM) over the flat fp32 gradient bucket per step
+(NCCL over NVLink/NVSwitch), followed by one fused AMSGrad launch.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+import nlt_native as nat
+
+
+class Strategy:
+    """Stand-in for tf.distribute.{OneDevice,Mirrored}Strategy
+    (trainvali.py:254-264): rank / world size of the torchrun job."""
+
+    def __init__(self, backend=None):
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+        if self.world > 1 and not dist.is_initialized():
+            if backend is None:
+                backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+            if backend == 'nccl':
+                torch.cuda.set_device(self.local_rank)
+            dist.init_process_group(backend)
+        if torch.cuda.is_available():
+            torch.cuda.set_device(self.local_rank if self.world > 1 else torch.cuda.current_device())
+
+    @property
+    def num_replicas_in_sync(self):
+        return self.world
+
+    def all_reduce_sum_(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t
+
+    def barrier(self):
+        if self.world > 1:
+            dist.barrier()
+
+
+def get_strategy(device='gpu'):
+    if device == 'gpu':
+        return Strategy()
+    if device == 'cpu':
+        # the reference offers OneDeviceStrategy('/cpu:0'); this hot path has
+        # no CPU implementation by design
+        raise NotImplementedError('device=cpu: the B200 hot path has no CPU fallback')
+    raise NotImplementedError(device)
+
+
+class Adam:
+    """tf.keras.optimizers.Adam(learning_rate, amsgrad=True) over the model's
+    flat parameter bucket (trainvali.py:122-127); Keras defaults b1 .9,
+    b2 .999, eps 1e-7."""
+
+    def __init__(self, learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7, amsgrad=False, clipnorm=None):
+        if not amsgrad:
+            raise NotImplementedError('only amsgrad=True is on the accelerated path')
+        if clipnorm is not None:
+            raise NotImplementedError('clipnorm (mgm > 0) is out of parity scope (SURVEY.md 8c)')
+        self.lr, self.b1, self.b2, self.eps = learning_rate, beta_1, beta_2, epsilon
+        self.iterations = 0
+        self.m = self.v = self.vhat = None
+
+    def apply_gradients(self, grads_and_vars, grad_scale=1.0):
+        gv = list(grads_and_vars)
+        g0, v0 = gv[0]
+        flat_g, flat_p = g0._base, v0._base
+        if flat_g is None or flat_p is None or any(g._base is not flat_g or v._base is not flat_p for g, v in gv):
+            raise ValueError('apply_gradients expects views of the model\'s flat parameter/gradient buckets')
+        if self.m is None:
+            self.m, self.v, self.vhat = (torch.zeros_like(flat_p) for _ in range(3))
+        self.iterations += 1
+        nat.check(nat.lib().nlt_amsgrad_step(
+            nat.ptr(flat_p), nat.ptr(flat_g), nat.ptr(self.m), nat.ptr(self.v), nat.ptr(self.vhat),
+            flat_p.numel(), self.iterations, self.lr, self.b1, self.b2, self.eps, grad_scale, nat.stream()))
+
+
+def distributed_train_step(strategy, model, batch, optimizer, global_bs):
+    """trainvali.py:267-290: per-replica train_step, gradient all-reduce,
+    loss SUM.  `batch` is this rank's shard of the global batch."""
+    assert model.trainable_registered, \
+        "Register the trainable layers before using `trainable_variables`"
+
+    def train_step(batch):
+        pred, gt, loss_kwargs, partial_to_vis = model(batch, mode='train')
+        loss_kwargs['keep_batch'] = True  # keep the batch dimension
+        model.set_loss_grad_scale(1.0 / global_bs)
+        per_example_loss = model.compute_loss(pred, gt, **loss_kwargs)
+        weighted_loss = per_example_loss.sum() / global_bs   # tf.nn.compute_average_loss
+        model.backward()
+        strategy.all_reduce_sum_(model.flat_grads)           # ONE collective per step
+        optimizer.apply_gradients(zip(model.gradients, model.trainable_variables))
+        return weighted_loss, partial_to_vis
+
+    weighted_loss, to_vis = train_step(batch)
+    loss = strategy.all_reduce_sum_(weighted_loss.clone())
+    return loss, to_vis
+
+
+def distributed_vali_step(strategy, model, batch, global_bs):
+    """trainvali.py:296-312."""
+    pred, gt, loss_kwargs, to_vis = model(batch, mode='vali')
+    loss_kwargs['keep_batch'] = True
+    per_example_loss = model.compute_loss(pred, gt, **loss_kwargs)
+    weighted_loss = per_example_loss.sum() / global_bs
+    loss = strategy.all_reduce_sum_(weighted_loss.clone())
+    return loss, to_vis
+
+
+def main(argv=None):
+    """Same CLI flags as the reference (--config --debug --device); trains on
+    synthetic batches because the dataset pipeline is out of scope (N3)."""
+    import argparse
+    import models
+    from util import io as ioutil, synth
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--config', default='dragon_specular.ini')
+    ap.add_argument('--debug', action='store_true')
+    ap.add_argument('--device', default='gpu')
+    ap.add_argument('--steps', type=int, default=4)
+    args = ap.parse_args(argv)
+    strategy = get_strategy(args.device)
+    config = ioutil.read_config(args.config)
+    Model = models.get_model_class(config.get('DEFAULT', 'model'))
+    model = Model(config)
+    model.register_trainable()
+    optimizer = Adam(learning_rate=config.getfloat('DEFAULT', 'lr'), amsgrad=True)
+    bs = config.getint('DEFAULT', 'bs')
+    global_bs = bs
+    local_bs = max(bs // strategy.world, 1)
+    for step in range(1 if args.debug else args.steps):
+        batch = synth.make_batch(local_bs, config.getint('DEFAULT', 'uvh'), config.getint('DEFAULT', 'imh'),
+                                 seed=1234 + step * strategy.world + strategy.rank, device='cuda')
+        loss, _ = distributed_train_step(strategy, model, batch, optimizer, global_bs)
+        if strategy.rank == 0:
+            print('step %d loss %.6f' % (step, float(loss)))
+
+
+if __name__ == '__main__':
+    main()
