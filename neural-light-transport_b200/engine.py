@@ -15,6 +15,41 @@ import torch
 import nlt_native as nat
 
 
+class Profiler:
+    """Optional per-call device timing (bench.py's roofline leg): CUDA events
+    on the launching stream around each C-ABI call, keyed by a label, with the
+    call's algorithmic bytes.  Disabled (zero overhead) unless `enabled`."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []     # (label, bytes, start_event, end_event)
+
+    def run(self, label, nbytes, fn):
+        if not self.enabled:
+            return fn()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        self.records.append((label, nbytes, e0, e1))
+        return r
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for label, nbytes, e0, e1 in self.records:
+            a = agg.setdefault(label, [0, 0.0, 0])
+            a[0] += 1
+            a[1] += e0.elapsed_time(e1)
+            a[2] += nbytes
+        self.records = []
+        return {k: {'launches': v[0], 'ms': v[1], 'bytes': v[2]} for k, v in agg.items()}
+
+
+PROF = Profiler()
+
+
 def same_pad(n, k, s):
     """TF 'SAME' (pad_before, pad_after) -- see SURVEY.md section 8c."""
     out = -(-n // s)
@@ -100,6 +135,7 @@ class ConvLayer:
         assert kind in ('conv', 'deconv')
         self.kind, self.k, self.s, self.cout, self.act = kind, k, s, cout, act
         self.cin = None
+        self.name = '%s%dx%d/s%d->%d' % (kind, k, k, s, cout)
         self.kernel = self.bias = self.gkernel = self.gbias = None
         self.grad_written = False
 
@@ -197,8 +233,9 @@ class ConvLayer:
                 raise ValueError('segment shape %s incompatible with %s' % (tuple(t.shape), tuple(ref.shape)))
         d = self._fwd_desc(segs, N, Hin, Win)
         out = torch.empty((N, d.Hout, d.Wout, self.cout), dtype=torch.float32, device=ref.device)
-        nat.check(lib.nlt_gconv_fwd(C.byref(d), nat.ptr(self.bias), nat.ACT_CODES[self.act], 0.0, None, 0,
-                                    nat.ptr(out), nat.stream()))
+        nb = 4 * (sum(sg.a.t.numel() * (2 if sg.sub is not None else 1) for sg in segs) + out.numel())
+        PROF.run('fwd ' + self.name, nb, lambda: nat.check(lib.nlt_gconv_fwd(
+            C.byref(d), nat.ptr(self.bias), nat.ACT_CODES[self.act], 0.0, None, 0, nat.ptr(out), nat.stream())))
         y = Act(out, act=self.act, needs_grad=tape is not None)
         if tape is not None:
             for sg in segs:
@@ -218,8 +255,10 @@ class ConvLayer:
         if need < 0:
             nat.check(-1)
         ws = _WS.get(need, dz.device)
-        nat.check(lib.nlt_gconv_wgrad(C.byref(d), nat.ptr(dz), nat.ptr(self.gkernel), nat.ptr(self.gbias),
-                                      1 if self.grad_written else 0, nat.ptr(ws), ws.numel() * 4, nat.stream()))
+        nb = 4 * (sum(sg.a.t.numel() * (2 if sg.sub is not None else 1) for sg in segs) + dz.numel())
+        PROF.run('wgrad ' + self.name, nb, lambda: nat.check(lib.nlt_gconv_wgrad(
+            C.byref(d), nat.ptr(dz), nat.ptr(self.gkernel), nat.ptr(self.gbias),
+            1 if self.grad_written else 0, nat.ptr(ws), ws.numel() * 4, nat.stream())))
         self.grad_written = True
         # input gradients, one adjoint launch per differentiable segment
         coff = 0
@@ -228,8 +267,9 @@ class ConvLayer:
                 dd = self._dgrad_desc(dz, N, Hin, Win, coff, sg.C)
 
                 def write(out, beta, mask, mask_act, dd=dd):
-                    nat.check(lib.nlt_gconv_fwd(C.byref(dd), None, 0, beta, nat.ptr(mask), mask_act,
-                                                nat.ptr(out), nat.stream()))
+                    nb = 4 * (dz.numel() + out.numel() * (1 + (beta != 0) + (mask is not None)))
+                    PROF.run('dgrad ' + self.name, nb, lambda: nat.check(lib.nlt_gconv_fwd(
+                        C.byref(dd), None, 0, beta, nat.ptr(mask), mask_act, nat.ptr(out), nat.stream())))
                 contribute(sg.a, write)
             coff += sg.C
         y.grad = None   # dz is dead: release it

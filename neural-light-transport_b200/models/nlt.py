@@ -115,6 +115,8 @@ class Model(BaseModel):
         for blk in o.layers:
             convs += blk.convs
         self._bucket = ParamBucket(convs, self.device)
+        for name, c in self.named_convs():   # profiler labels: 'query.1.0 conv2x2/s2 32->16'
+            c.name = '%s %s%dx%d/s%d %d->%d' % (name, c.kind, c.k, c.k, c.s, c.cin, c.cout)
 
     @property
     def trainable_variables(self):

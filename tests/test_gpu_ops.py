@@ -1,0 +1,260 @@
+"""Op-level parity: every CUDA entry point of include/nlt_b200.h against the
+oracle on seeded inputs.  Tolerances are fp32 round-off of sums of K terms
+(the SIMT path is plain fp32 FMA; no tensor-core truncation)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import nlt_oracle as O   # noqa: E402
+
+
+def _mods():
+    import engine
+    import nlt_native as nat
+    return engine, nat
+
+
+def _close(got, want, rtol=2e-5, atol=2e-5):
+    got = got.detach().double().cpu().numpy()
+    want = want.detach().double().cpu().numpy()
+    scale = max(1.0, float(np.abs(want).max()))
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=atol * scale)
+
+
+GEOMS = [
+    # kind, k, s, H, W, seg channels, cout
+    ('conv', 1, 1, 8, 8, [3, 1, 1], 16),
+    ('conv', 1, 1, 16, 8, [4, 32], 3),
+    ('conv', 2, 2, 16, 16, [16, 16], 16),
+    ('conv', 2, 1, 8, 8, [16], 16),
+    ('conv', 2, 2, 8, 8, [32, 32], 64),
+    ('conv', 2, 1, 4, 4, [256], 256),
+    ('conv', 3, 1, 9, 7, [5], 8),
+    ('conv', 3, 2, 8, 8, [8, 4], 32),
+    ('conv', 3, 2, 7, 9, [6], 12),
+    ('conv', 4, 2, 8, 8, [16], 20),
+    ('conv', 2, 2, 2, 2, [512, 512], 128),
+    ('deconv', 2, 2, 4, 4, [64, 64, 64, 64], 128),
+    ('deconv', 2, 1, 8, 8, [128], 128),
+    ('deconv', 2, 2, 8, 8, [8, 32], 4),
+    ('deconv', 2, 1, 16, 16, [4], 4),
+    ('deconv', 3, 2, 5, 6, [16, 3], 8),
+    ('deconv', 3, 1, 6, 5, [7], 5),
+    ('deconv', 4, 2, 4, 4, [16], 16),
+    ('deconv', 1, 2, 4, 4, [8], 8),
+    ('deconv', 2, 2, 1, 1, [1024, 1024], 64),
+]
+
+
+@pytest.mark.parametrize('kind,k,s,H,W,segc,cout', GEOMS)
+@pytest.mark.parametrize('act', ['leakyrelu', None, 'relu'])
+def test_gconv_forward_backward(kind, k, s, H, W, segc, cout, act):
+    engine, nat = _mods()
+    torch.manual_seed(hash((kind, k, s, H, W, cout)) % 1000)
+    N = 3
+    dev = torch.device('cuda')
+    xs = [torch.randn(N, H, W, c) for c in segc]
+    layer = engine.ConvLayer(kind, k, s, cout, act)
+    layer.build(sum(segc), dev, torch.Generator().manual_seed(1))
+    layer.bias.copy_(torch.randn(cout) * 0.1)
+    # oracle (fp64)
+    w64 = layer.kernel.double().cpu().requires_grad_(True)
+    b64 = layer.bias.double().cpu().requires_grad_(True)
+    x64 = [x.double().requires_grad_(True) for x in xs]
+    fn = O.conv2d_same if kind == 'conv' else O.conv2d_transpose_same
+    y64 = fn(torch.cat(x64, dim=3), w64, b64, s)
+    if act:
+        y64 = O.act(y64, act)
+    # product
+    tape = engine.Tape()
+    acts = [engine.Act(x.to(dev).contiguous(), act='leakyrelu', needs_grad=True) for x in xs]
+    y = layer.forward([engine.Seg(a) for a in acts], tape)
+    _close(y.t, y64)
+    gy = torch.randn_like(y64)
+    y64.backward(gy)
+    # dz is what the tape expects in y.grad (mask of y's own activation applied by its producer)
+    dz64 = gy * (torch.where(y64 > 0, 1.0, 0.3) if act == 'leakyrelu' else
+                 torch.where(y64 > 0, 1.0, 0.0) if act == 'relu' else 1.0)
+    y.grad = dz64.float().to(dev).contiguous()
+    tape.backward()
+    _close(layer.gkernel, w64.grad, rtol=1e-4, atol=1e-4)
+    _close(layer.gbias, b64.grad, rtol=1e-4, atol=1e-4)
+    for a, x in zip(acts, x64):
+        # every input Act was declared as a leakyrelu output: its grad carries the mask of a.t
+        want = x.grad * torch.where(x > 0, 1.0, 0.3)
+        _close(a.grad, want, rtol=1e-4, atol=1e-4)
+
+
+def test_gconv_sub_and_bcast_segments():
+    engine, nat = _mods()
+    dev = torch.device('cuda')
+    torch.manual_seed(0)
+    N, H, W = 4, 8, 8
+    a, b = torch.rand(N, H, W, 3), torch.rand(N, H, W, 3)
+    ov = torch.randn(1, H, W, 8)
+    q = torch.randn(N, H, W, 8)
+    L = engine.ConvLayer('conv', 1, 1, 16)
+    L.build(3, dev, torch.Generator().manual_seed(2))
+    y = L.forward([engine.Seg(engine.Act(a.to(dev)), sub=b.to(dev))])
+    _close(y.t, O.conv2d_same((a - b).double(), L.kernel.double().cpu(), L.bias.double().cpu(), 1))
+    L2 = engine.ConvLayer('conv', 2, 2, 16, 'relu')
+    L2.build(16, dev, torch.Generator().manual_seed(3))
+    y = L2.forward([engine.Seg(engine.Act(q.to(dev))), engine.Seg(engine.Act(ov.to(dev)), bcast=True)])
+    x = torch.cat((q, ov.expand(N, -1, -1, -1)), 3).double()
+    _close(y.t, O.act(O.conv2d_same(x, L2.kernel.double().cpu(), L2.bias.double().cpu(), 2), 'relu'))
+
+
+def test_gconv_accumulates_two_consumers_and_elu():
+    """One tensor feeding two convs: the second dgrad accumulates (beta=1) and
+    applies the ELU derivative mask once, as the last contributor."""
+    engine, nat = _mods()
+    dev = torch.device('cuda')
+    torch.manual_seed(4)
+    x = torch.randn(2, 8, 8, 8)
+    L0 = engine.ConvLayer('conv', 1, 1, 16, 'elu'); L0.build(8, dev, torch.Generator().manual_seed(5))
+    L1 = engine.ConvLayer('conv', 2, 2, 8, None); L1.build(16, dev, torch.Generator().manual_seed(6))
+    L2 = engine.ConvLayer('deconv', 2, 1, 4, None); L2.build(16, dev, torch.Generator().manual_seed(7))
+    tape = engine.Tape()
+    h = L0.forward([engine.Seg(engine.Act(x.to(dev)))], tape)
+    y1 = L1.forward([engine.Seg(h)], tape)
+    y2 = L2.forward([engine.Seg(h)], tape)
+    p = {n: getattr(L, n).double().cpu().requires_grad_(True) for L in (L0,) for n in ('kernel', 'bias')}
+    h64 = O.act(O.conv2d_same(x.double(), p['kernel'], p['bias'], 1), 'elu')
+    y164 = O.conv2d_same(h64, L1.kernel.double().cpu(), L1.bias.double().cpu(), 2)
+    y264 = O.conv2d_transpose_same(h64, L2.kernel.double().cpu(), L2.bias.double().cpu(), 1)
+    g1, g2 = torch.randn_like(y164), torch.randn_like(y264)
+    ((y164 * g1).sum() + (y264 * g2).sum()).backward()
+    y1.grad, y2.grad = g1.float().to(dev), g2.float().to(dev)
+    tape.backward()
+    _close(L0.gkernel, p['kernel'].grad, rtol=1e-4, atol=1e-4)
+    _close(L0.gbias, p['bias'].grad, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('K,B', [(2, 3), (6, 2)])
+def test_kmean(K, B):
+    engine, nat = _mods()
+    dev = torch.device('cuda')
+    torch.manual_seed(K)
+    x = torch.randn(K * B, 4, 4, 8)
+    a = engine.Act(x.to(dev), act='leakyrelu', needs_grad=True)
+    tape = engine.Tape()
+    m = engine.kmean(a, K, tape)
+    want = x.view(K, B, 4, 4, 8).mean(0)
+    _close(m.t, want)
+    g = torch.randn(B, 4, 4, 8)
+    m.grad = g.to(dev)
+    tape.backward()
+    want_g = (g / K).repeat(K, 1, 1, 1) * torch.where(x > 0, 1.0, 0.3)
+    _close(a.grad, want_g)
+
+
+@pytest.mark.parametrize('H,ih', [(16, 16), (32, 24)])
+def test_uv2cam_forward_backward(H, ih):
+    engine, nat = _mods()
+    from util import synth
+    dev = torch.device('cuda')
+    lib = nat.lib()
+    B = 2
+    bt = synth.make_batch(B, H, ih, seed=11)
+    base, warp, rgb_c = bt[1], bt[4], bt[6]
+    # add edge / out-of-range sample points
+    warp = warp.clone()
+    warp[0, 0, :6] = torch.tensor([[-0.01, 0.5], [1.0, 0.5], [0.999, 0.999], [0.5, -0.2], [0.0, 0.0], [1.02, 0.3]])
+    net_out = torch.randn(B, H, H, 3)
+    out = {k: torch.empty(B, ih, ih, 3, device=dev) for k in ('pred', 'base', 'fg', 'gt')}
+    pred_uv = torch.empty(B, H, H, 3, device=dev)
+    d = lambda t: t.to(dev).contiguous()
+    nat.check(lib.nlt_uv2cam_fwd(nat.ptr(d(net_out)), nat.ptr(d(base)), nat.ptr(d(warp)), nat.ptr(d(rgb_c)), B, H, H,
+                                 ih, ih, 1, nat.ptr(pred_uv), nat.ptr(out['pred']), nat.ptr(out['base']),
+                                 nat.ptr(out['fg']), nat.ptr(out['gt']), nat.stream()))
+    n64 = net_out.double().requires_grad_(True)
+    pred = O.set_left_top_corner(n64 + base.double(), 0)
+    w = torch.stack((warp[..., 0].double() * H, warp[..., 1].double() * H), 3)
+    # the kernel multiplies warp*uvw in fp32 like the reference; feed the oracle the same fp32 products
+    w = torch.stack((warp[..., 0] * H, warp[..., 1] * H), 3).double()
+    pc = O.resampler(pred, w)
+    fg = O.resampler(O.set_left_top_corner(torch.ones_like(pred), 0), w)
+    bc = O.resampler(O.set_left_top_corner(base.double(), 0), w)
+    _close(pred_uv, pred, atol=1e-6)
+    _close(out['pred'], pc, atol=2e-6)
+    _close(out['base'], bc, atol=2e-6)
+    _close(out['fg'], fg, atol=2e-6)
+    _close(out['gt'], rgb_c.double() * fg, atol=2e-6)
+    g = torch.randn(B, ih, ih, 3)
+    pc.backward(g.double())
+    dn = torch.empty(B, H, H, 3, device=dev)
+    nat.check(lib.nlt_uv2cam_bwd(nat.ptr(d(g)), nat.ptr(d(warp)), B, H, H, ih, ih, nat.ptr(dn), nat.stream()))
+    _close(dn, n64.grad, rtol=1e-4, atol=1e-5)
+    assert float(dn[:, 0, 0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('shape,new', [((8, 8), (16, 16)), ((12, 10), (5, 7))])
+def test_resize(shape, new):
+    engine, nat = _mods()
+    dev = torch.device('cuda')
+    lib = nat.lib()
+    x = torch.randn(2, shape[0], shape[1], 3)
+    y = torch.empty(2, new[0], new[1], 3, device=dev)
+    nat.check(lib.nlt_resize_bilinear_fwd(nat.ptr(x.to(dev)), 2, shape[0], shape[1], 3, new[0], new[1], nat.ptr(y),
+                                          nat.stream()))
+    x64 = x.double().requires_grad_(True)
+    y64 = O.resize_bilinear(x64, *new)
+    _close(y, y64, atol=1e-6)
+    g = torch.randn(2, new[0], new[1], 3)
+    y64.backward(g.double())
+    dx = torch.empty_like(x, device=dev)
+    nat.check(lib.nlt_resize_bilinear_bwd(nat.ptr(g.to(dev)), 2, shape[0], shape[1], 3, new[0], new[1], nat.ptr(dx),
+                                          nat.stream()))
+    _close(dx, x64.grad, atol=1e-5)
+
+
+def test_l2_loss_and_grad():
+    import losses
+    dev = torch.device('cuda')
+    torch.manual_seed(1)
+    pred, gt = torch.rand(3, 20, 24, 3), torch.rand(3, 20, 24, 3)
+    L = losses.L2()
+    L.grad_scale = 0.25
+    got = L(gt.to(dev), pred.to(dev), keep_batch=True)
+    p64 = pred.double().requires_grad_(True)
+    want = O.l2_loss(gt.double(), p64, keep_batch=True)
+    _close(got, want, rtol=1e-5, atol=1e-7)
+    (want.sum() * 0.25).backward()
+    _close(L.d_pred, p64.grad, rtol=1e-5, atol=1e-8)
+    L.grad_scale = None
+    got = L(gt.to(dev), pred.to(dev))
+    _close(got, O.l2_loss(gt.double(), pred.double()), rtol=1e-5, atol=1e-7)
+
+
+def test_amsgrad_kernel():
+    engine, nat = _mods()
+    dev = torch.device('cuda')
+    lib = nat.lib()
+    torch.manual_seed(2)
+    n = 1000
+    p = torch.randn(n); m = torch.zeros(n); v = torch.zeros(n); vh = torch.zeros(n)
+    pg, mg, vg, vhg = (t.clone().to(dev) for t in (p, m, v, vh))
+    p64, m64, v64, vh64 = (t.double() for t in (p, m, v, vh))
+    for t in range(1, 5):
+        g = torch.randn(n) * (0.5 if t != 3 else 0.01)
+        nat.check(lib.nlt_amsgrad_step(nat.ptr(pg), nat.ptr(g.to(dev)), nat.ptr(mg), nat.ptr(vg), nat.ptr(vhg), n, t,
+                                       1e-3, 0.9, 0.999, 1e-7, 1.0, nat.stream()))
+        p64, m64, v64, vh64 = O.amsgrad_step(p64, g.double(), m64, v64, vh64, t, 1e-3)
+    _close(pg, p64, rtol=1e-5, atol=1e-6)
+    _close(vhg, vh64, rtol=1e-5, atol=1e-9)
+
+
+def test_bad_arguments_raise():
+    engine, nat = _mods()
+    lib = nat.lib()
+    d = nat.GConvDesc()
+    rc = lib.nlt_gconv_fwd(C.byref(d), None, 0, 0.0, None, 0, None, None)
+    assert rc == -1 and b'geometry' in lib.nlt_last_error()
+    with pytest.raises(nat.NativeError):
+        nat.ptr(torch.zeros(4))            # CPU tensor: no CPU fallback
+    with pytest.raises(nat.NativeError):
+        nat.ptr(torch.zeros(4, 4, device='cuda').t())
