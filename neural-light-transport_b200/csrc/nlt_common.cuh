@@ -86,6 +86,10 @@ struct GConvK {
   long long wt, wc, wn;
   uint32_t M;  // lattice pixels in this phase = N * ay.nt * ax.nt
   FastDiv div_x, div_yx;
+  // depth-to-space mode (transposed op with k == stride, no padding): ONE pass over
+  // the input lattice with N' = k*k*cout_true GEMM columns (n' = tap*cout_true + n),
+  // each 4-channel group stored at output pixel (t*s + dy, t*s + dx).  Cout == N'.
+  int d2s, d2s_s, cout_true;
 };
 
 __device__ __forceinline__ void decode_pixel(const GConvK& g, uint32_t m, int& n, int& ty, int& tx) {
@@ -97,7 +101,42 @@ __device__ __forceinline__ void decode_pixel(const GConvK& g, uint32_t m, int& n
   tx = (int)(r - y * g.div_x.d);
 }
 
-// build the per-phase kernel descriptors of a public descriptor (host)
-int build_phases(const nlt_gconv_desc* d, GConvK* out, int* nphase);
+// build the per-phase kernel descriptors of a public descriptor (host).
+// allow_d2s: fold a k == stride transposed op into one depth-to-space phase.
+int build_phases(const nlt_gconv_desc* d, GConvK* out, int* nphase, bool allow_d2s = false);
+
+static __host__ __device__ inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// ---- wgrad descriptors shared by the tiled and the warp-stream kernels ------------
+struct WgradK {
+  GConvK g;
+  int GS;        // k-groups (4 channels each) per tap
+  int KG;        // total k-groups incl. the trailing bias group
+  int ld;        // padded Cout (multiple of 4) = workspace row stride
+  int nsplit;
+  uint32_t pix_per_split;
+};
+
+// k-group -> (tap uy,ux ; segment s ; first channel c); s = -1 bias group, -2 padding
+__device__ __forceinline__ void decode_kgroup(const WgradK& w, int kg, int& uy, int& ux, int& s, int& c) {
+  if (kg >= w.KG) { s = -2; uy = ux = c = 0; return; }
+  if (kg == w.KG - 1) { s = -1; uy = ux = c = 0; return; }
+  const int tap = kg / w.GS;
+  int gs = kg - tap * w.GS;
+  uy = tap / w.g.ax.nu; ux = tap - uy * w.g.ax.nu;
+  s = 0;
+  while (s < w.g.nseg - 1 && gs >= (w.g.seg[s].C + 3) / 4) { gs -= (w.g.seg[s].C + 3) / 4; ++s; }
+  c = gs * 4;
+}
+
+// specialised small-channel kernels (nlt_small.cu); return NLT_OK or an error
+bool pw_conv_applicable(const GConvK& k);
+int launch_pw_conv(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
+                   float* out, cudaStream_t st);
+bool wgrad_small_applicable(const GConvK& k);
+size_t wgrad_small_ws_floats(const GConvK& k);
+// fills w (nsplit, pix_per_split, ld, KG, GS) and *KD_pad for the reduce stage
+int launch_wgrad_small(const GConvK& k, const float* G, float* ws, WgradK* w, size_t* KD_pad, cudaStream_t st);
 
 }  // namespace nlt

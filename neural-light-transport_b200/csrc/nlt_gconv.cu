@@ -25,9 +25,8 @@ int set_err(int code, const char* fmt, ...) {
   return code;
 }
 
-static __host__ __device__ inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
-int build_phases(const nlt_gconv_desc* d, GConvK* out, int* nphase) {
+int build_phases(const nlt_gconv_desc* d, GConvK* out, int* nphase, bool allow_d2s) {
   NLT_CHECK_ARG(d != nullptr, "null descriptor");
   NLT_CHECK_ARG(d->N > 0 && d->Hin > 0 && d->Win > 0 && d->Hout > 0 && d->Wout > 0,
                 "bad geometry N=%d in=%dx%d out=%dx%d", d->N, d->Hin, d->Win, d->Hout, d->Wout);
@@ -54,7 +53,16 @@ int build_phases(const nlt_gconv_desc* d, GConvK* out, int* nphase) {
   }
   const int s = d->stride;
   int np = 0;
-  if (!d->transposed) {
+  base.cout_true = d->Cout;
+  const bool d2s = allow_d2s && d->transposed && s > 1 && d->kh == s && d->kw == s && d->pad_t == 0 &&
+                   d->pad_l == 0 && d->Hout == d->Hin * s && d->Wout == d->Win * s && d->Cout % 4 == 0;
+  if (d2s) {
+    GConvK k = base;
+    k.d2s = 1; k.d2s_s = s; k.Cout = s * s * d->Cout;
+    k.ay = AxisMap{0, 1, d->Hin, 1, 0, 0, 0, 0, 1, d->Hin};
+    k.ax = AxisMap{0, 1, d->Win, 1, 0, 0, 0, 0, 1, d->Win};
+    out[np++] = k;
+  } else if (!d->transposed) {
     GConvK k = base;
     k.ay = AxisMap{0, 1, d->Hout, s, 1, -d->pad_t, 0, 1, d->kh, d->Hin};
     k.ax = AxisMap{0, 1, d->Wout, s, 1, -d->pad_l, 0, 1, d->kw, d->Win};
@@ -105,12 +113,15 @@ __device__ __forceinline__ void chunk_advance(const GConvK& g, ChunkIt& it) {
   }
 }
 
-__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 template <int TM, int TN, int RM, int RN, int NTHR>
 __global__ void __launch_bounds__(NTHR)
 gconv_kernel(const GConvK g, const float* __restrict__ bias, const int act, const float beta,
-             const float* __restrict__ mask_y, const int mask_act, float* __restrict__ out) {
+             const float* __restrict__ mask_y, const int mask_act, float* __restrict__ out,
+             const int mtiles, const int ntiles) {
+  // Persistent CTAs: tiles (m-tile, n-tile) are walked with stride gridDim.x, and the
+  // register prefetch of the A/B chunk crosses tile boundaries, so the global loads of
+  // tile t+1 are in flight during the FMAs and the epilogue of tile t.
   constexpr int TNT = TN / RN;          // threads along n
   constexpr int TMT = NTHR / TNT;       // threads along m
   static_assert(TMT * RM == TM, "tile/thread mismatch");
@@ -125,23 +136,26 @@ gconv_kernel(const GConvK g, const float* __restrict__ bias, const int act, cons
 
   const int tid = threadIdx.x;
   const int tn = tid % TNT, tm = tid / TNT;
-  const uint32_t m0 = blockIdx.x * TM;
-  const int n0 = blockIdx.y * TN;
+  const int total_tiles = mtiles * ntiles;
+  int tile = blockIdx.x;
+  if (tile >= total_tiles) return;
 
-  // ---- per-thread loader rows (fixed over the K loop) ----
+  // ---- per-thread loader rows of the tile being LOADED ----
   const int c4 = tid & 3;
   int ln[LA], lby[LA], lbx[LA];
+  auto setup_rows = [&](uint32_t m0) {
 #pragma unroll
-  for (int i = 0; i < LA; ++i) {
-    const uint32_t m = m0 + (tid >> 2) + i * ROWS_PER_PASS;
-    if (m < g.M) {
-      int n, ty, tx;
-      decode_pixel(g, m, n, ty, tx);
-      ln[i] = n; lby[i] = ty * g.ay.it + g.ay.i0; lbx[i] = tx * g.ax.it + g.ax.i0;
-    } else {
-      ln[i] = -1; lby[i] = 0; lbx[i] = 0;
+    for (int i = 0; i < LA; ++i) {
+      const uint32_t m = m0 + (tid >> 2) + i * ROWS_PER_PASS;
+      if (m < g.M) {
+        int n, ty, tx;
+        decode_pixel(g, m, n, ty, tx);
+        ln[i] = n; lby[i] = ty * g.ay.it + g.ay.i0; lbx[i] = tx * g.ax.it + g.ax.i0;
+      } else {
+        ln[i] = -1; lby[i] = 0; lbx[i] = 0;
+      }
     }
-  }
+  };
 
   int nchunk_per_tap = 0;
   for (int s = 0; s < g.nseg; ++s) nchunk_per_tap += (g.seg[s].C + TK - 1) / TK;
@@ -150,7 +164,7 @@ gconv_kernel(const GConvK g, const float* __restrict__ bias, const int act, cons
   float4 ra[LA];
   float rb[LB];
 
-  auto load_chunk = [&](const ChunkIt& it) {
+  auto load_chunk = [&](const ChunkIt& it, const int n0) {
     const Seg sg = g.seg[it.s];
     const int c = it.c0 + c4 * 4;
 #pragma unroll
@@ -178,14 +192,17 @@ gconv_kernel(const GConvK g, const float* __restrict__ bias, const int act, cons
       ra[i] = v;
     }
     const int tap = (g.ay.d0 + g.ay.ds * it.uy) * g.kw + (g.ax.d0 + g.ax.ds * it.ux);
-    const float* wbase = g.w + (long long)tap * g.wt + (long long)(sg.coff + it.c0) * g.wc + (long long)n0 * g.wn;
+    const float* wrow = g.w + (long long)(sg.coff + it.c0) * g.wc;
 #pragma unroll
     for (int i = 0; i < LB; ++i) {
       const int idx = tid + i * NTHR;
-      const int kk = idx / TN, nn = idx % TN;
+      const int kk = idx / TN, nn = n0 + idx % TN;
       float v = 0.f;
-      if (idx < TK * TN && it.c0 + kk < sg.C && n0 + nn < g.Cout)
-        v = __ldg(wbase + (long long)kk * g.wc + (long long)nn * g.wn);
+      if (idx < TK * TN && it.c0 + kk < sg.C && nn < g.Cout) {
+        int t = tap, n = nn;
+        if (g.d2s) { t = nn / g.cout_true; n = nn - t * g.cout_true; }
+        v = __ldg(wrow + (long long)t * g.wt + (long long)kk * g.wc + (long long)n * g.wn);
+      }
       rb[i] = v;
     }
   };
@@ -202,93 +219,120 @@ gconv_kernel(const GConvK g, const float* __restrict__ bias, const int act, cons
     }
   };
 
-  float acc[RM][RN];
-#pragma unroll
-  for (int i = 0; i < RM; ++i)
-#pragma unroll
-    for (int j = 0; j < RN; ++j) acc[i][j] = 0.f;
-
+  const bool vec_out = (g.cout_true % 4 == 0) && aligned16(out) && (mask_y == nullptr || aligned16(mask_y));
+  uint32_t m0 = (uint32_t)(tile / ntiles) * TM;
+  int n0 = (tile % ntiles) * TN;
   ChunkIt it{0, 0, 0, 0};
-  if (nchunks > 0) load_chunk(it);
-  for (int ch = 0; ch < nchunks; ++ch) {
-    const int buf = ch & 1;
-    store_chunk(buf);
-    __syncthreads();
-    if (ch + 1 < nchunks) {
-      chunk_advance(g, it);
-      load_chunk(it);
-    }
-    const float* as = As[buf];
-    const float* bs = Bs[buf];
-#pragma unroll
-    for (int kq = 0; kq < TK / 4; ++kq) {
-      float4 a[RM];
-#pragma unroll
-      for (int i = 0; i < RM; ++i)
-        a[i] = *reinterpret_cast<const float4*>(&as[(tm + i * TMT) * SA + kq * 4]);
-      float b[4][RN];
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-        for (int jg = 0; jg < RN / 4; ++jg) {
-          const float4 t = *reinterpret_cast<const float4*>(&bs[(kq * 4 + kk) * TN + tn * 4 + jg * TNT * 4]);
-          b[kk][jg * 4 + 0] = t.x; b[kk][jg * 4 + 1] = t.y; b[kk][jg * 4 + 2] = t.z; b[kk][jg * 4 + 3] = t.w;
-        }
-#pragma unroll
-      for (int i = 0; i < RM; ++i)
-#pragma unroll
-        for (int j = 0; j < RN; ++j) {
-          acc[i][j] = fmaf(a[i].x, b[0][j], acc[i][j]);
-          acc[i][j] = fmaf(a[i].y, b[1][j], acc[i][j]);
-          acc[i][j] = fmaf(a[i].z, b[2][j], acc[i][j]);
-          acc[i][j] = fmaf(a[i].w, b[3][j], acc[i][j]);
-        }
-    }
-    // the next iteration writes the other buffer; a thread can be at most one
-    // barrier ahead, so buffer `buf` is not overwritten before everyone left it
-  }
+  if (nchunks > 0) { setup_rows(m0); load_chunk(it, n0); }
+  int gch = 0;   // running chunk counter: smem buffer parity continues across tiles
 
-  // ---- epilogue ----
-  const bool vec_out = (g.Cout % 4 == 0) && aligned16(out) && (mask_y == nullptr || aligned16(mask_y));
+  while (true) {
+    float acc[RM][RN];
 #pragma unroll
-  for (int i = 0; i < RM; ++i) {
-    const uint32_t m = m0 + tm + i * TMT;
-    if (m >= g.M) continue;
-    int n, ty, tx;
-    decode_pixel(g, m, n, ty, tx);
-    const int oy = g.ay.o0 + g.ay.os * ty, ox = g.ax.o0 + g.ax.os * tx;
-    const size_t obase = (((size_t)n * g.Hout + oy) * g.Wout + ox) * g.Cout;
+    for (int i = 0; i < RM; ++i)
 #pragma unroll
-    for (int jg = 0; jg < RN / 4; ++jg) {
-      const int nb = n0 + tn * 4 + jg * TNT * 4;
-      if (nb >= g.Cout) continue;
-      float v[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float t = acc[i][jg * 4 + e];
-        if (bias != nullptr && nb + e < g.Cout) t += __ldg(bias + nb + e);
-        v[e] = act_fwd(t, act);
-      }
-      if (vec_out) {
-        float4* op = reinterpret_cast<float4*>(out + obase + nb);
-        if (beta != 0.f) { const float4 o = *op; v[0] += beta * o.x; v[1] += beta * o.y; v[2] += beta * o.z; v[3] += beta * o.w; }
-        if (mask_y != nullptr) {
-          const float4 y = ld4(mask_y + obase + nb);
-          v[0] *= act_bwd_from_y(y.x, mask_act); v[1] *= act_bwd_from_y(y.y, mask_act);
-          v[2] *= act_bwd_from_y(y.z, mask_act); v[3] *= act_bwd_from_y(y.w, mask_act);
-        }
-        *op = make_float4(v[0], v[1], v[2], v[3]);
+      for (int j = 0; j < RN; ++j) acc[i][j] = 0.f;
+
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int buf = gch & 1;
+      ++gch;
+      store_chunk(buf);
+      __syncthreads();
+      if (ch + 1 < nchunks) {
+        chunk_advance(g, it);
+        load_chunk(it, n0);
       } else {
+        const int nt = tile + (int)gridDim.x;   // first chunk of this CTA's next tile
+        if (nt < total_tiles) {
+          setup_rows((uint32_t)(nt / ntiles) * TM);
+          it = ChunkIt{0, 0, 0, 0};
+          load_chunk(it, (nt % ntiles) * TN);
+        }
+      }
+      const float* as = As[buf];
+      const float* bs = Bs[buf];
+#pragma unroll
+      for (int kq = 0; kq < TK / 4; ++kq) {
+        float4 a[RM];
+#pragma unroll
+        for (int i = 0; i < RM; ++i)
+          a[i] = *reinterpret_cast<const float4*>(&as[(tm + i * TMT) * SA + kq * 4]);
+        float b[4][RN];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+          for (int jg = 0; jg < RN / 4; ++jg) {
+            const float4 t = *reinterpret_cast<const float4*>(&bs[(kq * 4 + kk) * TN + tn * 4 + jg * TNT * 4]);
+            b[kk][jg * 4 + 0] = t.x; b[kk][jg * 4 + 1] = t.y; b[kk][jg * 4 + 2] = t.z; b[kk][jg * 4 + 3] = t.w;
+          }
+#pragma unroll
+        for (int i = 0; i < RM; ++i)
+#pragma unroll
+          for (int j = 0; j < RN; ++j) {
+            acc[i][j] = fmaf(a[i].x, b[0][j], acc[i][j]);
+            acc[i][j] = fmaf(a[i].y, b[1][j], acc[i][j]);
+            acc[i][j] = fmaf(a[i].z, b[2][j], acc[i][j]);
+            acc[i][j] = fmaf(a[i].w, b[3][j], acc[i][j]);
+          }
+      }
+      // a thread can be at most one barrier ahead of the slowest one, so the buffer
+      // written two chunks later is never still being read
+    }
+
+    // ---- epilogue of (m0, n0) ----
+#pragma unroll
+    for (int i = 0; i < RM; ++i) {
+      const uint32_t m = m0 + tm + i * TMT;
+      if (m >= g.M) continue;
+      int n, ty, tx;
+      decode_pixel(g, m, n, ty, tx);
+      const int oy0 = g.d2s ? ty * g.d2s_s : g.ay.o0 + g.ay.os * ty;
+      const int ox0 = g.d2s ? tx * g.d2s_s : g.ax.o0 + g.ax.os * tx;
+#pragma unroll
+      for (int jg = 0; jg < RN / 4; ++jg) {
+        const int nb = n0 + tn * 4 + jg * TNT * 4;
+        if (nb >= g.Cout) continue;
+        int cb = nb, oy = oy0, ox = ox0;     // cb: channel inside the destination pixel
+        if (g.d2s) {
+          const int t = nb / g.cout_true;
+          cb = nb - t * g.cout_true;
+          const int dy = t / g.d2s_s;
+          oy += dy; ox += t - dy * g.d2s_s;
+        }
+        const size_t obase = (((size_t)n * g.Hout + oy) * g.Wout + ox) * g.cout_true + cb;
+        float v[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          if (nb + e >= g.Cout) continue;
-          float t = v[e];
-          if (beta != 0.f) t += beta * out[obase + nb + e];
-          if (mask_y != nullptr) t *= act_bwd_from_y(__ldg(mask_y + obase + nb + e), mask_act);
-          out[obase + nb + e] = t;
+          float t = acc[i][jg * 4 + e];
+          if (bias != nullptr && cb + e < g.cout_true) t += __ldg(bias + cb + e);
+          v[e] = act_fwd(t, act);
+        }
+        if (vec_out) {
+          float4* op = reinterpret_cast<float4*>(out + obase);
+          if (beta != 0.f) { const float4 o = *op; v[0] += beta * o.x; v[1] += beta * o.y; v[2] += beta * o.z; v[3] += beta * o.w; }
+          if (mask_y != nullptr) {
+            const float4 y = ld4(mask_y + obase);
+            v[0] *= act_bwd_from_y(y.x, mask_act); v[1] *= act_bwd_from_y(y.y, mask_act);
+            v[2] *= act_bwd_from_y(y.z, mask_act); v[3] *= act_bwd_from_y(y.w, mask_act);
+          }
+          *op = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (cb + e >= g.cout_true) continue;
+            float t = v[e];
+            if (beta != 0.f) t += beta * out[obase + e];
+            if (mask_y != nullptr) t *= act_bwd_from_y(__ldg(mask_y + obase + e), mask_act);
+            out[obase + e] = t;
+          }
         }
       }
     }
+
+    tile += (int)gridDim.x;
+    if (tile >= total_tiles) break;
+    m0 = (uint32_t)(tile / ntiles) * TM;
+    n0 = (tile % ntiles) * TN;
   }
 }
 
@@ -296,8 +340,18 @@ template <int TM, int TN, int RM, int RN>
 static int launch_fwd(const GConvK& k, const float* bias, int act, float beta, const float* mask_y,
                       int mask_act, float* out, cudaStream_t st) {
   constexpr int NTHR = 128;
-  dim3 grid((k.M + TM - 1) / TM, (k.Cout + TN - 1) / TN);
-  gconv_kernel<TM, TN, RM, RN, NTHR><<<grid, NTHR, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
+  static int ctas_per_sm = 0;   // occupancy of this instantiation (benign race: same value)
+  if (ctas_per_sm == 0) {
+    int nb = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gconv_kernel<TM, TN, RM, RN, NTHR>, NTHR, 0);
+    if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
+    ctas_per_sm = nb > 0 ? nb : 1;
+  }
+  const int mtiles = (int)((k.M + TM - 1) / TM), ntiles = (k.Cout + TN - 1) / TN;
+  const long long total = (long long)mtiles * ntiles;
+  const long long cap = 148ll * ctas_per_sm;
+  const int grid = (int)(total < cap ? total : cap);
+  gconv_kernel<TM, TN, RM, RN, NTHR><<<grid, NTHR, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out, mtiles, ntiles);
   NLT_CUDA_LAUNCH_CHECK("gconv_kernel");
   return NLT_OK;
 }
@@ -308,27 +362,6 @@ static int launch_fwd(const GConvK& k, const float* bias, int act, float beta, c
 // trailing bias group whose A value is (1,0,0,0).
 // -----------------------------------------------------------------------------
 constexpr int WTP = 16;  // pixels per smem stage
-
-struct WgradK {
-  GConvK g;
-  int GS;        // k-groups per tap
-  int KG;        // total k-groups incl. bias group
-  int ld;        // padded Cout (multiple of 4) = workspace row stride
-  int nsplit;
-  uint32_t pix_per_split;
-};
-
-__device__ __forceinline__ void decode_kgroup(const WgradK& w, int kg, int& uy, int& ux, int& s, int& c) {
-  // returns s = -1 for the bias group, s = -2 for padding groups
-  if (kg >= w.KG) { s = -2; uy = ux = c = 0; return; }
-  if (kg == w.KG - 1) { s = -1; uy = ux = c = 0; return; }
-  const int tap = kg / w.GS;
-  int gs = kg - tap * w.GS;
-  uy = tap / w.g.ax.nu; ux = tap - uy * w.g.ax.nu;
-  s = 0;
-  while (s < w.g.nseg - 1 && gs >= (w.g.seg[s].C + 3) / 4) { gs -= (w.g.seg[s].C + 3) / 4; ++s; }
-  c = gs * 4;
-}
 
 template <int TKG, int TN, int RK, int RN, int NTHR>
 __global__ void __launch_bounds__(NTHR)
@@ -512,8 +545,16 @@ __global__ void gconv_wgrad_reduce_kernel(const WgradK w, const float* __restric
       dst = dW + (long long)tap * w.g.wt + (long long)(w.g.seg[s].coff + c + e) * w.g.wc + (long long)n * w.g.wn;
     }
     if (dst == nullptr) continue;
-    float sum = 0.f;
-    for (int sp = 0; sp < w.nsplit; ++sp) sum += ws[((size_t)sp * KD_pad + k) * w.ld + n];
+    const float* src = ws + (size_t)k * w.ld + n;
+    const size_t stride = KD_pad * w.ld;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int sp = 0;
+    for (; sp + 4 <= w.nsplit; sp += 4) {
+      s0 += src[(size_t)(sp + 0) * stride]; s1 += src[(size_t)(sp + 1) * stride];
+      s2 += src[(size_t)(sp + 2) * stride]; s3 += src[(size_t)(sp + 3) * stride];
+    }
+    for (; sp < w.nsplit; ++sp) s0 += src[(size_t)sp * stride];
+    const float sum = (s0 + s1) + (s2 + s3);
     *dst = accumulate ? (*dst + sum) : sum;
   }
 }
@@ -545,7 +586,7 @@ static WgradPlan plan_wgrad(const GConvK& k) {
   long long max_split = ((long long)k.M + 63) / 64;
   if (want > max_split) want = max_split;
   if (want < 1) want = 1;
-  if (want > 4096) want = 4096;
+  if (want > 512) want = 512;
   uint32_t pps = (uint32_t)(((long long)k.M + want - 1) / want);
   pps = (pps + WTP - 1) / WTP * WTP;
   p.pix_per_split = pps;
@@ -569,7 +610,7 @@ int nlt_gconv_fwd(const nlt_gconv_desc* d, const float* bias, int act, float bet
                   int mask_act, float* out, void* stream) {
   GConvK ph[16];
   int np = 0;
-  int rc = build_phases(d, ph, &np);
+  int rc = build_phases(d, ph, &np, /*allow_d2s=*/true);
   if (rc != NLT_OK) return rc;
   NLT_CHECK_ARG(out != nullptr, "null output");
   NLT_CHECK_ARG(act >= 0 && act <= 3 && mask_act >= 0 && mask_act <= 3, "bad activation code");
@@ -578,7 +619,8 @@ int nlt_gconv_fwd(const nlt_gconv_desc* d, const float* bias, int act, float bet
   for (int i = 0; i < np; ++i) {
     const GConvK& k = ph[i];
     if (k.M == 0) continue;
-    if (k.Cout > 32) rc = launch_fwd<128, 64, 8, 8>(k, bias, act, beta, mask_y, mask_act, out, st);
+    if (pw_conv_applicable(k)) rc = launch_pw_conv(k, bias, act, beta, mask_y, mask_act, out, st);
+    else if (k.Cout > 32) rc = launch_fwd<128, 64, 8, 8>(k, bias, act, beta, mask_y, mask_act, out, st);
     else if (k.Cout > 16) rc = launch_fwd<128, 32, 8, 4>(k, bias, act, beta, mask_y, mask_act, out, st);
     else if (k.Cout > 8) rc = launch_fwd<256, 16, 8, 4>(k, bias, act, beta, mask_y, mask_act, out, st);
     else if (k.Cout > 4) rc = launch_fwd<256, 8, 4, 4>(k, bias, act, beta, mask_y, mask_act, out, st);
@@ -595,8 +637,8 @@ int64_t nlt_gconv_wgrad_workspace_bytes(const nlt_gconv_desc* d) {
   size_t mx = 0;
   for (int i = 0; i < np; ++i) {
     if (ph[i].M == 0) continue;
-    WgradPlan p = plan_wgrad(ph[i]);
-    if (p.ws_floats > mx) mx = p.ws_floats;
+    size_t need = wgrad_small_applicable(ph[i]) ? wgrad_small_ws_floats(ph[i]) : plan_wgrad(ph[i]).ws_floats;
+    if (need > mx) mx = need;
   }
   return (int64_t)(mx * sizeof(float));
 }
@@ -613,28 +655,35 @@ int nlt_gconv_wgrad(const nlt_gconv_desc* d, const float* G, float* dW, float* d
   for (int i = 0; i < np; ++i) {
     const GConvK& k = ph[i];
     if (k.M == 0) continue;
-    WgradPlan p = plan_wgrad(k);
-    NLT_CHECK_ARG((int64_t)(p.ws_floats * sizeof(float)) <= workspace_bytes, "workspace too small: need %lld have %lld",
-                  (long long)(p.ws_floats * sizeof(float)), (long long)workspace_bytes);
-    WgradK w;
-    w.g = k; w.GS = p.GS; w.KG = p.KG; w.ld = p.ld; w.nsplit = p.nsplit; w.pix_per_split = p.pix_per_split;
-    dim3 grid(p.kd_tiles, p.n_tiles, p.nsplit);
     float* ws = (float*)workspace;
-    switch (p.tn) {
-      case 64: gconv_wgrad_kernel<32, 64, 8, 8, 128><<<grid, 128, 0, st>>>(w, G, ws); break;
-      case 32: gconv_wgrad_kernel<32, 32, 8, 4, 128><<<grid, 128, 0, st>>>(w, G, ws); break;
-      case 16: gconv_wgrad_kernel<32, 16, 4, 4, 128><<<grid, 128, 0, st>>>(w, G, ws); break;
-      case 8: gconv_wgrad_kernel<32, 8, 4, 4, 64><<<grid, 64, 0, st>>>(w, G, ws); break;
-      default: gconv_wgrad_kernel<32, 4, 4, 4, 32><<<grid, 32, 0, st>>>(w, G, ws); break;
+    WgradK w;
+    size_t KD_pad = 0;
+    if (wgrad_small_applicable(k)) {
+      NLT_CHECK_ARG((int64_t)(wgrad_small_ws_floats(k) * sizeof(float)) <= workspace_bytes, "workspace too small");
+      rc = launch_wgrad_small(k, G, ws, &w, &KD_pad, st);
+      if (rc != NLT_OK) return rc;
+    } else {
+      WgradPlan p = plan_wgrad(k);
+      NLT_CHECK_ARG((int64_t)(p.ws_floats * sizeof(float)) <= workspace_bytes, "workspace too small: need %lld have %lld",
+                    (long long)(p.ws_floats * sizeof(float)), (long long)workspace_bytes);
+      w.g = k; w.GS = p.GS; w.KG = p.KG; w.ld = p.ld; w.nsplit = p.nsplit; w.pix_per_split = p.pix_per_split;
+      KD_pad = p.KD_pad;
+      dim3 grid(p.kd_tiles, p.n_tiles, p.nsplit);
+      switch (p.tn) {
+        case 64: gconv_wgrad_kernel<32, 64, 8, 8, 128><<<grid, 128, 0, st>>>(w, G, ws); break;
+        case 32: gconv_wgrad_kernel<32, 32, 8, 4, 128><<<grid, 128, 0, st>>>(w, G, ws); break;
+        case 16: gconv_wgrad_kernel<32, 16, 4, 4, 128><<<grid, 128, 0, st>>>(w, G, ws); break;
+        case 8: gconv_wgrad_kernel<32, 8, 4, 4, 64><<<grid, 64, 0, st>>>(w, G, ws); break;
+        default: gconv_wgrad_kernel<32, 4, 4, 4, 32><<<grid, 32, 0, st>>>(w, G, ws); break;
+      }
+      NLT_CUDA_LAUNCH_CHECK("gconv_wgrad_kernel");
     }
-    NLT_CUDA_LAUNCH_CHECK("gconv_wgrad_kernel");
     // every phase sees a disjoint subset of lattice pixels, so the bias gradient
     // accumulates across phases; taps are disjoint across phases.
     const size_t total = (size_t)w.KG * 4 * k.Cout;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    // dW: each phase owns its taps -> `accumulate` as given; db: first phase as given, later phases add
-    gconv_wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(w, ws, p.KD_pad, dW, db, accumulate,
+    gconv_wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(w, ws, KD_pad, dW, db, accumulate,
                                                       bias_done ? 1 : accumulate);
     NLT_CUDA_LAUNCH_CHECK("gconv_wgrad_reduce_kernel");
     bias_done = true;

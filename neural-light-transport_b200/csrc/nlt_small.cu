@@ -1,0 +1,391 @@
+// Small-channel specialisations for the full-resolution edge of the network
+// (the layers that own ~65 % of the HBM bytes: SURVEY.md 8a).
+//
+//  * pw_conv_kernel      : 1x1 / stride-1 convs and their input gradients with
+//                          <= 64 input and <= 16 output channels (level-0 convs
+//                          5->16 / 3->16, final conv 36->3 and its dgrad).  One
+//                          thread = one pixel x one quad of output channels,
+//                          weights broadcast from shared memory, no tile staging:
+//                          pure streaming, HBM-bound.
+//  * wgrad_small_kernel  : weight/bias gradients whose [K x N] result is small
+//                          (N <= 16).  Each WARP owns a private pixel stream and
+//                          keeps the whole dW tile in registers (k-groups across
+//                          lanes); warps, then CTAs, are reduced in a fixed order
+//                          (deterministic).  Replaces the tiled split-K kernel
+//                          where that one wasted 90 % of its lanes.
+#include "nlt_common.cuh"
+
+namespace nlt {
+
+constexpr int kSMs = 148;
+
+// -----------------------------------------------------------------------------
+// pointwise conv
+// -----------------------------------------------------------------------------
+constexpr int PW_KMAX = 64;
+constexpr int PW_THREADS = 256;
+
+bool pw_conv_applicable(const GConvK& k) {
+  if (k.d2s) return false;
+  if (k.ay.nu != 1 || k.ax.nu != 1) return false;
+  // identity pixel map: input coordinate == lattice coordinate == output coordinate
+  const AxisMap* ax[2] = {&k.ay, &k.ax};
+  for (int i = 0; i < 2; ++i) {
+    const AxisMap& a = *ax[i];
+    if (a.it != 1 || a.i0 + a.iu * 0 != 0 || a.o0 != 0 || a.os != 1) return false;
+  }
+  if (k.ay.nt != k.Hin || k.ax.nt != k.Win || k.Hout != k.Hin || k.Wout != k.Win) return false;
+  int ctot = 0;
+  for (int s = 0; s < k.nseg; ++s) ctot += k.seg[s].C;
+  return ctot <= PW_KMAX && k.Cout <= 16;
+}
+
+template <int NQ, int R>
+__global__ void __launch_bounds__(PW_THREADS)
+pw_conv_kernel(const GConvK g, const float* __restrict__ bias, const int act, const float beta,
+               const float* __restrict__ mask_y, const int mask_act, float* __restrict__ out) {
+  __shared__ float4 Ws[PW_KMAX * NQ];   // [k][quad] : 4 consecutive output channels
+  const int tid = threadIdx.x;
+  const int tap = (g.ay.d0) * g.kw + g.ax.d0;
+  int K = 0;
+  for (int s = 0; s < g.nseg; ++s) K += g.seg[s].C;
+  for (int idx = tid; idx < K * NQ; idx += PW_THREADS) {
+    const int k = idx / NQ, q = idx - k * NQ;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int n = q * 4 + e;
+      v[e] = n < g.Cout ? __ldg(g.w + (long long)tap * g.wt + (long long)k * g.wc + (long long)n * g.wn) : 0.f;
+    }
+    Ws[idx] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  __syncthreads();
+
+  constexpr int PPB = PW_THREADS / NQ;     // pixels per pass
+  const int q = tid % NQ;
+  const uint32_t pbase = (uint32_t)blockIdx.x * (PPB * R) + tid / NQ;
+  const uint32_t hw = g.div_yx.d;
+  float b4[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) b4[e] = (bias != nullptr && q * 4 + e < g.Cout) ? __ldg(bias + q * 4 + e) : 0.f;
+
+  uint32_t p[R];
+  bool ok[R];
+  float acc[R][4];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    p[r] = pbase + r * PPB;
+    ok[r] = p[r] < g.M;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[r][e] = b4[e];
+  }
+
+  int k = 0;
+  for (int s = 0; s < g.nseg; ++s) {
+    const Seg sg = g.seg[s];
+    size_t po[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      uint32_t pp = p[r];
+      if (sg.bcast) pp -= fdiv(pp, g.div_yx) * hw;   // batch-broadcast source: pixel index inside the image
+      po[r] = (size_t)pp * sg.C;
+    }
+    if (sg.vec) {
+      for (int c = 0; c < sg.C; c += 4) {
+        float4 a[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          a[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok[r]) {
+            a[r] = ld4(sg.ptr + po[r] + c);
+            if (sg.sub) { const float4 u = ld4(sg.sub + po[r] + c); a[r].x -= u.x; a[r].y -= u.y; a[r].z -= u.z; a[r].w -= u.w; }
+          }
+        }
+        const float4 w0 = Ws[(k + 0) * NQ + q], w1 = Ws[(k + 1) * NQ + q], w2 = Ws[(k + 2) * NQ + q],
+                     w3 = Ws[(k + 3) * NQ + q];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          acc[r][0] = fmaf(a[r].x, w0.x, acc[r][0]); acc[r][1] = fmaf(a[r].x, w0.y, acc[r][1]);
+          acc[r][2] = fmaf(a[r].x, w0.z, acc[r][2]); acc[r][3] = fmaf(a[r].x, w0.w, acc[r][3]);
+          acc[r][0] = fmaf(a[r].y, w1.x, acc[r][0]); acc[r][1] = fmaf(a[r].y, w1.y, acc[r][1]);
+          acc[r][2] = fmaf(a[r].y, w1.z, acc[r][2]); acc[r][3] = fmaf(a[r].y, w1.w, acc[r][3]);
+          acc[r][0] = fmaf(a[r].z, w2.x, acc[r][0]); acc[r][1] = fmaf(a[r].z, w2.y, acc[r][1]);
+          acc[r][2] = fmaf(a[r].z, w2.z, acc[r][2]); acc[r][3] = fmaf(a[r].z, w2.w, acc[r][3]);
+          acc[r][0] = fmaf(a[r].w, w3.x, acc[r][0]); acc[r][1] = fmaf(a[r].w, w3.y, acc[r][1]);
+          acc[r][2] = fmaf(a[r].w, w3.z, acc[r][2]); acc[r][3] = fmaf(a[r].w, w3.w, acc[r][3]);
+        }
+        k += 4;
+      }
+    } else {
+      for (int c = 0; c < sg.C; ++c) {
+        float a[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          a[r] = 0.f;
+          if (ok[r]) {
+            a[r] = __ldg(sg.ptr + po[r] + c);
+            if (sg.sub) a[r] -= __ldg(sg.sub + po[r] + c);
+          }
+        }
+        const float4 w0 = Ws[k * NQ + q];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          acc[r][0] = fmaf(a[r], w0.x, acc[r][0]); acc[r][1] = fmaf(a[r], w0.y, acc[r][1]);
+          acc[r][2] = fmaf(a[r], w0.z, acc[r][2]); acc[r][3] = fmaf(a[r], w0.w, acc[r][3]);
+        }
+        ++k;
+      }
+    }
+  }
+
+  const bool vec_out = (g.Cout % 4 == 0) && aligned16(out) && (mask_y == nullptr || aligned16(mask_y));
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (!ok[r] || q * 4 >= g.Cout) continue;
+    const size_t ob = (size_t)p[r] * g.Cout + q * 4;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = act_fwd(acc[r][e], act);
+    if (vec_out) {
+      float4* op = reinterpret_cast<float4*>(out + ob);
+      if (beta != 0.f) { const float4 o = *op; v[0] += beta * o.x; v[1] += beta * o.y; v[2] += beta * o.z; v[3] += beta * o.w; }
+      if (mask_y != nullptr) {
+        const float4 y = ld4(mask_y + ob);
+        v[0] *= act_bwd_from_y(y.x, mask_act); v[1] *= act_bwd_from_y(y.y, mask_act);
+        v[2] *= act_bwd_from_y(y.z, mask_act); v[3] *= act_bwd_from_y(y.w, mask_act);
+      }
+      *op = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (q * 4 + e >= g.Cout) continue;
+        float t = v[e];
+        if (beta != 0.f) t += beta * out[ob + e];
+        if (mask_y != nullptr) t *= act_bwd_from_y(__ldg(mask_y + ob + e), mask_act);
+        out[ob + e] = t;
+      }
+    }
+  }
+}
+
+int launch_pw_conv(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
+                   float* out, cudaStream_t st) {
+  constexpr int R = 4;
+  const int nq = (k.Cout + 3) / 4;
+  if (nq <= 1) {
+    const unsigned grid = (k.M + PW_THREADS * R - 1) / (PW_THREADS * R);
+    pw_conv_kernel<1, R><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
+  } else if (nq == 2) {
+    const unsigned grid = (k.M + PW_THREADS / 2 * R - 1) / (PW_THREADS / 2 * R);
+    pw_conv_kernel<2, R><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
+  } else {
+    const unsigned grid = (k.M + PW_THREADS / 4 * R - 1) / (PW_THREADS / 4 * R);
+    pw_conv_kernel<4, R><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
+  }
+  NLT_CUDA_LAUNCH_CHECK("pw_conv_kernel");
+  return NLT_OK;
+}
+
+// -----------------------------------------------------------------------------
+// warp-stream wgrad for small result tiles
+// -----------------------------------------------------------------------------
+constexpr int WS_WARPS = 4;
+constexpr int WS_THREADS = WS_WARPS * 32;
+
+struct WsPlan {
+  int nq, p, kq, GS, KG, nsplit;
+  uint32_t pps;
+  size_t KD_pad;
+  int ld;
+};
+
+static bool ws_plan(const GConvK& k, WsPlan& pl) {
+  if (k.d2s || k.Cout > 16 || k.M == 0) return false;
+  pl.nq = k.Cout <= 4 ? 1 : k.Cout <= 8 ? 2 : 4;
+  pl.kq = 32 / pl.nq;
+  pl.GS = 0;
+  for (int s = 0; s < k.nseg; ++s) pl.GS += (k.seg[s].C + 3) / 4;
+  pl.KG = k.ay.nu * k.ax.nu * pl.GS + 1;
+  const int real = pl.KG - 1;
+  int p = (real + pl.kq - 1) / pl.kq;
+  if (p < 1) p = 1;
+  // instantiated: NQ=4: P in {1,2,4,5}; NQ=2: {1,2}; NQ=1: {1,2}
+  if (pl.nq == 4) { if (p == 3) p = 4; if (p > 5) return false; }
+  else if (p > 2) return false;
+  pl.p = p;
+  pl.ld = pl.nq * 4;
+  pl.KD_pad = (size_t)(p * pl.kq + 1) * 4;
+  long long want = (long long)kSMs * 3;
+  const long long max_split = ((long long)k.M + 255) / 256;
+  if (want > max_split) want = max_split;
+  if (want < 1) want = 1;
+  pl.pps = (uint32_t)(((long long)k.M + want - 1) / want);
+  pl.nsplit = (int)((k.M + pl.pps - 1) / pl.pps);
+  return true;
+}
+
+bool wgrad_small_applicable(const GConvK& k) {
+  WsPlan pl;
+  return ws_plan(k, pl);
+}
+
+size_t wgrad_small_ws_floats(const GConvK& k) {
+  WsPlan pl;
+  if (!ws_plan(k, pl)) return 0;
+  return (size_t)pl.nsplit * pl.KD_pad * pl.ld;
+}
+
+template <int NQ, int P>
+__global__ void __launch_bounds__(WS_THREADS)
+wgrad_small_kernel(const WgradK w, const float* __restrict__ G, float* __restrict__ ws) {
+  constexpr int KQ = 32 / NQ;
+  constexpr int ROWS = (P * KQ + 1) * 4;       // tile rows incl. the bias group
+  constexpr int LD = NQ * 4;
+  __shared__ float tile[ROWS * LD];
+
+  const GConvK& g = w.g;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int kq = lane / NQ, nq = lane % NQ;
+
+  // this lane's k-groups (fixed): kg_j = kq + j*KQ
+  const float* jptr[P];
+  const float* jsub[P];
+  int jC[P], jc[P], jdy[P], jdx[P], jflag[P];   // flag: 0 dead, 1 vec, 2 scalar, |4 bcast
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    int uy, ux, s, c;
+    decode_kgroup(w, kq + j * KQ, uy, ux, s, c);
+    jptr[j] = nullptr; jsub[j] = nullptr; jC[j] = 0; jc[j] = 0; jdy[j] = 0; jdx[j] = 0; jflag[j] = 0;
+    if (s >= 0) {
+      const Seg sg = g.seg[s];
+      jptr[j] = sg.ptr; jsub[j] = sg.sub; jC[j] = sg.C; jc[j] = c;
+      jdy[j] = uy * g.ay.iu + g.ay.i0; jdx[j] = ux * g.ax.iu + g.ax.i0;
+      jflag[j] = (sg.vec ? 1 : 2) | (sg.bcast ? 4 : 0);
+    }
+  }
+  const bool g_vec = (g.Cout % 4 == 0) && aligned16(G);
+
+  float acc[P][4][4];
+  float gsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < P; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+      for (int f = 0; f < 4; ++f) acc[j][e][f] = 0.f;
+
+  const uint32_t p_begin = blockIdx.x * w.pix_per_split;
+  const uint32_t p_end = min(g.M, p_begin + w.pix_per_split);
+
+  auto load_pixel = [&](uint32_t m, float4 (&a)[P], float4& gv) {
+    gv = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < P; ++j) a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m >= p_end) return;
+    int n, ty, tx;
+    decode_pixel(g, m, n, ty, tx);
+    const int oy = g.ay.o0 + g.ay.os * ty, ox = g.ax.o0 + g.ax.os * tx;
+    const size_t goff = (((size_t)n * g.Hout + oy) * g.Wout + ox) * g.Cout + nq * 4;
+    if (nq * 4 < g.Cout) {
+      if (g_vec) {
+        gv = ld4(G + goff);
+      } else {
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (nq * 4 + e < g.Cout) t[e] = __ldg(G + goff + e);
+        gv = make_float4(t[0], t[1], t[2], t[3]);
+      }
+    }
+    const int by = ty * g.ay.it, bx = tx * g.ax.it;
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      if (jflag[j] == 0) continue;
+      const int iy = by + jdy[j], ix = bx + jdx[j];
+      if ((unsigned)iy >= (unsigned)g.Hin || (unsigned)ix >= (unsigned)g.Win) continue;
+      const size_t off = (((size_t)((jflag[j] & 4) ? 0 : n) * g.Hin + iy) * g.Win + ix) * jC[j] + jc[j];
+      if (jflag[j] & 1) {
+        float4 v = ld4(jptr[j] + off);
+        if (jsub[j]) { const float4 u = ld4(jsub[j] + off); v.x -= u.x; v.y -= u.y; v.z -= u.z; v.w -= u.w; }
+        a[j] = v;
+      } else {
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (jc[j] + e < jC[j]) {
+            t[e] = __ldg(jptr[j] + off + e);
+            if (jsub[j]) t[e] -= __ldg(jsub[j] + off + e);
+          }
+        a[j] = make_float4(t[0], t[1], t[2], t[3]);
+      }
+    }
+  };
+  auto fma_pixel = [&](const float4 (&a)[P], const float4& gv) {
+    const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+    for (int f = 0; f < 4; ++f) gsum[f] += gg[f];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const float aa[4] = {a[j].x, a[j].y, a[j].z, a[j].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int f = 0; f < 4; ++f) acc[j][e][f] = fmaf(aa[e], gg[f], acc[j][e][f]);
+    }
+  };
+
+  // two pixels in flight per warp iteration (adjacent warps take adjacent pixels)
+  for (uint32_t m = p_begin + warp; m < p_end; m += 2 * WS_WARPS) {
+    float4 a0[P], a1[P], g0, g1;
+    load_pixel(m, a0, g0);
+    load_pixel(m + WS_WARPS, a1, g1);
+    fma_pixel(a0, g0);
+    fma_pixel(a1, g1);
+  }
+
+  // ---- fixed-order reduction over the CTA's warps, then one partial per CTA ----
+  for (int i = tid; i < ROWS * LD; i += WS_THREADS) tile[i] = 0.f;
+  __syncthreads();
+  const int bias_row = (w.KG - 1) * 4;
+  for (int wi = 0; wi < WS_WARPS; ++wi) {
+    if (warp == wi) {
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        if (jflag[j] == 0) continue;
+        const int kg = kq + j * KQ;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+          for (int f = 0; f < 4; ++f) tile[(kg * 4 + e) * LD + nq * 4 + f] += acc[j][e][f];
+      }
+      if (kq == 0) {
+#pragma unroll
+        for (int f = 0; f < 4; ++f) tile[bias_row * LD + nq * 4 + f] += gsum[f];
+      }
+    }
+    __syncthreads();
+  }
+  float* dst = ws + (size_t)blockIdx.x * ROWS * LD;
+  for (int i = tid; i < ROWS * LD; i += WS_THREADS) dst[i] = tile[i];
+}
+
+int launch_wgrad_small(const GConvK& k, const float* G, float* ws, WgradK* w, size_t* KD_pad, cudaStream_t st) {
+  WsPlan pl;
+  if (!ws_plan(k, pl)) return set_err(NLT_ERR_INVALID, "wgrad_small not applicable");
+  w->g = k; w->GS = pl.GS; w->KG = pl.KG; w->ld = pl.ld; w->nsplit = pl.nsplit; w->pix_per_split = pl.pps;
+  *KD_pad = pl.KD_pad;
+  const unsigned grid = pl.nsplit;
+#define NLT_WS(NQ_, P_) wgrad_small_kernel<NQ_, P_><<<grid, WS_THREADS, 0, st>>>(*w, G, ws)
+  if (pl.nq == 4) {
+    if (pl.p == 1) NLT_WS(4, 1); else if (pl.p == 2) NLT_WS(4, 2); else if (pl.p == 4) NLT_WS(4, 4); else NLT_WS(4, 5);
+  } else if (pl.nq == 2) {
+    if (pl.p == 1) NLT_WS(2, 1); else NLT_WS(2, 2);
+  } else {
+    if (pl.p == 1) NLT_WS(1, 1); else NLT_WS(1, 2);
+  }
+#undef NLT_WS
+  NLT_CUDA_LAUNCH_CHECK("wgrad_small_kernel");
+  return NLT_OK;
+}
+
+}  // namespace nlt

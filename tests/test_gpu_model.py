@@ -45,6 +45,11 @@ def run_pair(over, B=2, seed=1234, c_extra=0, im=None):
     m, cfg = make_model(**over)
     oc = ocfg(cfg)
     bt = synth.make_batch(B, oc['uvh'], im or oc['imh'], seed=seed, c_extra=c_extra)
+    if im and im != oc['imh']:
+        # the dataset resizes rgb_camspc to (imh, imw) but leaves the warp at its native
+        # resolution (nlt/datasets/nlt.py:141-147): "always warp first and then resize"
+        small = synth.make_batch(B, oc['uvh'], oc['imh'], seed=seed + 1)
+        bt = bt[:6] + (small[6],) + bt[7:10] + (small[10],)
     params = O.init_params(oc, c_query=5 + c_extra, c_obs=3, seed=7, dtype=torch.float64)
     m.build(5 + c_extra, 3)
     m.load_params(params)
