@@ -117,15 +117,11 @@ __device__ __forceinline__ void chunk_advance(const GConvK& g, ChunkIt& it) {
 template <int TM, int TN, int RM, int RN, int NTHR>
 __global__ void __launch_bounds__(NTHR)
 gconv_kernel(const GConvK g, const float* __restrict__ bias, const int act, const float beta,
-             const float* __restrict__ mask_y, const int mask_act, float* __restrict__ out,
-             const int mtiles, const int ntiles) {
-  // Persistent CTAs: tiles (m-tile, n-tile) are walked with stride gridDim.x, and the
-  // register prefetch of the A/B chunk crosses tile boundaries, so the global loads of
-  // tile t+1 are in flight during the FMAs and the epilogue of tile t.
+             const float* __restrict__ mask_y, const int mask_act, float* __restrict__ out) {
   constexpr int TNT = TN / RN;          // threads along n
   constexpr int TMT = NTHR / TNT;       // threads along m
   static_assert(TMT * RM == TM, "tile/thread mismatch");
-  static_assert(RN % 4 == 0, "RN must be a multiple of 4");
+  static_assert(RN % 4 == 0 && RM % 2 == 0, "thread tile");
   constexpr int LA = TM * (TK / 4) / NTHR;  // float4 A loads per thread per chunk
   static_assert(LA * NTHR == TM * (TK / 4), "A loader mismatch");
   constexpr int LB = (TK * TN + NTHR - 1) / NTHR;
@@ -136,26 +132,23 @@ gconv_kernel(const GConvK g, const float* __restrict__ bias, const int act, cons
 
   const int tid = threadIdx.x;
   const int tn = tid % TNT, tm = tid / TNT;
-  const int total_tiles = mtiles * ntiles;
-  int tile = blockIdx.x;
-  if (tile >= total_tiles) return;
+  const uint32_t m0 = blockIdx.x * TM;
+  const int n0 = blockIdx.y * TN;
 
-  // ---- per-thread loader rows of the tile being LOADED ----
+  // ---- per-thread loader rows (fixed over the K loop) ----
   const int c4 = tid & 3;
   int ln[LA], lby[LA], lbx[LA];
-  auto setup_rows = [&](uint32_t m0) {
 #pragma unroll
-    for (int i = 0; i < LA; ++i) {
-      const uint32_t m = m0 + (tid >> 2) + i * ROWS_PER_PASS;
-      if (m < g.M) {
-        int n, ty, tx;
-        decode_pixel(g, m, n, ty, tx);
-        ln[i] = n; lby[i] = ty * g.ay.it + g.ay.i0; lbx[i] = tx * g.ax.it + g.ax.i0;
-      } else {
-        ln[i] = -1; lby[i] = 0; lbx[i] = 0;
-      }
+  for (int i = 0; i < LA; ++i) {
+    const uint32_t m = m0 + (tid >> 2) + i * ROWS_PER_PASS;
+    if (m < g.M) {
+      int n, ty, tx;
+      decode_pixel(g, m, n, ty, tx);
+      ln[i] = n; lby[i] = ty * g.ay.it + g.ay.i0; lbx[i] = tx * g.ax.it + g.ax.i0;
+    } else {
+      ln[i] = -1; lby[i] = 0; lbx[i] = 0;
     }
-  };
+  }
 
   int nchunk_per_tap = 0;
   for (int s = 0; s < g.nseg; ++s) nchunk_per_tap += (g.seg[s].C + TK - 1) / TK;
@@ -164,7 +157,7 @@ gconv_kernel(const GConvK g, const float* __restrict__ bias, const int act, cons
   float4 ra[LA];
   float rb[LB];
 
-  auto load_chunk = [&](const ChunkIt& it, const int n0) {
+  auto load_chunk = [&](const ChunkIt& it) {
     const Seg sg = g.seg[it.s];
     const int c = it.c0 + c4 * 4;
 #pragma unroll
@@ -219,79 +212,74 @@ gconv_kernel(const GConvK g, const float* __restrict__ bias, const int act, cons
     }
   };
 
-  const bool vec_out = (g.cout_true % 4 == 0) && aligned16(out) && (mask_y == nullptr || aligned16(mask_y));
-  uint32_t m0 = (uint32_t)(tile / ntiles) * TM;
-  int n0 = (tile % ntiles) * TN;
+  float acc[RM][RN];
+#pragma unroll
+  for (int i = 0; i < RM; ++i)
+#pragma unroll
+    for (int j = 0; j < RN; ++j) acc[i][j] = 0.f;
+
   ChunkIt it{0, 0, 0, 0};
-  if (nchunks > 0) { setup_rows(m0); load_chunk(it, n0); }
-  int gch = 0;   // running chunk counter: smem buffer parity continues across tiles
-
-  while (true) {
-    float acc[RM][RN];
-#pragma unroll
-    for (int i = 0; i < RM; ++i)
-#pragma unroll
-      for (int j = 0; j < RN; ++j) acc[i][j] = 0.f;
-
-    for (int ch = 0; ch < nchunks; ++ch) {
-      const int buf = gch & 1;
-      ++gch;
-      store_chunk(buf);
-      __syncthreads();
-      if (ch + 1 < nchunks) {
-        chunk_advance(g, it);
-        load_chunk(it, n0);
-      } else {
-        const int nt = tile + (int)gridDim.x;   // first chunk of this CTA's next tile
-        if (nt < total_tiles) {
-          setup_rows((uint32_t)(nt / ntiles) * TM);
-          it = ChunkIt{0, 0, 0, 0};
-          load_chunk(it, (nt % ntiles) * TN);
-        }
-      }
-      const float* as = As[buf];
-      const float* bs = Bs[buf];
-#pragma unroll
-      for (int kq = 0; kq < TK / 4; ++kq) {
-        float4 a[RM];
-#pragma unroll
-        for (int i = 0; i < RM; ++i)
-          a[i] = *reinterpret_cast<const float4*>(&as[(tm + i * TMT) * SA + kq * 4]);
-        float b[4][RN];
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-          for (int jg = 0; jg < RN / 4; ++jg) {
-            const float4 t = *reinterpret_cast<const float4*>(&bs[(kq * 4 + kk) * TN + tn * 4 + jg * TNT * 4]);
-            b[kk][jg * 4 + 0] = t.x; b[kk][jg * 4 + 1] = t.y; b[kk][jg * 4 + 2] = t.z; b[kk][jg * 4 + 3] = t.w;
-          }
-#pragma unroll
-        for (int i = 0; i < RM; ++i)
-#pragma unroll
-          for (int j = 0; j < RN; ++j) {
-            acc[i][j] = fmaf(a[i].x, b[0][j], acc[i][j]);
-            acc[i][j] = fmaf(a[i].y, b[1][j], acc[i][j]);
-            acc[i][j] = fmaf(a[i].z, b[2][j], acc[i][j]);
-            acc[i][j] = fmaf(a[i].w, b[3][j], acc[i][j]);
-          }
-      }
-      // a thread can be at most one barrier ahead of the slowest one, so the buffer
-      // written two chunks later is never still being read
+  if (nchunks > 0) load_chunk(it);
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int buf = ch & 1;
+    store_chunk(buf);
+    __syncthreads();
+    if (ch + 1 < nchunks) {
+      chunk_advance(g, it);
+      load_chunk(it);
     }
-
-    // ---- epilogue of (m0, n0) ----
+    const float* as = As[buf];
+    const float* bs = Bs[buf];
 #pragma unroll
-    for (int i = 0; i < RM; ++i) {
-      const uint32_t m = m0 + tm + i * TMT;
-      if (m >= g.M) continue;
-      int n, ty, tx;
-      decode_pixel(g, m, n, ty, tx);
+    for (int kq = 0; kq < TK / 4; ++kq) {
+      float4 a[RM];
+#pragma unroll
+      for (int i = 0; i < RM; ++i)
+        a[i] = *reinterpret_cast<const float4*>(&as[(tm + i * TMT) * SA + kq * 4]);
+      float b[4][RN];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+        for (int jg = 0; jg < RN / 4; ++jg) {
+          const float4 t = *reinterpret_cast<const float4*>(&bs[(kq * 4 + kk) * TN + tn * 4 + jg * TNT * 4]);
+          b[kk][jg * 4 + 0] = t.x; b[kk][jg * 4 + 1] = t.y; b[kk][jg * 4 + 2] = t.z; b[kk][jg * 4 + 3] = t.w;
+        }
+#pragma unroll
+      for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int j = 0; j < RN; ++j) {
+          acc[i][j] = fmaf(a[i].x, b[0][j], acc[i][j]);
+          acc[i][j] = fmaf(a[i].y, b[1][j], acc[i][j]);
+          acc[i][j] = fmaf(a[i].z, b[2][j], acc[i][j]);
+          acc[i][j] = fmaf(a[i].w, b[3][j], acc[i][j]);
+        }
+    }
+    // the next iteration writes the other buffer; a thread can be at most one
+    // barrier ahead, so buffer `buf` is not overwritten before everyone left it
+  }
+
+  // ---- epilogue: two pixel rows at a time; all read-modify-write operands (old
+  // gradient for beta, saved activation for the mask) are loaded as one batch
+  // before the first store so their latencies overlap ----
+  const bool vec_out = (g.cout_true % 4 == 0) && aligned16(out) && (mask_y == nullptr || aligned16(mask_y));
+  constexpr int NG = RN / 4;
+#pragma unroll
+  for (int i0 = 0; i0 < RM; i0 += 2) {
+    size_t ob[2][NG];
+    int cbv[2][NG];
+    bool live[2][NG];
+    float4 oldv[2][NG], yv[2][NG];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const uint32_t m = m0 + tm + (i0 + r) * TMT;
+      int n = 0, ty = 0, tx = 0;
+      const bool mok = m < g.M;
+      if (mok) decode_pixel(g, m, n, ty, tx);
       const int oy0 = g.d2s ? ty * g.d2s_s : g.ay.o0 + g.ay.os * ty;
       const int ox0 = g.d2s ? tx * g.d2s_s : g.ax.o0 + g.ax.os * tx;
 #pragma unroll
-      for (int jg = 0; jg < RN / 4; ++jg) {
+      for (int jg = 0; jg < NG; ++jg) {
         const int nb = n0 + tn * 4 + jg * TNT * 4;
-        if (nb >= g.Cout) continue;
         int cb = nb, oy = oy0, ox = ox0;     // cb: channel inside the destination pixel
         if (g.d2s) {
           const int t = nb / g.cout_true;
@@ -299,40 +287,49 @@ gconv_kernel(const GConvK g, const float* __restrict__ bias, const int act, cons
           const int dy = t / g.d2s_s;
           oy += dy; ox += t - dy * g.d2s_s;
         }
-        const size_t obase = (((size_t)n * g.Hout + oy) * g.Wout + ox) * g.cout_true + cb;
+        live[r][jg] = mok && nb < g.Cout;
+        cbv[r][jg] = cb;
+        ob[r][jg] = (((size_t)n * g.Hout + oy) * g.Wout + ox) * g.cout_true + cb;
+        oldv[r][jg] = make_float4(0.f, 0.f, 0.f, 0.f);
+        yv[r][jg] = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (live[r][jg] && vec_out) {
+          if (beta != 0.f) oldv[r][jg] = *reinterpret_cast<const float4*>(out + ob[r][jg]);
+          if (mask_y != nullptr) yv[r][jg] = ld4(mask_y + ob[r][jg]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int jg = 0; jg < NG; ++jg) {
+        if (!live[r][jg]) continue;
+        const int cb = cbv[r][jg];
         float v[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          float t = acc[i][jg * 4 + e];
+          float t = acc[i0 + r][jg * 4 + e];
           if (bias != nullptr && cb + e < g.cout_true) t += __ldg(bias + cb + e);
           v[e] = act_fwd(t, act);
         }
         if (vec_out) {
-          float4* op = reinterpret_cast<float4*>(out + obase);
-          if (beta != 0.f) { const float4 o = *op; v[0] += beta * o.x; v[1] += beta * o.y; v[2] += beta * o.z; v[3] += beta * o.w; }
+          const float4 o = oldv[r][jg], y = yv[r][jg];
+          v[0] += beta * o.x; v[1] += beta * o.y; v[2] += beta * o.z; v[3] += beta * o.w;
           if (mask_y != nullptr) {
-            const float4 y = ld4(mask_y + obase);
             v[0] *= act_bwd_from_y(y.x, mask_act); v[1] *= act_bwd_from_y(y.y, mask_act);
             v[2] *= act_bwd_from_y(y.z, mask_act); v[3] *= act_bwd_from_y(y.w, mask_act);
           }
-          *op = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(out + ob[r][jg]) = make_float4(v[0], v[1], v[2], v[3]);
         } else {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             if (cb + e >= g.cout_true) continue;
             float t = v[e];
-            if (beta != 0.f) t += beta * out[obase + e];
-            if (mask_y != nullptr) t *= act_bwd_from_y(__ldg(mask_y + obase + e), mask_act);
-            out[obase + e] = t;
+            if (beta != 0.f) t += beta * out[ob[r][jg] + e];
+            if (mask_y != nullptr) t *= act_bwd_from_y(__ldg(mask_y + ob[r][jg] + e), mask_act);
+            out[ob[r][jg] + e] = t;
           }
         }
       }
-    }
-
-    tile += (int)gridDim.x;
-    if (tile >= total_tiles) break;
-    m0 = (uint32_t)(tile / ntiles) * TM;
-    n0 = (tile % ntiles) * TN;
   }
 }
 
@@ -340,18 +337,8 @@ template <int TM, int TN, int RM, int RN>
 static int launch_fwd(const GConvK& k, const float* bias, int act, float beta, const float* mask_y,
                       int mask_act, float* out, cudaStream_t st) {
   constexpr int NTHR = 128;
-  static int ctas_per_sm = 0;   // occupancy of this instantiation (benign race: same value)
-  if (ctas_per_sm == 0) {
-    int nb = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gconv_kernel<TM, TN, RM, RN, NTHR>, NTHR, 0);
-    if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
-    ctas_per_sm = nb > 0 ? nb : 1;
-  }
-  const int mtiles = (int)((k.M + TM - 1) / TM), ntiles = (k.Cout + TN - 1) / TN;
-  const long long total = (long long)mtiles * ntiles;
-  const long long cap = 148ll * ctas_per_sm;
-  const int grid = (int)(total < cap ? total : cap);
-  gconv_kernel<TM, TN, RM, RN, NTHR><<<grid, NTHR, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out, mtiles, ntiles);
+  dim3 grid((k.M + TM - 1) / TM, (k.Cout + TN - 1) / TN);
+  gconv_kernel<TM, TN, RM, RN, NTHR><<<grid, NTHR, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
   NLT_CUDA_LAUNCH_CHECK("gconv_kernel");
   return NLT_OK;
 }

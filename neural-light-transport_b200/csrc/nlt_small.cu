@@ -139,6 +139,17 @@ pw_conv_kernel(const GConvK g, const float* __restrict__ bias, const int act, co
   }
 
   const bool vec_out = (g.Cout % 4 == 0) && aligned16(out) && (mask_y == nullptr || aligned16(mask_y));
+  float4 oldv[R], yv[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {   // batch the read-modify-write operands before the first store
+    oldv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    yv[r] = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (ok[r] && q * 4 < g.Cout && vec_out) {
+      const size_t ob = (size_t)p[r] * g.Cout + q * 4;
+      if (beta != 0.f) oldv[r] = *reinterpret_cast<const float4*>(out + ob);
+      if (mask_y != nullptr) yv[r] = ld4(mask_y + ob);
+    }
+  }
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     if (!ok[r] || q * 4 >= g.Cout) continue;
@@ -147,14 +158,13 @@ pw_conv_kernel(const GConvK g, const float* __restrict__ bias, const int act, co
 #pragma unroll
     for (int e = 0; e < 4; ++e) v[e] = act_fwd(acc[r][e], act);
     if (vec_out) {
-      float4* op = reinterpret_cast<float4*>(out + ob);
-      if (beta != 0.f) { const float4 o = *op; v[0] += beta * o.x; v[1] += beta * o.y; v[2] += beta * o.z; v[3] += beta * o.w; }
+      const float4 o = oldv[r], y = yv[r];
+      v[0] += beta * o.x; v[1] += beta * o.y; v[2] += beta * o.z; v[3] += beta * o.w;
       if (mask_y != nullptr) {
-        const float4 y = ld4(mask_y + ob);
         v[0] *= act_bwd_from_y(y.x, mask_act); v[1] *= act_bwd_from_y(y.y, mask_act);
         v[2] *= act_bwd_from_y(y.z, mask_act); v[3] *= act_bwd_from_y(y.w, mask_act);
       }
-      *op = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(out + ob) = make_float4(v[0], v[1], v[2], v[3]);
     } else {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -215,7 +225,7 @@ static bool ws_plan(const GConvK& k, WsPlan& pl) {
   pl.p = p;
   pl.ld = pl.nq * 4;
   pl.KD_pad = (size_t)(p * pl.kq + 1) * 4;
-  long long want = (long long)kSMs * 3;
+  long long want = (long long)kSMs * (p <= 2 ? 8 : 4);
   const long long max_split = ((long long)k.M + 255) / 256;
   if (want > max_split) want = max_split;
   if (want < 1) want = 1;
@@ -235,7 +245,7 @@ size_t wgrad_small_ws_floats(const GConvK& k) {
   return (size_t)pl.nsplit * pl.KD_pad * pl.ld;
 }
 
-template <int NQ, int P>
+template <int NQ, int P, int U>
 __global__ void __launch_bounds__(WS_THREADS)
 wgrad_small_kernel(const WgradK w, const float* __restrict__ G, float* __restrict__ ws) {
   constexpr int KQ = 32 / NQ;
@@ -334,13 +344,14 @@ wgrad_small_kernel(const WgradK w, const float* __restrict__ G, float* __restric
     }
   };
 
-  // two pixels in flight per warp iteration (adjacent warps take adjacent pixels)
-  for (uint32_t m = p_begin + warp; m < p_end; m += 2 * WS_WARPS) {
-    float4 a0[P], a1[P], g0, g1;
-    load_pixel(m, a0, g0);
-    load_pixel(m + WS_WARPS, a1, g1);
-    fma_pixel(a0, g0);
-    fma_pixel(a1, g1);
+  // U pixels in flight per warp iteration (adjacent warps take adjacent pixels): the
+  // kernel is a pure stream, so memory-level parallelism is what sets its speed
+  for (uint32_t m = p_begin + warp; m < p_end; m += U * WS_WARPS) {
+    float4 a[U][P], gv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) load_pixel(m + u * WS_WARPS, a[u], gv[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) fma_pixel(a[u], gv[u]);
   }
 
   // ---- fixed-order reduction over the CTA's warps, then one partial per CTA ----
@@ -375,7 +386,7 @@ int launch_wgrad_small(const GConvK& k, const float* G, float* ws, WgradK* w, si
   w->g = k; w->GS = pl.GS; w->KG = pl.KG; w->ld = pl.ld; w->nsplit = pl.nsplit; w->pix_per_split = pl.pps;
   *KD_pad = pl.KD_pad;
   const unsigned grid = pl.nsplit;
-#define NLT_WS(NQ_, P_) wgrad_small_kernel<NQ_, P_><<<grid, WS_THREADS, 0, st>>>(*w, G, ws)
+#define NLT_WS(NQ_, P_) wgrad_small_kernel<NQ_, P_, (P_ == 1 ? 8 : P_ == 2 ? 4 : 2)><<<grid, WS_THREADS, 0, st>>>(*w, G, ws)
   if (pl.nq == 4) {
     if (pl.p == 1) NLT_WS(4, 1); else if (pl.p == 2) NLT_WS(4, 2); else if (pl.p == 4) NLT_WS(4, 4); else NLT_WS(4, 5);
   } else if (pl.nq == 2) {
