@@ -80,6 +80,15 @@ uint64_t nlt_launch_count(void);
 int nlt_gconv_fwd(const nlt_gconv_desc* d, const float* bias, int act,
                   float beta, const float* mask_y, int mask_act,
                   float* out, void* stream);
+/* Same op with caller-provided scratch: enables the tcgen05 (3xTF32 split,
+ * fp32 accumulate in TMEM) tensor-core path where the shape allows it (all
+ * sources with C % 32 == 0, Cout % 16 == 0, tileable lattice); the scratch holds
+ * the per-call hi/lo TF32 weight planes.  Falls back to the fp32 kernels
+ * otherwise.  Set NLT_DISABLE_TC=1 in the environment to force the fp32 path. */
+int64_t nlt_gconv_fwd_workspace_bytes(const nlt_gconv_desc* d);
+int nlt_gconv_fwd_ws(const nlt_gconv_desc* d, const float* bias, int act,
+                     float beta, const float* mask_y, int mask_act, float* out,
+                     void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Weight/bias gradient of the op described by d:
  *   dW[tap,c,n] (+)= sum_p A[map(p,tap),c] * G[p,n],   db[n] (+)= sum_p G[p,n]

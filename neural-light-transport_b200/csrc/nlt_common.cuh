@@ -139,4 +139,10 @@ size_t wgrad_small_ws_floats(const GConvK& k);
 // fills w (nsplit, pix_per_split, ld, KG, GS) and *KD_pad for the reduce stage
 int launch_wgrad_small(const GConvK& k, const float* G, float* ws, WgradK* w, size_t* KD_pad, cudaStream_t st);
 
+// tcgen05 tensor-core path (nlt_tc.cu)
+bool tc_applicable(const GConvK& k);
+size_t tc_workspace_bytes(const GConvK& k);
+int launch_tc(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act, float* out,
+              void* workspace, size_t workspace_bytes, cudaStream_t st);
+
 }  // namespace nlt

@@ -10,6 +10,7 @@
 // Bound: for Cout <= 16 these layers are HBM-bound (AI ~ 4-7 FLOP/B); for
 // larger Cout this fp32-FFMA path is FMA-bound and the tcgen05 path
 // (nlt_tc.cu) takes over where the shape allows.
+#include <stdlib.h>
 #include "nlt_common.cuh"
 
 namespace nlt {
@@ -593,8 +594,22 @@ const char* nlt_version(void) { return "nlt_b200 0.1 (sm_100a)"; }
 const char* nlt_last_error(void) { return nlt::g_err; }
 uint64_t nlt_launch_count(void) { return __atomic_load_n(&nlt::g_launches, __ATOMIC_RELAXED); }
 
-int nlt_gconv_fwd(const nlt_gconv_desc* d, const float* bias, int act, float beta, const float* mask_y,
-                  int mask_act, float* out, void* stream) {
+static bool tc_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NLT_DISABLE_TC"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+
+int64_t nlt_gconv_fwd_workspace_bytes(const nlt_gconv_desc* d) {
+  GConvK ph[16];
+  int np = 0;
+  if (build_phases(d, ph, &np, /*allow_d2s=*/true) != NLT_OK) return -1;
+  if (np == 1 && tc_enabled() && tc_applicable(ph[0])) return (int64_t)tc_workspace_bytes(ph[0]);
+  return 0;
+}
+
+int nlt_gconv_fwd_ws(const nlt_gconv_desc* d, const float* bias, int act, float beta, const float* mask_y,
+                     int mask_act, float* out, void* workspace, int64_t workspace_bytes, void* stream) {
   GConvK ph[16];
   int np = 0;
   int rc = build_phases(d, ph, &np, /*allow_d2s=*/true);
@@ -603,6 +618,9 @@ int nlt_gconv_fwd(const nlt_gconv_desc* d, const float* bias, int act, float bet
   NLT_CHECK_ARG(act >= 0 && act <= 3 && mask_act >= 0 && mask_act <= 3, "bad activation code");
   NLT_CHECK_ARG(beta == 0.f || beta == 1.f, "beta must be 0 or 1");
   cudaStream_t st = (cudaStream_t)stream;
+  if (np == 1 && workspace != nullptr && tc_enabled() && ph[0].M > 0 && tc_applicable(ph[0]) &&
+      (int64_t)tc_workspace_bytes(ph[0]) <= workspace_bytes)
+    return launch_tc(ph[0], bias, act, beta, mask_y, mask_act, out, workspace, (size_t)workspace_bytes, st);
   for (int i = 0; i < np; ++i) {
     const GConvK& k = ph[i];
     if (k.M == 0) continue;
@@ -615,6 +633,11 @@ int nlt_gconv_fwd(const nlt_gconv_desc* d, const float* bias, int act, float bet
     if (rc != NLT_OK) return rc;
   }
   return NLT_OK;
+}
+
+int nlt_gconv_fwd(const nlt_gconv_desc* d, const float* bias, int act, float beta, const float* mask_y,
+                  int mask_act, float* out, void* stream) {
+  return nlt_gconv_fwd_ws(d, bias, act, beta, mask_y, mask_act, out, nullptr, 0, stream);
 }
 
 int64_t nlt_gconv_wgrad_workspace_bytes(const nlt_gconv_desc* d) {

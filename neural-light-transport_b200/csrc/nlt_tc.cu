@@ -1,0 +1,582 @@
+// tcgen05 tensor-core path of the generalised convolution (sm_100a only).
+//
+// Implicit GEMM  D[128 pixels x BN] += A[128 pixels x 32 ch] * B[32 ch x BN]  per K-block, where a
+// K-block is (tap, segment, 32-channel chunk).  No im2col: for every tap the A tile is ONE TMA box of the
+// NHWC activation tensor, [TH x TW pixels] x [32 channels], landing in shared memory as 128 rows of 128 B with
+// the 128-byte swizzle -- exactly the K-major operand layout tcgen05.mma consumes.  SAME padding is TMA
+// out-of-bounds zero fill (coordinates may be negative); the k == stride "patch" conv is a 5-D view of the
+// same tensor (c, dx, x/s, dy, n*H/s + y/s) so that no element stride is needed.
+//
+// fp32-class accuracy on TF32 tensor cores: 3xTF32.  Weights are split once per call into hi/lo TF32
+// planes (pack kernel); activations are split in shared memory by four transform warps
+// (hi = rna_tf32(a) in place, lo = rna_tf32(a - hi) in a second buffer) and the MMA warp issues
+// D += Ahi*Bhi + Ahi*Blo + Alo*Bhi with fp32 accumulation in TMEM.
+//
+// Warp roles (320 threads, 1 CTA / SM, persistent over output tiles):
+//   warp 0      TMA producer      (A raw tile + Bhi + Blo per stage, mbarrier complete_tx)
+//   warp 1      MMA issuer        (single thread; tcgen05.commit frees stages / publishes accumulators)
+//   warps 2-5   operand transform (smem -> smem split, fence.proxy.async)
+//   warps 6-9   epilogue          (tcgen05.ld -> bias / activation / beta / derivative mask -> global)
+// Accumulators are double-buffered in TMEM so the epilogue of tile t overlaps the MMAs of tile t+1.
+#include <cuda.h>
+#include "nlt_common.cuh"
+
+namespace nlt {
+
+constexpr int TC_STAGES = 3;
+constexpr int TC_BM = 128;
+constexpr int TC_KB = 32;                       // channels per K-block (128 bytes of fp32)
+constexpr int TC_A_BYTES = TC_BM * TC_KB * 4;   // 16 KB
+constexpr int TC_THREADS = 320;
+constexpr uint32_t TC_SPIN_LIMIT = 1u << 28;    // watchdog: trap instead of hanging the GPU
+
+struct TcParams {
+  // lattice / tiling
+  int N, Hl, Wl;            // lattice size (pixels this kernel enumerates)
+  int TW, TH;               // tile = TH x TW lattice pixels (TW*TH == 128)
+  int tiles_x, tiles_y;     // per image
+  int n_tiles_n;            // column tiles (Cout / BN)
+  int total_tiles;          // N * tiles_y * tiles_x * n_tiles_n
+  // K-blocks
+  int ntap_y, ntap_x;
+  int nseg;
+  int seg_chunks[NLT_MAX_SEG];
+  int kb_total;
+  // TMA coordinate maps: x = tx0*mx + ux*ux_step + x_off (mode A); mode B (patch) uses (ux, tx0, uy, n*Hs + ty0)
+  int mode_patch;           // 1: 5-D patch view
+  int ux_step, x_off, uy_step, y_off;
+  int Hs;                   // mode B: H / s  (rows of the merged n*H/s dimension per image)
+  // output
+  int Hout, Wout, cout_true, Cout;   // Cout = GEMM columns (d2s: s*s*cout_true)
+  int o0y, osy, o0x, osx;            // output pixel = o0 + os * lattice coordinate (non-d2s)
+  int d2s, d2s_s;
+  int act, mask_act;
+  float beta;
+  const float* bias;
+  const float* mask_y;
+  float* out;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > TC_SPIN_LIMIT) { asm volatile("trap;"); }
+  }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], TF32 inputs, fp32 accumulate, M=128
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+// K-major, 128-byte-swizzled operand tile (rows of 128 B, 8-row atoms of 1024 B): sm_100 smem descriptor
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address
+  d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major) = 16 B
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset: 8 rows * 128 B
+  d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight pack: Bhi/Blo [kb][Cout_pad][32] (K-major rows of 128 B), TF32-rounded split
+// ---------------------------------------------------------------------------------------------
+__global__ void tc_pack_weights_kernel(const GConvK g, int kb_total, int chunks_per_tap, int cout_pad,
+                                       float* __restrict__ bhi, float* __restrict__ blo) {
+  const size_t total = (size_t)kb_total * cout_pad * TC_KB;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int kk = (int)(i % TC_KB);
+    const int n = (int)((i / TC_KB) % cout_pad);
+    const int kb = (int)(i / ((size_t)TC_KB * cout_pad));
+    const int tapi = kb / chunks_per_tap;
+    int ch = kb - tapi * chunks_per_tap;
+    int s = 0;
+    while (s < g.nseg - 1 && ch >= g.seg[s].C / TC_KB) { ch -= g.seg[s].C / TC_KB; ++s; }
+    const int c = g.seg[s].coff + ch * TC_KB + kk;
+    const int uy = tapi / g.ax.nu, ux = tapi - uy * g.ax.nu;
+    float v = 0.f;
+    if (n < g.Cout) {
+      int tap = (g.ay.d0 + g.ay.ds * uy) * g.kw + (g.ax.d0 + g.ax.ds * ux), nn = n;
+      if (g.d2s) { tap = n / g.cout_true; nn = n - tap * g.cout_true; }
+      v = __ldg(g.w + (long long)tap * g.wt + (long long)c * g.wc + (long long)nn * g.wn);
+    }
+    const float hi = tf32_rna(v);
+    bhi[i] = hi;
+    blo[i] = tf32_rna(v - hi);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------
+struct TcMaps {
+  CUtensorMap a[NLT_MAX_SEG];
+  CUtensorMap bhi, blo;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+  constexpr int B_BYTES = BN * TC_KB * 4;
+  constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B swizzle
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t bars[3 * TC_STAGES + 4];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_ready = [&](int s) { return bar0 + 8u * (TC_STAGES + s); };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (2 * TC_STAGES + s); };
+  auto bar_accf = [&](int b) { return bar0 + 8u * (3 * TC_STAGES + b); };
+  auto bar_acce = [&](int b) { return bar0 + 8u * (3 * TC_STAGES + 2 + b); };
+  const uint32_t smem_base = smem_u32(smem);
+  auto a_hi = [&](int s) { return smem_base + (uint32_t)s * STAGE_BYTES; };
+  auto a_lo = [&](int s) { return smem_base + (uint32_t)s * STAGE_BYTES + TC_A_BYTES; };
+  auto b_hi = [&](int s) { return smem_base + (uint32_t)s * STAGE_BYTES + 2 * TC_A_BYTES; };
+  auto b_lo = [&](int s) { return smem_base + (uint32_t)s * STAGE_BYTES + 2 * TC_A_BYTES + B_BYTES; };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_ready(s), 128);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_accf(b), 1);
+      mbar_init(bar_acce(b), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                 "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int kb_total = p.kb_total;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles_n;
+        const int mt = tile / p.n_tiles_n;
+        const int n = mt / tiles_per_img;
+        const int r = mt - n * tiles_per_img;
+        const int ty0 = (r / p.tiles_x) * p.TH, tx0 = (r % p.tiles_x) * p.TW;
+        int kb = 0;
+        for (int uy = 0; uy < p.ntap_y; ++uy)
+          for (int ux = 0; ux < p.ntap_x; ++ux)
+            for (int s = 0; s < p.nseg; ++s)
+              for (int ch = 0; ch < p.seg_chunks[s]; ++ch, ++kb) {
+                mbar_wait(bar_empty(stage), phase ^ 1);
+                mbar_expect_tx(bar_full(stage), TC_A_BYTES + 2 * B_BYTES);
+                if (p.mode_patch)
+                  tma_load_5d(a_hi(stage), &maps.a[s], bar_full(stage), ch * TC_KB, ux, tx0, uy, n * p.Hs + ty0);
+                else
+                  tma_load_4d(a_hi(stage), &maps.a[s], bar_full(stage), ch * TC_KB, tx0 + ux * p.ux_step + p.x_off,
+                              ty0 + uy * p.uy_step + p.y_off, n);
+                tma_load_3d(b_hi(stage), &maps.bhi, bar_full(stage), 0, nt * BN, kb);
+                tma_load_3d(b_lo(stage), &maps.blo, bar_full(stage), 0, nt * BN, kb);
+                if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+              }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1;
+        mbar_wait(bar_acce(buf), acc_phase ^ 1);     // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(bar_ready(stage), phase);        // operands split and visible to the async proxy
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < TC_KB / 8; ++k) {
+            const uint64_t ah = umma_desc_sw128(a_hi(stage) + k * 32), al = umma_desc_sw128(a_lo(stage) + k * 32);
+            const uint64_t bh = umma_desc_sw128(b_hi(stage) + k * 32), bl = umma_desc_sw128(b_lo(stage) + k * 32);
+            tc_mma_tf32(d_tmem, al, bh, IDESC, (kb | k) != 0);   // small terms first
+            tc_mma_tf32(d_tmem, ah, bl, IDESC, 1);
+            tc_mma_tf32(d_tmem, ah, bh, IDESC, 1);
+          }
+          tc_commit(bar_empty(stage));               // stage reusable once these MMAs have read it
+          if (kb == kb_total - 1) tc_commit(bar_accf(buf));
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ================= operand transform: fp32 -> (hi, lo) TF32 planes =================
+    const int t = threadIdx.x - 64;   // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < kb_total; ++kb) {
+        mbar_wait(bar_full(stage), phase);
+        float4* ah = reinterpret_cast<float4*>(smem + (size_t)stage * STAGE_BYTES);
+        float4* al = reinterpret_cast<float4*>(smem + (size_t)stage * STAGE_BYTES + TC_A_BYTES);
+#pragma unroll
+        for (int i = 0; i < TC_A_BYTES / 16 / 128; ++i) {
+          const int q = t + i * 128;              // physical 16-byte chunk: elementwise, swizzle-agnostic
+          const float4 v = ah[q];
+          float4 h, l;
+          h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+          l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+          ah[q] = h;
+          al[q] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(bar_ready(stage));
+        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue =================
+    const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32)
+    const int row = quarter * 32 + lane;          // row of the 128-pixel tile
+    const bool vec_ok = aligned16(p.out) && (p.mask_y == nullptr || aligned16(p.mask_y));
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1;
+      const int nt = tile % p.n_tiles_n;
+      const int mt = tile / p.n_tiles_n;
+      const int n = mt / tiles_per_img;
+      const int r = mt - n * tiles_per_img;
+      const int ty = (r / p.tiles_x) * p.TH + row / p.TW, tx = (r % p.tiles_x) * p.TW + row % p.TW;
+      const bool pix_ok = ty < p.Hl && tx < p.Wl;
+      mbar_wait(bar_accf(buf), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t v[16];
+        tc_ld16(taddr + c0, v);
+        if (!pix_ok) continue;
+#pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4) {
+          const int nb = nt * BN + c0 + g4 * 4;       // GEMM column of this quad
+          if (nb >= p.Cout) continue;
+          int cb = nb, oy, ox;
+          if (p.d2s) {
+            const int tap = nb / p.cout_true;
+            cb = nb - tap * p.cout_true;
+            const int dy = tap / p.d2s_s;
+            oy = ty * p.d2s_s + dy; ox = tx * p.d2s_s + (tap - dy * p.d2s_s);
+          } else {
+            oy = p.o0y + p.osy * ty; ox = p.o0x + p.osx * tx;
+          }
+          const size_t ob = (((size_t)n * p.Hout + oy) * p.Wout + ox) * p.cout_true + cb;
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x = __uint_as_float(v[g4 * 4 + e]);
+            if (p.bias != nullptr) x += __ldg(p.bias + cb + e);
+            o[e] = act_fwd(x, p.act);
+          }
+          if (vec_ok) {
+            if (p.beta != 0.f) {
+              const float4 old = *reinterpret_cast<const float4*>(p.out + ob);
+              o[0] += p.beta * old.x; o[1] += p.beta * old.y; o[2] += p.beta * old.z; o[3] += p.beta * old.w;
+            }
+            if (p.mask_y != nullptr) {
+              const float4 y = ld4(p.mask_y + ob);
+              o[0] *= act_bwd_from_y(y.x, p.mask_act); o[1] *= act_bwd_from_y(y.y, p.mask_act);
+              o[2] *= act_bwd_from_y(y.z, p.mask_act); o[3] *= act_bwd_from_y(y.w, p.mask_act);
+            }
+            *reinterpret_cast<float4*>(p.out + ob) = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float x = o[e];
+              if (p.beta != 0.f) x += p.beta * p.out[ob + e];
+              if (p.mask_y != nullptr) x *= act_bwd_from_y(__ldg(p.mask_y + ob + e), p.mask_act);
+              p.out[ob + e] = x;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_acce(buf));
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)sym;
+  }
+  return fn;
+}
+
+struct TcPlan {
+  bool ok;
+  int bn;
+  TcParams p;
+  int chunks_per_tap;
+  int cout_pad;
+  size_t pack_floats;   // per plane
+  size_t smem_bytes;
+};
+
+static int pick_bn(int cout) {
+  if (cout % 128 == 0) return 128;
+  if (cout % 64 == 0) return 64;
+  if (cout % 32 == 0) return 32;
+  if (cout % 16 == 0) return 16;
+  return 0;
+}
+
+// Which single-phase GConvK shapes the tensor path takes (everything else stays on the SIMT kernels).
+static TcPlan tc_plan(const GConvK& k) {
+  TcPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  pl.ok = false;
+  if (k.cout_true % 4 != 0) return pl;
+  pl.bn = pick_bn(k.Cout);
+  if (pl.bn == 0) return pl;
+  int ctot = 0;
+  for (int s = 0; s < k.nseg; ++s) {
+    const Seg& sg = k.seg[s];
+    if (sg.C % TC_KB != 0 || sg.sub != nullptr || sg.bcast || !aligned16(sg.ptr)) return pl;
+    ctot += sg.C;
+  }
+  if (ctot < 64 && k.ay.nu * k.ax.nu * ctot < 64) return pl;      // too little K to pay for the pipeline
+  if (k.ay.nu < 1 || k.ax.nu < 1) return pl;
+  TcParams& p = pl.p;
+  p.N = k.N; p.Hl = k.ay.nt; p.Wl = k.ax.nt;
+  // tile shape
+  if (p.Wl >= TC_BM) {
+    if (p.Wl % TC_BM) return pl;
+    p.TW = TC_BM; p.TH = 1;
+  } else {
+    if (TC_BM % p.Wl) return pl;
+    p.TW = p.Wl; p.TH = TC_BM / p.Wl;
+    if (p.Hl % p.TH) return pl;
+  }
+  p.tiles_x = p.Wl / p.TW; p.tiles_y = p.Hl / p.TH;
+  // coordinate map
+  const bool stride1 = (k.ay.it == 1 && k.ax.it == 1);
+  const bool patch = (!k.d2s && k.ay.it > 1 && k.ay.it == k.ax.it && k.ay.iu == 1 && k.ax.iu == 1 && k.ay.i0 == 0 &&
+                      k.ax.i0 == 0 && k.ay.nu == k.ay.it && k.ax.nu == k.ax.it && k.Hin == k.ay.nt * k.ay.it &&
+                      k.Win == k.ax.nt * k.ax.it);
+  if (!stride1 && !patch) return pl;
+  p.mode_patch = patch ? 1 : 0;
+  p.ux_step = k.ax.iu; p.x_off = k.ax.i0; p.uy_step = k.ay.iu; p.y_off = k.ay.i0;
+  p.Hs = patch ? k.Hin / k.ay.it : 0;
+  if (patch && (k.ay.it > 256 || p.TW > 256)) return pl;
+  p.ntap_y = k.ay.nu; p.ntap_x = k.ax.nu;
+  p.nseg = k.nseg;
+  pl.chunks_per_tap = 0;
+  for (int s = 0; s < k.nseg; ++s) { p.seg_chunks[s] = k.seg[s].C / TC_KB; pl.chunks_per_tap += p.seg_chunks[s]; }
+  p.kb_total = p.ntap_y * p.ntap_x * pl.chunks_per_tap;
+  p.Hout = k.Hout; p.Wout = k.Wout; p.cout_true = k.cout_true; p.Cout = k.Cout;
+  p.o0y = k.ay.o0; p.osy = k.ay.os; p.o0x = k.ax.o0; p.osx = k.ax.os;
+  p.d2s = k.d2s; p.d2s_s = k.d2s_s;
+  p.n_tiles_n = k.Cout / pl.bn;
+  const long long tt = (long long)p.N * p.tiles_x * p.tiles_y * p.n_tiles_n;
+  if (tt > (1ll << 30)) return pl;
+  p.total_tiles = (int)tt;
+  pl.cout_pad = k.Cout;
+  pl.pack_floats = (size_t)p.kb_total * pl.cout_pad * TC_KB;
+  pl.smem_bytes = (size_t)TC_STAGES * (2 * TC_A_BYTES + 2 * (size_t)pl.bn * TC_KB * 4) + 1024;
+  if (get_encode() == nullptr) return pl;
+  pl.ok = true;
+  return pl;
+}
+
+static int encode_maps(const GConvK& k, const TcPlan& pl, const float* bhi, const float* blo, TcMaps* maps) {
+  EncodeTiledFn enc = get_encode();
+  const TcParams& p = pl.p;
+  for (int s = 0; s < k.nseg; ++s) {
+    const Seg& sg = k.seg[s];
+    const cuuint64_t C = sg.C, W = k.Win, H = k.Hin, N = k.N;
+    CUresult r;
+    if (p.mode_patch) {
+      const cuuint64_t st = k.ay.it;
+      cuuint64_t dims[5] = {C, st, W / st, st, N * (H / st)};
+      cuuint64_t strides[4] = {C * 4, st * C * 4, W * C * 4, st * W * C * 4};
+      cuuint32_t box[5] = {(cuuint32_t)TC_KB, 1, (cuuint32_t)p.TW, 1, (cuuint32_t)p.TH};
+      cuuint32_t es[5] = {1, 1, 1, 1, 1};
+      r = enc(&maps->a[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)sg.ptr, dims, strides, box, es,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      cuuint64_t dims[4] = {C, W, H, N};
+      cuuint64_t strides[3] = {C * 4, W * C * 4, H * W * C * 4};
+      cuuint32_t box[4] = {(cuuint32_t)TC_KB, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      r = enc(&maps->a[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)sg.ptr, dims, strides, box, es,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) return set_err(NLT_ERR_CUDA, "cuTensorMapEncodeTiled(A seg %d) failed: %d", s, (int)r);
+  }
+  const float* planes[2] = {bhi, blo};
+  CUtensorMap* bm[2] = {&maps->bhi, &maps->blo};
+  for (int i = 0; i < 2; ++i) {
+    cuuint64_t dims[3] = {(cuuint64_t)TC_KB, (cuuint64_t)pl.cout_pad, (cuuint64_t)p.kb_total};
+    cuuint64_t strides[2] = {(cuuint64_t)TC_KB * 4, (cuuint64_t)TC_KB * 4 * pl.cout_pad};
+    cuuint32_t box[3] = {(cuuint32_t)TC_KB, (cuuint32_t)pl.bn, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(bm[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)planes[i], dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(NLT_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+  }
+  return NLT_OK;
+}
+
+bool tc_applicable(const GConvK& k) { return tc_plan(k).ok; }
+
+size_t tc_workspace_bytes(const GConvK& k) {
+  TcPlan pl = tc_plan(k);
+  return pl.ok ? 2 * pl.pack_floats * sizeof(float) + 256 : 0;
+}
+
+template <int BN>
+static int tc_launch_bn(const TcMaps& maps, const TcPlan& pl, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gconv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)((size_t)TC_STAGES * (2 * TC_A_BYTES + 2 * (size_t)BN * TC_KB * 4) + 1024));
+    if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int grid = pl.p.total_tiles < 148 ? pl.p.total_tiles : 148;
+  tc_gconv_kernel<BN><<<grid, TC_THREADS, pl.smem_bytes, st>>>(maps, pl.p);
+  NLT_CUDA_LAUNCH_CHECK("tc_gconv_kernel");
+  return NLT_OK;
+}
+
+int launch_tc(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act, float* out,
+              void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  TcPlan pl = tc_plan(k);
+  if (!pl.ok) return set_err(NLT_ERR_INVALID, "tensor-core path not applicable");
+  const size_t need = 2 * pl.pack_floats * sizeof(float) + 256;
+  NLT_CHECK_ARG(workspace != nullptr && workspace_bytes >= need, "tc workspace too small: need %zu", need);
+  float* bhi = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  float* blo = bhi + pl.pack_floats;
+  {
+    const size_t total = pl.pack_floats;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    tc_pack_weights_kernel<<<blocks, 256, 0, st>>>(k, pl.p.kb_total, pl.chunks_per_tap, pl.cout_pad, bhi, blo);
+    NLT_CUDA_LAUNCH_CHECK("tc_pack_weights_kernel");
+  }
+  TcMaps maps;
+  int rc = encode_maps(k, pl, bhi, blo, &maps);
+  if (rc != NLT_OK) return rc;
+  pl.p.act = act; pl.p.mask_act = mask_act; pl.p.beta = beta; pl.p.bias = bias; pl.p.mask_y = mask_y; pl.p.out = out;
+  switch (pl.bn) {
+    case 128: return tc_launch_bn<128>(maps, pl, st);
+    case 64: return tc_launch_bn<64>(maps, pl, st);
+    case 32: return tc_launch_bn<32>(maps, pl, st);
+    default: return tc_launch_bn<16>(maps, pl, st);
+  }
+}
+
+}  // namespace nlt

@@ -112,6 +112,22 @@ class Workspace:
 _WS = Workspace()
 
 
+def gconv_fwd(d, bias, act, beta, mask, mask_act, out):
+    """nlt_gconv_fwd_ws with the shared scratch (tensor-core path where the
+    shape allows it, fp32 kernels otherwise)."""
+    lib = nat.lib()
+    need = lib.nlt_gconv_fwd_workspace_bytes(C.byref(d))
+    if need < 0:
+        nat.check(-1)
+    if need > 0:
+        ws = _WS.get(need, out.device)
+        nat.check(lib.nlt_gconv_fwd_ws(C.byref(d), nat.ptr(bias), act, beta, nat.ptr(mask), mask_act, nat.ptr(out),
+                                       nat.ptr(ws), ws.numel() * 4, nat.stream()))
+    else:
+        nat.check(lib.nlt_gconv_fwd_ws(C.byref(d), nat.ptr(bias), act, beta, nat.ptr(mask), mask_act, nat.ptr(out),
+                                       None, 0, nat.stream()))
+
+
 def contribute(target, write_fn):
     """Adds one gradient contribution into target.grad.
     write_fn(out, beta, mask_y, mask_act) launches the producing kernel."""
@@ -234,8 +250,7 @@ class ConvLayer:
         d = self._fwd_desc(segs, N, Hin, Win)
         out = torch.empty((N, d.Hout, d.Wout, self.cout), dtype=torch.float32, device=ref.device)
         nb = 4 * (sum(sg.a.t.numel() * (2 if sg.sub is not None else 1) for sg in segs) + out.numel())
-        PROF.run('fwd ' + self.name, nb, lambda: nat.check(lib.nlt_gconv_fwd(
-            C.byref(d), nat.ptr(self.bias), nat.ACT_CODES[self.act], 0.0, None, 0, nat.ptr(out), nat.stream())))
+        PROF.run('fwd ' + self.name, nb, lambda: gconv_fwd(d, self.bias, nat.ACT_CODES[self.act], 0.0, None, 0, out))
         y = Act(out, act=self.act, needs_grad=tape is not None)
         if tape is not None:
             for sg in segs:
@@ -268,8 +283,7 @@ class ConvLayer:
 
                 def write(out, beta, mask, mask_act, dd=dd):
                     nb = 4 * (dz.numel() + out.numel() * (1 + (beta != 0) + (mask is not None)))
-                    PROF.run('dgrad ' + self.name, nb, lambda: nat.check(lib.nlt_gconv_fwd(
-                        C.byref(dd), None, 0, beta, nat.ptr(mask), mask_act, nat.ptr(out), nat.stream())))
+                    PROF.run('dgrad ' + self.name, nb, lambda: gconv_fwd(dd, None, 0, beta, mask, mask_act, out))
                 contribute(sg.a, write)
             coff += sg.C
         y.grad = None   # dz is dead: release it

@@ -45,6 +45,9 @@ _SIGS = {
     'nlt_launch_count': (C.c_uint64, []),
     'nlt_gconv_fwd': (C.c_int, [C.POINTER(GConvDesc), C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int,
                                 C.c_void_p, C.c_void_p]),
+    'nlt_gconv_fwd_workspace_bytes': (C.c_int64, [C.POINTER(GConvDesc)]),
+    'nlt_gconv_fwd_ws': (C.c_int, [C.POINTER(GConvDesc), C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'nlt_gconv_wgrad_workspace_bytes': (C.c_int64, [C.POINTER(GConvDesc)]),
     'nlt_gconv_wgrad': (C.c_int, [C.POINTER(GConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                   C.c_int64, C.c_void_p]),

@@ -59,6 +59,16 @@ GEOMS = [
     ('deconv', 2, 2, 128, 256, [8, 32], 4),
     ('conv', 2, 1, 256, 256, [16], 16),
     ('deconv', 2, 2, 64, 64, [32, 64], 32),
+    # tensor-core (tcgen05, 3xTF32) eligible shapes: every source C % 32 == 0, Cout % 16 == 0, tileable lattice
+    ('conv', 2, 2, 32, 32, [32, 32], 64),       # patch view (5-D TMA), lattice 16x16 -> tile 8x16
+    ('conv', 2, 1, 16, 16, [64], 64),           # stride-1 taps, SAME pad by TMA OOB fill
+    ('conv', 3, 1, 16, 16, [32], 32),           # negative start coordinates
+    ('deconv', 2, 2, 16, 16, [64, 64], 32),     # depth-to-space, N' = 128
+    ('deconv', 2, 1, 16, 16, [32], 32),
+    ('conv', 2, 2, 64, 256, [32], 128),         # lattice width 128 -> tile 1x128
+    ('conv', 2, 1, 32, 32, [256], 256),         # two column tiles of 128, K = 1024
+    ('deconv', 2, 2, 16, 16, [128, 128], 128),  # N' = 512: four column tiles
+    ('conv', 1, 1, 16, 16, [64, 32], 48),       # BN = 16
 ]
 
 
