@@ -218,8 +218,10 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     l0 = nat.launch_count()
+    tc0 = nat.tc_launch_count()
     ms_step = timed(lambda i: step(resident[i % 2]), args.steps)
     launches = nat.launch_count() - l0
+    tc_launches = nat.tc_launch_count() - tc0
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end-to-end arm: pinned host inputs -> H2D each step -> loss read back ----
@@ -309,7 +311,7 @@ def run_b200(args):
             'config': workload_config(args, world),
             'e2e': {'value': texels_step / (ms_e2e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e,
                     'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4},
-            'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
+            'gpu_launches': launches, 'tcgen05_launches': tc_launches, 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

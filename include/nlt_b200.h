@@ -72,6 +72,8 @@ const char* nlt_version(void);
 const char* nlt_last_error(void);
 /* number of CUDA kernels this library has launched so far in this process (diagnostic counter) */
 uint64_t nlt_launch_count(void);
+/* how many of those were tcgen05 tensor-core kernels (diagnostic counter) */
+uint64_t nlt_tc_launch_count(void);
 
 /* out = act(A*W + bias);   then  out = beta*out_old + out;  then out *= act'(mask_y)
  * Replaces Conv2D / Conv2DTranspose + LeakyReLU (elements.py:26-39, 69-78) and,

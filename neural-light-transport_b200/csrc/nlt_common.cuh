@@ -139,7 +139,12 @@ size_t wgrad_small_ws_floats(const GConvK& k);
 // fills w (nsplit, pix_per_split, ld, KG, GS) and *KD_pad for the reduce stage
 int launch_wgrad_small(const GConvK& k, const float* G, float* ws, WgradK* w, size_t* KD_pad, cudaStream_t st);
 
+bool wgrad_tpp_applicable(const GConvK& k);
+size_t wgrad_tpp_ws_floats(const GConvK& k);
+int launch_wgrad_tpp(const GConvK& k, const float* G, float* ws, WgradK* w, size_t* KD_pad, cudaStream_t st);
+
 // tcgen05 tensor-core path (nlt_tc.cu)
+extern unsigned long long g_tc_launches;
 bool tc_applicable(const GConvK& k);
 size_t tc_workspace_bytes(const GConvK& k);
 int launch_tc(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act, float* out,

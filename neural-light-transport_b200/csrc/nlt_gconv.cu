@@ -593,6 +593,7 @@ extern "C" {
 const char* nlt_version(void) { return "nlt_b200 0.1 (sm_100a)"; }
 const char* nlt_last_error(void) { return nlt::g_err; }
 uint64_t nlt_launch_count(void) { return __atomic_load_n(&nlt::g_launches, __ATOMIC_RELAXED); }
+uint64_t nlt_tc_launch_count(void) { return __atomic_load_n(&nlt::g_tc_launches, __ATOMIC_RELAXED); }
 
 static bool tc_enabled() {
   static int v = -1;
@@ -647,7 +648,8 @@ int64_t nlt_gconv_wgrad_workspace_bytes(const nlt_gconv_desc* d) {
   size_t mx = 0;
   for (int i = 0; i < np; ++i) {
     if (ph[i].M == 0) continue;
-    size_t need = wgrad_small_applicable(ph[i]) ? wgrad_small_ws_floats(ph[i]) : plan_wgrad(ph[i]).ws_floats;
+    size_t need = wgrad_tpp_applicable(ph[i]) ? wgrad_tpp_ws_floats(ph[i])
+                  : wgrad_small_applicable(ph[i]) ? wgrad_small_ws_floats(ph[i]) : plan_wgrad(ph[i]).ws_floats;
     if (need > mx) mx = need;
   }
   return (int64_t)(mx * sizeof(float));
@@ -668,7 +670,11 @@ int nlt_gconv_wgrad(const nlt_gconv_desc* d, const float* G, float* dW, float* d
     float* ws = (float*)workspace;
     WgradK w;
     size_t KD_pad = 0;
-    if (wgrad_small_applicable(k)) {
+    if (wgrad_tpp_applicable(k)) {
+      NLT_CHECK_ARG((int64_t)(wgrad_tpp_ws_floats(k) * sizeof(float)) <= workspace_bytes, "workspace too small");
+      rc = launch_wgrad_tpp(k, G, ws, &w, &KD_pad, st);
+      if (rc != NLT_OK) return rc;
+    } else if (wgrad_small_applicable(k)) {
       NLT_CHECK_ARG((int64_t)(wgrad_small_ws_floats(k) * sizeof(float)) <= workspace_bytes, "workspace too small");
       rc = launch_wgrad_small(k, G, ws, &w, &KD_pad, st);
       if (rc != NLT_OK) return rc;

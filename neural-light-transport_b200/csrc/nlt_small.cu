@@ -380,6 +380,228 @@ wgrad_small_kernel(const WgradK w, const float* __restrict__ G, float* __restric
   for (int i = tid; i < ROWS * LD; i += WS_THREADS) dst[i] = tile[i];
 }
 
+// -----------------------------------------------------------------------------
+// thread-per-pixel wgrad for tiny results (K*N <= ~128: level-0 convs, final
+// conv, the 4->4 full-resolution deconv).  Every THREAD owns a pixel stream and
+// the complete dW tile in registers, so per pixel it costs only the loads and
+// the K*N FMAs (no per-pixel work replicated across a warp); warp shuffles,
+// then a fixed-order smem pass, reduce the tile (deterministic).
+// -----------------------------------------------------------------------------
+constexpr int TPP_MAX_LOADS = 12;
+constexpr int TPP_THREADS = 128;
+
+struct TppLoad {
+  const float* ptr;
+  const float* sub;
+  int C, c, dy, dx, row, bcast;
+};
+struct TppK {
+  GConvK g;
+  TppLoad ld[TPP_MAX_LOADS];
+  int nl;          // loads per pixel
+  int rows;        // workspace rows (KG * 4 incl. the bias group)
+  int ldw;         // workspace row stride (padded Cout)
+  int bias_row;
+};
+
+template <int NL, int VEC, int N>
+__global__ void __launch_bounds__(TPP_THREADS)
+wgrad_tpp_kernel(const TppK t, const float* __restrict__ G, float* __restrict__ ws) {
+  constexpr int R = NL * VEC;
+  constexpr int NW = TPP_THREADS / 32;
+  __shared__ float red[NW][R * N + N];
+  const GConvK& g = t.g;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float acc[R][N];
+  float gsum[N];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int n = 0; n < N; ++n) acc[r][n] = 0.f;
+#pragma unroll
+  for (int n = 0; n < N; ++n) gsum[n] = 0.f;
+  const bool g_vec = (N % 4 == 0) && (g.Cout == N) && aligned16(G);
+
+  for (uint32_t m = blockIdx.x * TPP_THREADS + tid; m < g.M; m += gridDim.x * TPP_THREADS) {
+    int n, ty, tx;
+    decode_pixel(g, m, n, ty, tx);
+    const int oy = g.ay.o0 + g.ay.os * ty, ox = g.ax.o0 + g.ax.os * tx;
+    const size_t goff = (((size_t)n * g.Hout + oy) * g.Wout + ox) * g.Cout;
+    float gv[N];
+    if (g_vec) {
+#pragma unroll
+      for (int q = 0; q < N / 4; ++q) {
+        const float4 v = ld4(G + goff + q * 4);
+        gv[q * 4 + 0] = v.x; gv[q * 4 + 1] = v.y; gv[q * 4 + 2] = v.z; gv[q * 4 + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < N; ++e) gv[e] = e < g.Cout ? __ldg(G + goff + e) : 0.f;
+    }
+    float a[R];
+    const int by = ty * g.ay.it, bx = tx * g.ax.it;
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      const TppLoad L = t.ld[l];
+      const int iy = by + L.dy, ix = bx + L.dx;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) a[l * VEC + e] = 0.f;
+      if ((unsigned)iy < (unsigned)g.Hin && (unsigned)ix < (unsigned)g.Win) {
+        const size_t off = (((size_t)(L.bcast ? 0 : n) * g.Hin + iy) * g.Win + ix) * L.C + L.c;
+        if (VEC == 4) {
+          float4 v = ld4(L.ptr + off);
+          if (L.sub) { const float4 u = ld4(L.sub + off); v.x -= u.x; v.y -= u.y; v.z -= u.z; v.w -= u.w; }
+          a[l * VEC + 0] = v.x; a[l * VEC + (VEC > 1 ? 1 : 0)] = VEC > 1 ? v.y : v.x;
+          a[l * VEC + (VEC > 2 ? 2 : 0)] = VEC > 2 ? v.z : v.x; a[l * VEC + (VEC > 3 ? 3 : 0)] = VEC > 3 ? v.w : v.x;
+        } else {
+          float v = __ldg(L.ptr + off);
+          if (L.sub) v -= __ldg(L.sub + off);
+          a[l * VEC] = v;
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < N; ++e) gsum[e] += gv[e];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int e = 0; e < N; ++e) acc[r][e] = fmaf(a[r], gv[e], acc[r][e]);
+  }
+
+  // warp reduction (fixed butterfly order), then warps in fixed order
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int e = 0; e < N; ++e) {
+      float v = acc[r][e];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[warp][r * N + e] = v;
+    }
+#pragma unroll
+  for (int e = 0; e < N; ++e) {
+    float v = gsum[e];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][R * N + e] = v;
+  }
+  __syncthreads();
+  float* dst = ws + (size_t)blockIdx.x * t.rows * t.ldw;
+  for (int i = tid; i < t.rows * t.ldw; i += TPP_THREADS) dst[i] = 0.f;
+  __syncthreads();
+  for (int i = tid; i < R * N + N; i += TPP_THREADS) {
+    float v = 0.f;
+#pragma unroll
+    for (int wi = 0; wi < NW; ++wi) v += red[wi][i];
+    int row, col;
+    if (i < R * N) {
+      const int r = i / N;
+      col = i - r * N;
+      row = t.ld[r / VEC].row + (r % VEC);
+    } else {
+      row = t.bias_row; col = i - R * N;
+    }
+    if (col < t.ldw) dst[(size_t)row * t.ldw + col] = v;
+  }
+}
+
+struct TppPlan {
+  bool ok;
+  int nl, vec, n;
+  int GS, KG, nsplit;
+  TppK k;
+};
+
+static TppPlan tpp_plan(const GConvK& k) {
+  TppPlan pl;
+  pl.ok = false;
+  if (k.d2s || k.M == 0 || k.Cout > 16) return pl;
+  bool all_vec = true, none_vec = true;
+  for (int s = 0; s < k.nseg; ++s) { if (k.seg[s].vec) none_vec = false; else all_vec = false; }
+  if (!all_vec && !none_vec) return pl;
+  pl.vec = all_vec ? 4 : 1;
+  pl.n = k.Cout <= 3 ? 3 : k.Cout <= 4 ? 4 : k.Cout == 16 ? 16 : 0;
+  if (pl.n == 0) return pl;
+  pl.GS = 0;
+  for (int s = 0; s < k.nseg; ++s) pl.GS += (k.seg[s].C + 3) / 4;
+  const int taps = k.ay.nu * k.ax.nu;
+  pl.KG = taps * pl.GS + 1;
+  memset(&pl.k, 0, sizeof(pl.k));
+  pl.k.g = k;
+  int nl = 0;
+  for (int uy = 0; uy < k.ay.nu; ++uy)
+    for (int ux = 0; ux < k.ax.nu; ++ux) {
+      int gs = 0;
+      for (int s = 0; s < k.nseg; ++s) {
+        const Seg& sg = k.seg[s];
+        const int step = pl.vec;
+        for (int c = 0; c < sg.C; c += step) {
+          if (nl >= TPP_MAX_LOADS) return pl;
+          TppLoad& L = pl.k.ld[nl++];
+          L.ptr = sg.ptr; L.sub = sg.sub; L.C = sg.C; L.c = c; L.bcast = sg.bcast;
+          L.dy = uy * k.ay.iu + k.ay.i0; L.dx = ux * k.ax.iu + k.ax.i0;
+          L.row = ((uy * k.ax.nu + ux) * pl.GS + gs + c / 4) * 4 + (c % 4);
+        }
+        gs += (sg.C + 3) / 4;
+      }
+    }
+  pl.nl = nl;
+  if (nl * pl.vec * pl.n > 128) return pl;
+  // instantiated (NL, VEC, N): scalar sources into 16 channels (level-0 convs) and
+  // vector sources into <= 4 channels (final conv, 4->4 deconv)
+  const bool inst = (pl.vec == 1 && pl.n == 16 && nl >= 1 && nl <= 8) ||
+                    (pl.vec == 4 && pl.n == 3 && (nl == 9 || nl <= 4)) ||
+                    (pl.vec == 4 && pl.n == 4 && nl >= 1 && nl <= 4);
+  if (!inst) return pl;
+  pl.k.nl = nl;
+  pl.k.rows = pl.KG * 4;
+  pl.k.ldw = (k.Cout + 3) / 4 * 4;
+  pl.k.bias_row = (pl.KG - 1) * 4;
+  long long want = (long long)kSMs * 8;
+  const long long max_split = ((long long)k.M + TPP_THREADS * 4 - 1) / (TPP_THREADS * 4);
+  if (want > max_split) want = max_split;
+  if (want < 1) want = 1;
+  pl.nsplit = (int)want;
+  pl.ok = true;
+  return pl;
+}
+
+bool wgrad_tpp_applicable(const GConvK& k) { return tpp_plan(k).ok; }
+
+size_t wgrad_tpp_ws_floats(const GConvK& k) {
+  TppPlan pl = tpp_plan(k);
+  return pl.ok ? (size_t)pl.nsplit * pl.k.rows * pl.k.ldw : 0;
+}
+
+int launch_wgrad_tpp(const GConvK& k, const float* G, float* ws, WgradK* w, size_t* KD_pad, cudaStream_t st) {
+  TppPlan pl = tpp_plan(k);
+  if (!pl.ok) return set_err(NLT_ERR_INVALID, "wgrad_tpp not applicable");
+  w->g = k; w->GS = pl.GS; w->KG = pl.KG; w->ld = pl.k.ldw; w->nsplit = pl.nsplit; w->pix_per_split = 0;
+  *KD_pad = (size_t)pl.k.rows;
+  const unsigned grid = pl.nsplit;
+#define NLT_TPP(NL_, V_, N_) wgrad_tpp_kernel<NL_, V_, N_><<<grid, TPP_THREADS, 0, st>>>(pl.k, G, ws)
+  if (pl.vec == 1) {
+    switch (pl.nl) {
+      case 1: NLT_TPP(1, 1, 16); break; case 2: NLT_TPP(2, 1, 16); break; case 3: NLT_TPP(3, 1, 16); break;
+      case 4: NLT_TPP(4, 1, 16); break; case 5: NLT_TPP(5, 1, 16); break; case 6: NLT_TPP(6, 1, 16); break;
+      case 7: NLT_TPP(7, 1, 16); break; default: NLT_TPP(8, 1, 16); break;
+    }
+  } else if (pl.n == 3) {
+    switch (pl.nl) {
+      case 1: NLT_TPP(1, 4, 3); break; case 2: NLT_TPP(2, 4, 3); break; case 3: NLT_TPP(3, 4, 3); break;
+      case 4: NLT_TPP(4, 4, 3); break; default: NLT_TPP(9, 4, 3); break;
+    }
+  } else {
+    switch (pl.nl) {
+      case 1: NLT_TPP(1, 4, 4); break; case 2: NLT_TPP(2, 4, 4); break; case 3: NLT_TPP(3, 4, 4); break;
+      default: NLT_TPP(4, 4, 4); break;
+    }
+  }
+#undef NLT_TPP
+  NLT_CUDA_LAUNCH_CHECK("wgrad_tpp_kernel");
+  return NLT_OK;
+}
+
 int launch_wgrad_small(const GConvK& k, const float* G, float* ws, WgradK* w, size_t* KD_pad, cudaStream_t st) {
   WsPlan pl;
   if (!ws_plan(k, pl)) return set_err(NLT_ERR_INVALID, "wgrad_small not applicable");

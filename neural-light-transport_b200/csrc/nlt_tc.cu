@@ -29,6 +29,7 @@ constexpr int TC_KB = 32;                       // channels per K-block (128 byt
 constexpr int TC_A_BYTES = TC_BM * TC_KB * 4;   // 16 KB
 constexpr int TC_THREADS = 320;
 constexpr uint32_t TC_SPIN_LIMIT = 1u << 28;    // watchdog: trap instead of hanging the GPU
+unsigned long long g_tc_launches = 0;           // tensor-core kernel launches (diagnostic)
 
 struct TcParams {
   // lattice / tiling
@@ -549,6 +550,7 @@ static int tc_launch_bn(const TcMaps& maps, const TcPlan& pl, cudaStream_t st) {
   const int grid = pl.p.total_tiles < 148 ? pl.p.total_tiles : 148;
   tc_gconv_kernel<BN><<<grid, TC_THREADS, pl.smem_bytes, st>>>(maps, pl.p);
   NLT_CUDA_LAUNCH_CHECK("tc_gconv_kernel");
+  __atomic_add_fetch(&g_tc_launches, 1ull, __ATOMIC_RELAXED);
   return NLT_OK;
 }
 

@@ -43,6 +43,7 @@ _SIGS = {
     'nlt_version': (C.c_char_p, []),
     'nlt_last_error': (C.c_char_p, []),
     'nlt_launch_count': (C.c_uint64, []),
+    'nlt_tc_launch_count': (C.c_uint64, []),
     'nlt_gconv_fwd': (C.c_int, [C.POINTER(GConvDesc), C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int,
                                 C.c_void_p, C.c_void_p]),
     'nlt_gconv_fwd_workspace_bytes': (C.c_int64, [C.POINTER(GConvDesc)]),
@@ -108,3 +109,8 @@ def stream():
 def launch_count():
     """Kernels launched by the library so far (bench.py's gpu_launches)."""
     return int(lib().nlt_launch_count())
+
+
+def tc_launch_count():
+    """tcgen05 tensor-core kernel launches so far."""
+    return int(lib().nlt_tc_launch_count())

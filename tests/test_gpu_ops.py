@@ -111,6 +111,30 @@ def test_gconv_forward_backward(kind, k, s, H, W, segc, cout, act):
         _close(a.grad, want, rtol=1e-4, atol=1e-4)
 
 
+def test_tensor_core_path_is_taken_and_matches_fp32_path():
+    """Eligible shapes must run on the tcgen05 kernel (launch counter moves) and agree with the
+    fp32-FMA kernel of the same library to 3xTF32 accuracy (<= 4e-6 relative to the output scale)."""
+    import ctypes as C
+    engine, nat = _mods()
+    dev = torch.device('cuda')
+    lib = nat.lib()
+    torch.manual_seed(5)
+    x = [torch.randn(2, 32, 32, 32, device=dev), torch.randn(2, 32, 32, 32, device=dev)]
+    L = engine.ConvLayer('conv', 2, 2, 64, 'leakyrelu')
+    L.build(64, dev, torch.Generator().manual_seed(8))
+    segs = [engine.Seg(engine.Act(t)) for t in x]
+    n0 = nat.tc_launch_count()
+    y_tc = L.forward(segs).t
+    assert nat.tc_launch_count() == n0 + 1, 'tensor-core path not taken'
+    d = L._fwd_desc(segs, 2, 32, 32)
+    y_fp = torch.empty_like(y_tc)
+    nat.check(lib.nlt_gconv_fwd(C.byref(d), nat.ptr(L.bias), nat.ACT_CODES['leakyrelu'], 0.0, None, 0, nat.ptr(y_fp),
+                                nat.stream()))
+    assert nat.tc_launch_count() == n0 + 1
+    err = float((y_tc - y_fp).abs().max() / y_fp.abs().max())
+    assert err <= 4e-6, err
+
+
 def test_gconv_sub_and_bcast_segments():
     engine, nat = _mods()
     dev = torch.device('cuda')
