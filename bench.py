@@ -163,7 +163,7 @@ def workload_config(args, world):
                         '%dx%d UV, %dx%d camera, batch %d per GPU, fwd+L2+bwd+AMSGrad' % (
                             args.uv, args.uv, args.uv, args.uv, args.batch),
             'query_channels': 5 + args.c_extra, 'global_batch': args.batch * world, 'uv': args.uv,
-            'parallelism': 'dp%d' % world,
+            'parallelism': 'dp%d' % world, 'cuda_graph': not getattr(args, 'no_graph', False),
             'l2_flush': 'inputs+activations per step (>2.5 GB) exceed the 126 MB L2; fresh batch buffers rotate'}
 
 
@@ -192,7 +192,11 @@ def run_b200(args):
     resident = [tuple(t.to(dev) if torch.is_tensor(t) else t for t in b) for b in host]
     texels_step = args.batch * args.uv * args.uv * world
 
+    graphed = None if args.no_graph else trainvali.GraphedTrainStep(strategy, model, opt, global_bs)
+
     def step(batch):
+        if graphed is not None and not engine.PROF.enabled:
+            return graphed(batch)
         return trainvali.distributed_train_step(strategy, model, batch, opt, global_bs)
 
     def timed(fn, steps):
@@ -222,6 +226,10 @@ def run_b200(args):
     ms_step = timed(lambda i: step(resident[i % 2]), args.steps)
     launches = nat.launch_count() - l0
     tc_launches = nat.tc_launch_count() - tc0
+    if graphed is not None and graphed.graph is not None:
+        # replayed kernels are not seen by the library's counter: add the captured ones per replay
+        launches += args.steps * graphed.captured_launches
+        tc_launches += args.steps * graphed.captured_tc_launches
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end-to-end arm: pinned host inputs -> H2D each step -> loss read back ----
@@ -329,6 +337,7 @@ def main():
     ap.add_argument('--c-extra', dest='c_extra', type=int, default=0, help='59 -> cfg4 64-channel query stack')
     ap.add_argument('--cpu-batch', dest='cpu_batch', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', dest='no_graph', action='store_true', help='launch kernels eagerly (no CUDA graph)')
     ap.add_argument('--profile-out', dest='profile_out', default=None, help='write the per-op device-time table here')
     args = ap.parse_args()
     if args.impl == 'reference':

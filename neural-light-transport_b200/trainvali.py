@@ -104,6 +104,67 @@ def distributed_train_step(strategy, model, batch, optimizer, global_bs):
     return loss, to_vis
 
 
+class GraphedTrainStep:
+    """distributed_train_step with the forward + loss + backward of one replica
+    captured ONCE in a CUDA graph (shapes are static; every activation, gradient
+    and scratch buffer lives in the graph's private pool, so TMA descriptors and
+    kernel arguments stay valid across replays).  Per step: copy the batch into
+    the static input buffers, replay, all-reduce the flat gradient bucket, one
+    fused AMSGrad launch (its bias-corrected lr is a host scalar, so it stays
+    outside the graph).  Same semantics as nlt/trainvali.py:267-290."""
+
+    def __init__(self, strategy, model, optimizer, global_bs):
+        self.strategy, self.model, self.optimizer, self.global_bs = strategy, model, optimizer, global_bs
+        self.graph = None
+        self.static_batch = None
+        self.loss = None
+        self.to_vis = None
+
+    def _body(self, batch):
+        model = self.model
+        pred, gt, loss_kwargs, to_vis = model(batch, mode='train')
+        loss_kwargs['keep_batch'] = True
+        model.set_loss_grad_scale(1.0 / self.global_bs)
+        per_example_loss = model.compute_loss(pred, gt, **loss_kwargs)
+        weighted_loss = per_example_loss.sum() / self.global_bs
+        model.backward()
+        return weighted_loss, to_vis
+
+    def _capture(self, batch):
+        dev = self.model.device
+        self.static_batch = tuple(t.to(dev, torch.float32).contiguous().clone() if torch.is_tensor(t) else t
+                                  for t in batch)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):      # warm-up: lazy build, one-time CUDA attribute calls, scratch sizing
+            for _ in range(2):
+                self._body(self.static_batch)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        l0, t0 = nat.launch_count(), nat.tc_launch_count()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.to_vis = self._body(self.static_batch)
+        # kernels of this library inside ONE replay (the counters only see the capture)
+        self.captured_launches = nat.launch_count() - l0
+        self.captured_tc_launches = nat.tc_launch_count() - t0
+
+    def __call__(self, batch):
+        assert self.model.trainable_registered, \
+            "Register the trainable layers before using `trainable_variables`"
+        if self.graph is None:
+            self._capture(batch)
+        if batch is not self.static_batch:
+            for dst, src in zip(self.static_batch, batch):
+                if torch.is_tensor(dst):
+                    dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        self.strategy.all_reduce_sum_(self.model.flat_grads)
+        self.optimizer.apply_gradients(zip(self.model.gradients, self.model.trainable_variables))
+        loss = self.strategy.all_reduce_sum_(self.loss.clone())
+        return loss, self.to_vis
+
+
 def distributed_vali_step(strategy, model, batch, global_bs):
     """trainvali.py:296-312."""
     pred, gt, loss_kwargs, to_vis = model(batch, mode='vali')
