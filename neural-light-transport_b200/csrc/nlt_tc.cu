@@ -25,8 +25,9 @@ namespace nlt {
 
 constexpr int TC_STAGES = 3;
 constexpr int TC_BM = 128;
-constexpr int TC_KB = 32;                       // channels per K-block (128 bytes of fp32)
-constexpr int TC_A_BYTES = TC_BM * TC_KB * 4;   // 16 KB
+// channels per K-block: 32 (128-byte rows, SWIZZLE_128B) or 16 (64-byte rows, SWIZZLE_64B)
+constexpr int TC_EPI_PAD = 36;                  // floats per staging row (32 columns + 4 pad: conflict-free)
+constexpr int TC_EPI_BYTES = 4 * 32 * TC_EPI_PAD * 4;   // epilogue staging: 4 warps x 32 rows
 constexpr int TC_THREADS = 320;
 constexpr uint32_t TC_SPIN_LIMIT = 1u << 28;    // watchdog: trap instead of hanging the GPU
 unsigned long long g_tc_launches = 0;           // tensor-core kernel launches (diagnostic)
@@ -130,32 +131,33 @@ __device__ __forceinline__ float tf32_rna(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
-// K-major, 128-byte-swizzled operand tile (rows of 128 B, 8-row atoms of 1024 B): sm_100 smem descriptor
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+// K-major swizzled operand tile: rows of ROWB bytes (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B), 8-row atoms.
+template <int ROWB>
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address
   d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major) = 16 B
-  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset: 8 rows * 128 B
+  d |= (uint64_t)((8 * ROWB) >> 4) << 32;             // stride byte offset: 8 rows
   d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  d |= (uint64_t)(ROWB == 128 ? 2 : 4) << 61;         // SWIZZLE_128B / SWIZZLE_64B
   return d;
 }
 
 // ---------------------------------------------------------------------------------------------
 // weight pack: Bhi/Blo [kb][Cout_pad][32] (K-major rows of 128 B), TF32-rounded split
 // ---------------------------------------------------------------------------------------------
-__global__ void tc_pack_weights_kernel(const GConvK g, int kb_total, int chunks_per_tap, int cout_pad,
+__global__ void tc_pack_weights_kernel(const GConvK g, int kbw, int kb_total, int chunks_per_tap, int cout_pad,
                                        float* __restrict__ bhi, float* __restrict__ blo) {
-  const size_t total = (size_t)kb_total * cout_pad * TC_KB;
+  const size_t total = (size_t)kb_total * cout_pad * kbw;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int kk = (int)(i % TC_KB);
-    const int n = (int)((i / TC_KB) % cout_pad);
-    const int kb = (int)(i / ((size_t)TC_KB * cout_pad));
+    const int kk = (int)(i % kbw);
+    const int n = (int)((i / kbw) % cout_pad);
+    const int kb = (int)(i / ((size_t)kbw * cout_pad));
     const int tapi = kb / chunks_per_tap;
     int ch = kb - tapi * chunks_per_tap;
     int s = 0;
-    while (s < g.nseg - 1 && ch >= g.seg[s].C / TC_KB) { ch -= g.seg[s].C / TC_KB; ++s; }
-    const int c = g.seg[s].coff + ch * TC_KB + kk;
+    while (s < g.nseg - 1 && ch >= g.seg[s].C / kbw) { ch -= g.seg[s].C / kbw; ++s; }
+    const int c = g.seg[s].coff + ch * kbw + kk;
     const int uy = tapi / g.ax.nu, ux = tapi - uy * g.ax.nu;
     float v = 0.f;
     if (n < g.Cout) {
@@ -177,10 +179,13 @@ struct TcMaps {
   CUtensorMap bhi, blo;
 };
 
-template <int BN>
+template <int BN, int KBW>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
-  constexpr int B_BYTES = BN * TC_KB * 4;
+  constexpr int ROWB = KBW * 4;                   // bytes per operand row
+  constexpr int TC_KB = KBW;
+  constexpr int TC_A_BYTES = TC_BM * ROWB;
+  constexpr int B_BYTES = BN * ROWB;
   constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
@@ -275,8 +280,8 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           tc_fence_after();
 #pragma unroll
           for (int k = 0; k < TC_KB / 8; ++k) {
-            const uint64_t ah = umma_desc_sw128(a_hi(stage) + k * 32), al = umma_desc_sw128(a_lo(stage) + k * 32);
-            const uint64_t bh = umma_desc_sw128(b_hi(stage) + k * 32), bl = umma_desc_sw128(b_lo(stage) + k * 32);
+            const uint64_t ah = umma_desc_kmajor<ROWB>(a_hi(stage) + k * 32), al = umma_desc_kmajor<ROWB>(a_lo(stage) + k * 32);
+            const uint64_t bh = umma_desc_kmajor<ROWB>(b_hi(stage) + k * 32), bl = umma_desc_kmajor<ROWB>(b_lo(stage) + k * 32);
             tc_mma_tf32(d_tmem, al, bh, IDESC, (kb | k) != 0);   // small terms first
             tc_mma_tf32(d_tmem, ah, bl, IDESC, 1);
             tc_mma_tf32(d_tmem, ah, bh, IDESC, 1);
@@ -314,69 +319,102 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     }
   } else {
     // ================= epilogue =================
+    // TMEM -> registers (lane = pixel) -> bias/activation -> per-warp smem staging -> transposed read
+    // (8 lanes = 128 contiguous bytes of one pixel) -> beta / derivative-mask -> coalesced global store.
+    // The read-modify-write operands of the NEXT 32-column chunk are loaded before the current one is
+    // processed, so their DRAM latency overlaps the TMEM drain.
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32)
-    const int row = quarter * 32 + lane;          // row of the 128-pixel tile
-    const bool vec_ok = aligned16(p.out) && (p.mask_y == nullptr || aligned16(p.mask_y));
+    float* stg = reinterpret_cast<float*>(smem + (size_t)TC_STAGES * STAGE_BYTES) + quarter * 32 * TC_EPI_PAD;
+    const bool rmw = (p.beta != 0.f) || (p.mask_y != nullptr);
+    constexpr int NCH = (BN + 31) / 32;           // 32-column chunks per tile (BN == 16: one half-used chunk)
+    constexpr int CW = BN < 32 ? BN : 32;         // columns per chunk
+    constexpr int QPR = CW / 4;                   // float4 quads per pixel row of a chunk
+    constexpr int RPI = 32 / QPR;                 // pixel rows covered per pass of the warp
+    constexpr int NPASS = 32 / RPI;               // passes per chunk (== QPR)
+    const int lq = lane % QPR, lr = lane / QPR;
+
+    struct Coord { int n, ty0, tx0, nt; };
+    auto tile_coord = [&](int tile) {
+      Coord c;
+      c.nt = tile % p.n_tiles_n;
+      const int mt = tile / p.n_tiles_n;
+      c.n = mt / tiles_per_img;
+      const int r = mt - c.n * tiles_per_img;
+      c.ty0 = (r / p.tiles_x) * p.TH; c.tx0 = (r % p.tiles_x) * p.TW;
+      return c;
+    };
+    // element offset of (tile row, GEMM column) in the output tensor
+    auto out_off = [&](const Coord& c, int row, int nb) -> size_t {
+      const int ty = c.ty0 + row / p.TW, tx = c.tx0 + row % p.TW;
+      int cb = nb, oy, ox;
+      if (p.d2s) {
+        const int tap = nb / p.cout_true;
+        cb = nb - tap * p.cout_true;
+        const int dy = tap / p.d2s_s;
+        oy = ty * p.d2s_s + dy; ox = tx * p.d2s_s + (tap - dy * p.d2s_s);
+      } else {
+        oy = p.o0y + p.osy * ty; ox = p.o0x + p.osx * tx;
+      }
+      return (((size_t)c.n * p.Hout + oy) * p.Wout + ox) * p.cout_true + cb;
+    };
+    float4 rm_old[NPASS], rm_y[NPASS];
+    auto prefetch = [&](const Coord& c, int ch) {
+#pragma unroll
+      for (int i = 0; i < NPASS; ++i) {
+        const size_t ob = out_off(c, quarter * 32 + i * RPI + lr, c.nt * BN + ch * 32 + lq * 4);
+        rm_old[i] = (p.beta != 0.f) ? *reinterpret_cast<const float4*>(p.out + ob) : make_float4(0.f, 0.f, 0.f, 0.f);
+        rm_y[i] = (p.mask_y != nullptr) ? ld4(p.mask_y + ob) : make_float4(1.f, 1.f, 1.f, 1.f);
+      }
+    };
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1;
-      const int nt = tile % p.n_tiles_n;
-      const int mt = tile / p.n_tiles_n;
-      const int n = mt / tiles_per_img;
-      const int r = mt - n * tiles_per_img;
-      const int ty = (r / p.tiles_x) * p.TH + row / p.TW, tx = (r % p.tiles_x) * p.TW + row % p.TW;
-      const bool pix_ok = ty < p.Hl && tx < p.Wl;
-      mbar_wait(bar_accf(buf), acc_phase);
-      tc_fence_after();
+      const Coord tc = tile_coord(tile);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        uint32_t v[16];
-        tc_ld16(taddr + c0, v);
-        if (!pix_ok) continue;
+      for (int ch = 0; ch < NCH; ++ch) {
+        // read-modify-write operands first: their latency overlaps the accumulator wait / TMEM drain
+        if (rmw) prefetch(tc, ch);
+        if (ch == 0) {
+          mbar_wait(bar_accf(buf), acc_phase);
+          tc_fence_after();
+        }
+        const int col0 = tc.nt * BN + ch * 32;    // GEMM column of this chunk
 #pragma unroll
-        for (int g4 = 0; g4 < 4; ++g4) {
-          const int nb = nt * BN + c0 + g4 * 4;       // GEMM column of this quad
-          if (nb >= p.Cout) continue;
-          int cb = nb, oy, ox;
-          if (p.d2s) {
-            const int tap = nb / p.cout_true;
-            cb = nb - tap * p.cout_true;
-            const int dy = tap / p.d2s_s;
-            oy = ty * p.d2s_s + dy; ox = tx * p.d2s_s + (tap - dy * p.d2s_s);
-          } else {
-            oy = p.o0y + p.osy * ty; ox = p.o0x + p.osx * tx;
-          }
-          const size_t ob = (((size_t)n * p.Hout + oy) * p.Wout + ox) * p.cout_true + cb;
-          float o[4];
+        for (int h = 0; h < CW / 16; ++h) {
+          uint32_t v[16];
+          tc_ld16(taddr + ch * 32 + h * 16, v);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float x = __uint_as_float(v[g4 * 4 + e]);
-            if (p.bias != nullptr) x += __ldg(p.bias + cb + e);
-            o[e] = act_fwd(x, p.act);
-          }
-          if (vec_ok) {
-            if (p.beta != 0.f) {
-              const float4 old = *reinterpret_cast<const float4*>(p.out + ob);
-              o[0] += p.beta * old.x; o[1] += p.beta * old.y; o[2] += p.beta * old.z; o[3] += p.beta * old.w;
-            }
-            if (p.mask_y != nullptr) {
-              const float4 y = ld4(p.mask_y + ob);
-              o[0] *= act_bwd_from_y(y.x, p.mask_act); o[1] *= act_bwd_from_y(y.y, p.mask_act);
-              o[2] *= act_bwd_from_y(y.z, p.mask_act); o[3] *= act_bwd_from_y(y.w, p.mask_act);
-            }
-            *reinterpret_cast<float4*>(p.out + ob) = make_float4(o[0], o[1], o[2], o[3]);
-          } else {
+          for (int q4 = 0; q4 < 4; ++q4) {
+            int cb = col0 + h * 16 + q4 * 4;
+            if (p.d2s) cb -= (cb / p.cout_true) * p.cout_true;
+            float o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float x = o[e];
-              if (p.beta != 0.f) x += p.beta * p.out[ob + e];
-              if (p.mask_y != nullptr) x *= act_bwd_from_y(__ldg(p.mask_y + ob + e), p.mask_act);
-              p.out[ob + e] = x;
+              float x = __uint_as_float(v[q4 * 4 + e]);
+              if (p.bias != nullptr) x += __ldg(p.bias + cb + e);
+              o[e] = act_fwd(x, p.act);
             }
+            *reinterpret_cast<float4*>(stg + lane * TC_EPI_PAD + h * 16 + q4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
           }
         }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < NPASS; ++i) {
+          const int row = i * RPI + lr;
+          float4 o = *reinterpret_cast<const float4*>(stg + row * TC_EPI_PAD + lq * 4);
+          if (rmw) {
+            o.x += p.beta * rm_old[i].x; o.y += p.beta * rm_old[i].y; o.z += p.beta * rm_old[i].z; o.w += p.beta * rm_old[i].w;
+            if (p.mask_y != nullptr) {
+              o.x *= act_bwd_from_y(rm_y[i].x, p.mask_act); o.y *= act_bwd_from_y(rm_y[i].y, p.mask_act);
+              o.z *= act_bwd_from_y(rm_y[i].z, p.mask_act); o.w *= act_bwd_from_y(rm_y[i].w, p.mask_act);
+            }
+          }
+          const size_t ob = out_off(tc, quarter * 32 + row, col0 + lq * 4);
+          *reinterpret_cast<float4*>(p.out + ob) = o;
+        }
+        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(bar_acce(buf));
@@ -416,6 +454,7 @@ static EncodeTiledFn get_encode() {
 struct TcPlan {
   bool ok;
   int bn;
+  int kbw;
   TcParams p;
   int chunks_per_tap;
   int cout_pad;
@@ -440,11 +479,15 @@ static TcPlan tc_plan(const GConvK& k) {
   pl.bn = pick_bn(k.Cout);
   if (pl.bn == 0) return pl;
   int ctot = 0;
+  pl.kbw = 32;
   for (int s = 0; s < k.nseg; ++s) {
     const Seg& sg = k.seg[s];
-    if (sg.C % TC_KB != 0 || sg.sub != nullptr || sg.bcast || !aligned16(sg.ptr)) return pl;
+    if (sg.C % 16 != 0 || sg.sub != nullptr || sg.bcast || !aligned16(sg.ptr)) return pl;
+    if (sg.C % 32 != 0) pl.kbw = 16;
     ctot += sg.C;
   }
+  const int TC_KB = pl.kbw;
+  if (!aligned16(k.w)) { /* weights are only read by the pack kernel: no alignment needed */ }
   if (ctot < 64 && k.ay.nu * k.ax.nu * ctot < 64) return pl;      // too little K to pay for the pipeline
   if (k.ay.nu < 1 || k.ax.nu < 1) return pl;
   TcParams& p = pl.p;
@@ -477,13 +520,15 @@ static TcPlan tc_plan(const GConvK& k) {
   p.Hout = k.Hout; p.Wout = k.Wout; p.cout_true = k.cout_true; p.Cout = k.Cout;
   p.o0y = k.ay.o0; p.osy = k.ay.os; p.o0x = k.ax.o0; p.osx = k.ax.os;
   p.d2s = k.d2s; p.d2s_s = k.d2s_s;
+  // few output tiles: narrower column tiles so that more SMs get work (A is re-read from L2)
+  while (pl.bn > 32 && (long long)p.N * p.tiles_x * p.tiles_y * (k.Cout / pl.bn) < 148) pl.bn /= 2;
   p.n_tiles_n = k.Cout / pl.bn;
   const long long tt = (long long)p.N * p.tiles_x * p.tiles_y * p.n_tiles_n;
   if (tt > (1ll << 30)) return pl;
   p.total_tiles = (int)tt;
   pl.cout_pad = k.Cout;
   pl.pack_floats = (size_t)p.kb_total * pl.cout_pad * TC_KB;
-  pl.smem_bytes = (size_t)TC_STAGES * (2 * TC_A_BYTES + 2 * (size_t)pl.bn * TC_KB * 4) + 1024;
+  pl.smem_bytes = (size_t)TC_STAGES * (2 * (size_t)TC_BM * TC_KB * 4 + 2 * (size_t)pl.bn * TC_KB * 4) + TC_EPI_BYTES + 1024;
   if (get_encode() == nullptr) return pl;
   pl.ok = true;
   return pl;
@@ -492,6 +537,8 @@ static TcPlan tc_plan(const GConvK& k) {
 static int encode_maps(const GConvK& k, const TcPlan& pl, const float* bhi, const float* blo, TcMaps* maps) {
   EncodeTiledFn enc = get_encode();
   const TcParams& p = pl.p;
+  const int TC_KB = pl.kbw;
+  const CUtensorMapSwizzle swz = pl.kbw == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   for (int s = 0; s < k.nseg; ++s) {
     const Seg& sg = k.seg[s];
     const cuuint64_t C = sg.C, W = k.Win, H = k.Hin, N = k.N;
@@ -503,7 +550,7 @@ static int encode_maps(const GConvK& k, const TcPlan& pl, const float* bhi, cons
       cuuint32_t box[5] = {(cuuint32_t)TC_KB, 1, (cuuint32_t)p.TW, 1, (cuuint32_t)p.TH};
       cuuint32_t es[5] = {1, 1, 1, 1, 1};
       r = enc(&maps->a[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)sg.ptr, dims, strides, box, es,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
       cuuint64_t dims[4] = {C, W, H, N};
@@ -511,7 +558,7 @@ static int encode_maps(const GConvK& k, const TcPlan& pl, const float* bhi, cons
       cuuint32_t box[4] = {(cuuint32_t)TC_KB, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
       cuuint32_t es[4] = {1, 1, 1, 1};
       r = enc(&maps->a[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)sg.ptr, dims, strides, box, es,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
     if (r != CUDA_SUCCESS) return set_err(NLT_ERR_CUDA, "cuTensorMapEncodeTiled(A seg %d) failed: %d", s, (int)r);
@@ -524,7 +571,7 @@ static int encode_maps(const GConvK& k, const TcPlan& pl, const float* bhi, cons
     cuuint32_t box[3] = {(cuuint32_t)TC_KB, (cuuint32_t)pl.bn, 1};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = enc(bm[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)planes[i], dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_err(NLT_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
   }
@@ -538,17 +585,18 @@ size_t tc_workspace_bytes(const GConvK& k) {
   return pl.ok ? 2 * pl.pack_floats * sizeof(float) + 256 : 0;
 }
 
-template <int BN>
+template <int BN, int KBW>
 static int tc_launch_bn(const TcMaps& maps, const TcPlan& pl, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gconv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)((size_t)TC_STAGES * (2 * TC_A_BYTES + 2 * (size_t)BN * TC_KB * 4) + 1024));
+    cudaError_t e = cudaFuncSetAttribute(
+        tc_gconv_kernel<BN, KBW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        (int)((size_t)TC_STAGES * (2 * (size_t)TC_BM * KBW * 4 + 2 * (size_t)BN * KBW * 4) + TC_EPI_BYTES + 1024));
     if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const int grid = pl.p.total_tiles < 148 ? pl.p.total_tiles : 148;
-  tc_gconv_kernel<BN><<<grid, TC_THREADS, pl.smem_bytes, st>>>(maps, pl.p);
+  tc_gconv_kernel<BN, KBW><<<grid, TC_THREADS, pl.smem_bytes, st>>>(maps, pl.p);
   NLT_CUDA_LAUNCH_CHECK("tc_gconv_kernel");
   __atomic_add_fetch(&g_tc_launches, 1ull, __ATOMIC_RELAXED);
   return NLT_OK;
@@ -566,18 +614,26 @@ int launch_tc(const GConvK& k, const float* bias, int act, float beta, const flo
     const size_t total = pl.pack_floats;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    tc_pack_weights_kernel<<<blocks, 256, 0, st>>>(k, pl.p.kb_total, pl.chunks_per_tap, pl.cout_pad, bhi, blo);
+    tc_pack_weights_kernel<<<blocks, 256, 0, st>>>(k, pl.kbw, pl.p.kb_total, pl.chunks_per_tap, pl.cout_pad, bhi, blo);
     NLT_CUDA_LAUNCH_CHECK("tc_pack_weights_kernel");
   }
   TcMaps maps;
   int rc = encode_maps(k, pl, bhi, blo, &maps);
   if (rc != NLT_OK) return rc;
   pl.p.act = act; pl.p.mask_act = mask_act; pl.p.beta = beta; pl.p.bias = bias; pl.p.mask_y = mask_y; pl.p.out = out;
+  if (pl.kbw == 32) {
+    switch (pl.bn) {
+      case 128: return tc_launch_bn<128, 32>(maps, pl, st);
+      case 64: return tc_launch_bn<64, 32>(maps, pl, st);
+      case 32: return tc_launch_bn<32, 32>(maps, pl, st);
+      default: return tc_launch_bn<16, 32>(maps, pl, st);
+    }
+  }
   switch (pl.bn) {
-    case 128: return tc_launch_bn<128>(maps, pl, st);
-    case 64: return tc_launch_bn<64>(maps, pl, st);
-    case 32: return tc_launch_bn<32>(maps, pl, st);
-    default: return tc_launch_bn<16>(maps, pl, st);
+    case 128: return tc_launch_bn<128, 16>(maps, pl, st);
+    case 64: return tc_launch_bn<64, 16>(maps, pl, st);
+    case 32: return tc_launch_bn<32, 16>(maps, pl, st);
+    default: return tc_launch_bn<16, 16>(maps, pl, st);
   }
 }
 

@@ -69,6 +69,12 @@ GEOMS = [
     ('conv', 2, 1, 32, 32, [256], 256),         # two column tiles of 128, K = 1024
     ('deconv', 2, 2, 16, 16, [128, 128], 128),  # N' = 512: four column tiles
     ('conv', 1, 1, 16, 16, [64, 32], 48),       # BN = 16
+    # 16-channel sources: 64-byte rows / SWIZZLE_64B K-blocks
+    ('conv', 2, 2, 32, 32, [16, 16], 16),       # level-1 query conv shape
+    ('conv', 2, 1, 16, 16, [16], 16),
+    ('deconv', 2, 2, 16, 16, [16, 32, 32], 8),  # level-11 up-conv shape: N' = 32
+    ('deconv', 2, 1, 32, 16, [16], 16),
+    ('conv', 2, 2, 64, 64, [32, 16], 32),       # mixed 32/16 sources -> 16-wide blocks
 ]
 
 
