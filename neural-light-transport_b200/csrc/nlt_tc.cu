@@ -23,7 +23,7 @@
 
 namespace nlt {
 
-constexpr int TC_STAGES = 3;
+constexpr int TC_MAX_STAGES = 8;                // smem ring depth is chosen per shape (2..8): bytes in flight, not math, bound most layers
 constexpr int TC_BM = 128;
 // channels per K-block: 32 (128-byte rows, SWIZZLE_128B) or 16 (64-byte rows, SWIZZLE_64B)
 constexpr int TC_EPI_PAD = 36;                  // floats per staging row (32 columns + 4 pad: conflict-free)
@@ -53,6 +53,7 @@ struct TcParams {
   int o0y, osy, o0x, osx;            // output pixel = o0 + os * lattice coordinate (non-d2s)
   int d2s, d2s_s;
   int act, mask_act;
+  int stages;               // smem ring depth
   float beta;
   const float* bias;
   const float* mask_y;
@@ -193,16 +194,17 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t bars[3 * TC_STAGES + 4];
+  __shared__ __align__(8) uint64_t bars[3 * TC_MAX_STAGES + 4];
+  const int TC_STAGES = p.stages;
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
-  auto bar_ready = [&](int s) { return bar0 + 8u * (TC_STAGES + s); };
-  auto bar_empty = [&](int s) { return bar0 + 8u * (2 * TC_STAGES + s); };
-  auto bar_accf = [&](int b) { return bar0 + 8u * (3 * TC_STAGES + b); };
-  auto bar_acce = [&](int b) { return bar0 + 8u * (3 * TC_STAGES + 2 + b); };
+  auto bar_ready = [&](int s) { return bar0 + 8u * (TC_MAX_STAGES + s); };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (2 * TC_MAX_STAGES + s); };
+  auto bar_accf = [&](int b) { return bar0 + 8u * (3 * TC_MAX_STAGES + b); };
+  auto bar_acce = [&](int b) { return bar0 + 8u * (3 * TC_MAX_STAGES + 2 + b); };
   const uint32_t smem_base = smem_u32(smem);
   auto a_hi = [&](int s) { return smem_base + (uint32_t)s * STAGE_BYTES; };
   auto a_lo = [&](int s) { return smem_base + (uint32_t)s * STAGE_BYTES + TC_A_BYTES; };
@@ -488,7 +490,7 @@ static TcPlan tc_plan(const GConvK& k) {
   }
   const int TC_KB = pl.kbw;
   if (!aligned16(k.w)) { /* weights are only read by the pack kernel: no alignment needed */ }
-  if (ctot < 64 && k.ay.nu * k.ax.nu * ctot < 64) return pl;      // too little K to pay for the pipeline
+  if (k.ay.nu * k.ax.nu * ctot < 16) return pl;
   if (k.ay.nu < 1 || k.ax.nu < 1) return pl;
   TcParams& p = pl.p;
   p.N = k.N; p.Hl = k.ay.nt; p.Wl = k.ax.nt;
@@ -528,7 +530,14 @@ static TcPlan tc_plan(const GConvK& k) {
   p.total_tiles = (int)tt;
   pl.cout_pad = k.Cout;
   pl.pack_floats = (size_t)p.kb_total * pl.cout_pad * TC_KB;
-  pl.smem_bytes = (size_t)TC_STAGES * (2 * (size_t)TC_BM * TC_KB * 4 + 2 * (size_t)pl.bn * TC_KB * 4) + TC_EPI_BYTES + 1024;
+  {
+    const size_t stage_bytes = 2 * (size_t)TC_BM * TC_KB * 4 + 2 * (size_t)pl.bn * TC_KB * 4;
+    int st = (int)((227 * 1024 - TC_EPI_BYTES - 2048) / stage_bytes);
+    if (st > TC_MAX_STAGES) st = TC_MAX_STAGES;
+    if (st < 2) return pl;
+    p.stages = st;
+    pl.smem_bytes = (size_t)st * stage_bytes + TC_EPI_BYTES + 1024;
+  }
   if (get_encode() == nullptr) return pl;
   pl.ok = true;
   return pl;
@@ -589,9 +598,8 @@ template <int BN, int KBW>
 static int tc_launch_bn(const TcMaps& maps, const TcPlan& pl, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(
-        tc_gconv_kernel<BN, KBW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-        (int)((size_t)TC_STAGES * (2 * (size_t)TC_BM * KBW * 4 + 2 * (size_t)BN * KBW * 4) + TC_EPI_BYTES + 1024));
+    cudaError_t e = cudaFuncSetAttribute(tc_gconv_kernel<BN, KBW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024 - 1024);
     if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
