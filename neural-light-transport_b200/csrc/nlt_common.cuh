@@ -150,4 +150,8 @@ size_t tc_workspace_bytes(const GConvK& k);
 int launch_tc(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act, float* out,
               void* workspace, size_t workspace_bytes, cudaStream_t st);
 
+bool tc_wgrad_applicable(const GConvK& k);
+size_t tc_wgrad_ws_floats(const GConvK& k);
+int launch_tc_wgrad(const GConvK& k, const float* G, float* ws, WgradK* w, size_t* KD_pad, cudaStream_t st);
+
 }  // namespace nlt

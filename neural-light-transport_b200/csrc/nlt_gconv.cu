@@ -601,6 +601,12 @@ static bool tc_enabled() {
   return v == 1;
 }
 
+static bool tc_wgrad_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NLT_DISABLE_TC_WGRAD"); v = (tc_enabled() && !(e && e[0] == '1')) ? 1 : 0; }
+  return v == 1;
+}
+
 int64_t nlt_gconv_fwd_workspace_bytes(const nlt_gconv_desc* d) {
   GConvK ph[16];
   int np = 0;
@@ -648,7 +654,8 @@ int64_t nlt_gconv_wgrad_workspace_bytes(const nlt_gconv_desc* d) {
   size_t mx = 0;
   for (int i = 0; i < np; ++i) {
     if (ph[i].M == 0) continue;
-    size_t need = wgrad_tpp_applicable(ph[i]) ? wgrad_tpp_ws_floats(ph[i])
+    size_t need = (tc_wgrad_enabled() && tc_wgrad_applicable(ph[i])) ? tc_wgrad_ws_floats(ph[i])
+                  : wgrad_tpp_applicable(ph[i]) ? wgrad_tpp_ws_floats(ph[i])
                   : wgrad_small_applicable(ph[i]) ? wgrad_small_ws_floats(ph[i]) : plan_wgrad(ph[i]).ws_floats;
     if (need > mx) mx = need;
   }
@@ -670,7 +677,11 @@ int nlt_gconv_wgrad(const nlt_gconv_desc* d, const float* G, float* dW, float* d
     float* ws = (float*)workspace;
     WgradK w;
     size_t KD_pad = 0;
-    if (wgrad_tpp_applicable(k)) {
+    if (tc_wgrad_enabled() && tc_wgrad_applicable(k)) {
+      NLT_CHECK_ARG((int64_t)(tc_wgrad_ws_floats(k) * sizeof(float)) <= workspace_bytes, "workspace too small");
+      rc = launch_tc_wgrad(k, G, ws, &w, &KD_pad, st);
+      if (rc != NLT_OK) return rc;
+    } else if (wgrad_tpp_applicable(k)) {
       NLT_CHECK_ARG((int64_t)(wgrad_tpp_ws_floats(k) * sizeof(float)) <= workspace_bytes, "workspace too small");
       rc = launch_wgrad_tpp(k, G, ws, &w, &KD_pad, st);
       if (rc != NLT_OK) return rc;
