@@ -11,6 +11,7 @@
 // larger Cout this fp32-FFMA path is FMA-bound and the tcgen05 path
 // (nlt_tc.cu) takes over where the shape allows.
 #include <stdlib.h>
+#include <string.h>
 #include "nlt_common.cuh"
 
 namespace nlt {
@@ -595,16 +596,22 @@ const char* nlt_last_error(void) { return nlt::g_err; }
 uint64_t nlt_launch_count(void) { return __atomic_load_n(&nlt::g_launches, __ATOMIC_RELAXED); }
 uint64_t nlt_tc_launch_count(void) { return __atomic_load_n(&nlt::g_tc_launches, __ATOMIC_RELAXED); }
 
+static int g_opt_tc = -1, g_opt_tc_wgrad = -1;   // -1: take the environment default
 static bool tc_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("NLT_DISABLE_TC"); v = (e && e[0] == '1') ? 0 : 1; }
-  return v == 1;
+  if (g_opt_tc < 0) { const char* e = getenv("NLT_DISABLE_TC"); g_opt_tc = (e && e[0] == '1') ? 0 : 1; }
+  return g_opt_tc == 1;
 }
 
 static bool tc_wgrad_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("NLT_DISABLE_TC_WGRAD"); v = (tc_enabled() && !(e && e[0] == '1')) ? 1 : 0; }
-  return v == 1;
+  if (g_opt_tc_wgrad < 0) { const char* e = getenv("NLT_DISABLE_TC_WGRAD"); g_opt_tc_wgrad = (e && e[0] == '1') ? 0 : 1; }
+  return tc_enabled() && g_opt_tc_wgrad == 1;
+}
+
+int nlt_set_option(const char* name, int value) {
+  NLT_CHECK_ARG(name != nullptr, "null option name");
+  if (strcmp(name, "tc") == 0) { g_opt_tc = value ? 1 : 0; return NLT_OK; }
+  if (strcmp(name, "tc_wgrad") == 0) { g_opt_tc_wgrad = value ? 1 : 0; return NLT_OK; }
+  return set_err(NLT_ERR_INVALID, "unknown option '%s'", name);
 }
 
 int64_t nlt_gconv_fwd_workspace_bytes(const nlt_gconv_desc* d) {

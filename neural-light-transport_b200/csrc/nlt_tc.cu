@@ -590,113 +590,122 @@ static int encode_maps(const GConvK& k, const TcPlan& pl, const float* bhi, cons
 // =============================================================================================
 // tcgen05 weight gradient:  dW[Kd x N] = sum_p A[p, Kd]^T * G[p, N]   (3xTF32, fp32 accumulate in TMEM)
 //
-// The contraction runs over PIXELS, so both operands are "MN-major": the same TMA tiles
-// [pixels x channels] as in the forward kernel, read by tcgen05.mma with the channel index as M (for
-// A: 128 rows = 128/KBW (tap, source, chunk) groups) or N (for G = dz), and 8 pixels per MMA as K.
-// One CTA accumulates its share of the pixel tiles into a single [128 x BN] TMEM tile and writes one
-// fp32 partial; the fixed-order reduce kernel of the fp32 path sums the partials (deterministic) and
-// scatters them into the Keras weight layout.  The bias gradient rides along as an all-ones "channel"
-// (a constant operand tile), i.e. one more M row.
+// The contraction runs over PIXELS.  tf32 tensor-core operands must be K-major here (the only MN-major
+// tf32 layout, 128B_ATOM_32B, needs 32-channel rows and would exclude the 16-channel layers that own most
+// of the bytes), so the four transform warps TRANSPOSE while they split: TMA brings raw [32 pixels x w
+// channels] pieces (w <= 32, hardware-swizzled so the transposing reads are bank-conflict free), the
+// transform writes hi/lo planes [channel row][32 pixels = 128 B] in the K-major SWIZZLE_128B layout, and
+// the MMA warp issues 4 K-steps x 3 products per 32-pixel stage into ONE [128 x BN] accumulator that lives
+// in TMEM for the CTA's whole pixel range.  Works for any channel counts that are multiples of 4.
+// The bias gradient (column sums of G) is accumulated by the transform warps on the way.  One fp32
+// partial per CTA goes to the workspace; the fp32 path's fixed-order reduce kernel sums the partials
+// (deterministic) and scatters them into the Keras weight layout.
 // =============================================================================================
-constexpr int WG_PT = 32;                       // pixels per pipeline stage
-constexpr int WG_MAX_GROUPS = 8;                // A groups per M tile (128 / 16)
+constexpr int WG_PT = 32;             // pixels per stage (= 128 B of fp32 per transposed row)
+constexpr int WG_MAX_PIECES = 36;     // raw pieces per stage: <= 32 for A (128 rows / 4) + <= 2 for G (+ slack)
+constexpr int WG_PLANE_A = TC_BM * 128;   // one transposed A plane: 128 rows x 128 B
+
+struct WgPiece {
+  int16_t is_g, seg, uy, ux;   // source
+  int16_t c0, w;               // channel range inside the source
+  int16_t row, pad;            // first transposed row (A: row of the M tile; G: row of the N tile)
+  int32_t raw_off;             // byte offset of the raw tile inside a raw stage (1024-aligned)
+};
 
 struct WgParams {
   int N, Hl, Wl, TW, TH, tiles_x, tiles_y, total_ptiles;
-  // A groups of this launch (all M tiles): tap, source, channel chunk
-  int n_groups;                 // real groups (without the ones group)
-  int mt_groups;                // group slots per M tile (128 / KBW)
-  int n_mtiles;
   int mode_patch, ux_step, x_off, uy_step, y_off, Hs;     // A coordinate map (as TcParams)
-  int g_patch, g_px, g_py, g_Hs;                          // G: 5-D strided lattice view (transposed phases)
-  int ntap_x;
-  int nseg;
-  int seg_chunks[NLT_MAX_SEG];
-  int seg_coff[NLT_MAX_SEG];
-  int chunks_per_tap;
-  int ctot;
-  int ng;                       // G chunks per column tile
-  int n_ntiles;                 // column tiles (Cout / BN)
-  int stages;
+  int g_patch, g_px, g_py, g_Hs;                          // G on a strided sub-lattice (transposed phases)
+  int ntap_x, nseg, ctot, Kd;
+  int seg_C[NLT_MAX_SEG], seg_coff[NLT_MAX_SEG];
+  int n_mtiles, n_ntiles;
+  int raw_stages, raw_stage_bytes;
   int Cout, ld, KD_pad, bias_row;
   float* ws;
 };
 
 struct WgMaps {
-  CUtensorMap a[NLT_MAX_SEG];
-  CUtensorMap g;
+  CUtensorMap a[NLT_MAX_SEG][4];   // per source, per piece width class: 4, 8, 16, 32 channels
+  CUtensorMap g;                   // G pieces (width BN <= 32 -> BN, else 32)
 };
 
-// MN-major swizzled operand: rows (= K index, pixels) of ROWB bytes; MN atoms LBO bytes apart
-template <int ROWB>
-__device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // leading byte offset: next MN atom
-  d |= (uint64_t)((8 * ROWB) >> 4) << 32;             // stride byte offset: next 8 K-rows
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)(ROWB == 128 ? 2 : 4) << 61;
-  return d;
+__device__ __forceinline__ int wg_wclass(int w) { return w == 32 ? 3 : w == 16 ? 2 : w == 8 ? 1 : 0; }
+
+// physical 16-byte chunk of logical chunk `cq` in pixel row `p` of a raw [32 x w] tile (TMA swizzle by row bytes)
+__device__ __forceinline__ int wg_raw_chunk(int w, int p, int cq) {
+  return w == 32 ? (cq ^ (p & 7)) : w == 16 ? (cq ^ ((p >> 1) & 3)) : w == 8 ? (cq ^ ((p >> 2) & 1)) : cq;
 }
 
-template <int BN, int KBW, int GCW>
+template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
-  constexpr int ROWA = KBW * 4, ROWG = GCW * 4;
-  constexpr int TILE_A = WG_PT * ROWA, TILE_G = WG_PT * ROWG;
-  constexpr int MT = TC_BM / KBW;                 // A group slots
-  constexpr int NG = BN / GCW;                    // G chunks
-  constexpr int HI_BYTES = MT * TILE_A + NG * TILE_G;
-  constexpr int STAGE_BYTES = 2 * HI_BYTES;
-  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  constexpr int PLANE_G = BN * 128;
+  constexpr int PLANES_BYTES = 2 * WG_PLANE_A + 2 * PLANE_G;      // Ahi, Alo, Ghi, Glo
+  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : 128;
+  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  constexpr int GQ = BN / 4;                    // channel quads of G
+  constexpr int GI = (GQ + 3) / 4;              // G quads per transform thread
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t bars[3 * TC_MAX_STAGES + 1];
+  __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 5];
   __shared__ uint32_t tmem_base_smem;
-  const int stages = p.stages;
+  __shared__ WgPiece pieces[WG_MAX_PIECES];
+  __shared__ int n_pieces_s, raw_bytes_s;
+  __shared__ float bias_part[4][64];
+
+  const int S = p.raw_stages;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
-  auto bar_full = [&](int s) { return bar0 + 8u * s; };
-  auto bar_ready = [&](int s) { return bar0 + 8u * (TC_MAX_STAGES + s); };
-  auto bar_empty = [&](int s) { return bar0 + 8u * (2 * TC_MAX_STAGES + s); };
-  const uint32_t bar_accf = bar0 + 8u * (3 * TC_MAX_STAGES);
-  const uint32_t smem_base = smem_u32(smem);
+  auto bar_rfull = [&](int s) { return bar0 + 8u * s; };
+  auto bar_rempty = [&](int s) { return bar0 + 8u * (TC_MAX_STAGES + s); };
+  auto bar_tready = [&](int b) { return bar0 + 8u * (2 * TC_MAX_STAGES + b); };
+  auto bar_tempty = [&](int b) { return bar0 + 8u * (2 * TC_MAX_STAGES + 2 + b); };
+  const uint32_t bar_accf = bar0 + 8u * (2 * TC_MAX_STAGES + 4);
+  uint8_t* planes = smem;                                         // 2 x PLANES_BYTES
+  uint8_t* raw = smem + 2 * PLANES_BYTES;                         // S x raw_stage_bytes
+  const uint32_t planes_u32 = smem_u32(planes), raw_u32 = smem_u32(raw);
 
   const int mtile = blockIdx.y, ntile = blockIdx.z;
-  const int g0 = mtile * MT;                                        // first group of this M tile
-  int n_active = p.n_groups - g0;                                   // real groups here
-  const bool has_bias = (n_active >= 0 && n_active < MT);           // the ones group sits right after the last real one
-  if (n_active > MT) n_active = MT;
-  if (n_active < 0) n_active = 0;
+  const int k_lo = mtile * TC_BM, k_hi = min(p.Kd, k_lo + TC_BM);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_ready(s), 128); mbar_init(bar_empty(s), 1); }
+    // piece table of this (M tile, N tile): A pieces in flattened (tap, concat-channel) order, then G pieces
+    int np = 0, off = 0, k = k_lo;
+    while (k < k_hi) {
+      const int tap = k / p.ctot, c = k - tap * p.ctot;
+      int s = 0;
+      while (s < p.nseg - 1 && c >= p.seg_coff[s] + p.seg_C[s]) ++s;
+      const int cin = c - p.seg_coff[s];
+      int w = p.seg_C[s] - cin;
+      if (w > 32) w = 32;
+      if (w > k_hi - k) w = k_hi - k;
+      w = w >= 32 ? 32 : w >= 16 ? 16 : w >= 8 ? 8 : 4;         // power-of-two piece widths (all sizes are multiples of 4)
+      WgPiece& pc = pieces[np++];
+      pc.is_g = 0; pc.seg = (int16_t)s; pc.uy = (int16_t)(tap / p.ntap_x); pc.ux = (int16_t)(tap % p.ntap_x);
+      pc.c0 = (int16_t)cin; pc.w = (int16_t)w; pc.row = (int16_t)(k - k_lo); pc.pad = 0; pc.raw_off = off;
+      off += (WG_PT * w * 4 + 1023) & ~1023;
+      k += w;
+    }
+    const int gw = BN < 32 ? BN : 32;
+    for (int c = 0; c < BN; c += gw) {
+      WgPiece& pc = pieces[np++];
+      pc.is_g = 1; pc.seg = 0; pc.uy = 0; pc.ux = 0; pc.c0 = (int16_t)(ntile * BN + c); pc.w = (int16_t)gw;
+      pc.row = (int16_t)c; pc.pad = 0; pc.raw_off = off;
+      off += (WG_PT * gw * 4 + 1023) & ~1023;
+    }
+    n_pieces_s = np;
+    int bytes = 0;
+    for (int i = 0; i < np; ++i) bytes += WG_PT * pieces[i].w * 4;
+    raw_bytes_s = bytes;
+    for (int s = 0; s < S; ++s) { mbar_init(bar_rfull(s), 1); mbar_init(bar_rempty(s), 128); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_tready(b), 128); mbar_init(bar_tempty(b), 1); }
     mbar_init(bar_accf, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // constant parts of every stage: unused group slots are zero, the bias slot is the all-ones channel 0
-  for (int st = 0; st < stages; ++st) {
-    float* hi = reinterpret_cast<float*>(smem + (size_t)st * STAGE_BYTES);
-    float* lo = reinterpret_cast<float*>(smem + (size_t)st * STAGE_BYTES + HI_BYTES);
-    for (int i = threadIdx.x; i < (MT - n_active) * TILE_A / 4; i += TC_THREADS) {
-      hi[n_active * TILE_A / 4 + i] = 0.f;
-      lo[n_active * TILE_A / 4 + i] = 0.f;
-    }
-  }
-  __syncthreads();
-  if (has_bias) {
-    for (int st = 0; st < stages; ++st) {
-      uint8_t* tile = smem + (size_t)st * STAGE_BYTES + (size_t)n_active * TILE_A;
-      for (int r = threadIdx.x; r < WG_PT; r += TC_THREADS) {
-        // logical (row r, channel 0) -> physical 16-byte chunk under the TMA/UMMA swizzle
-        const int chunk = (ROWA == 128) ? (r & 7) : ((r >> 1) & 3);
-        *reinterpret_cast<float*>(tile + (size_t)r * ROWA + chunk * 16) = 1.0f;
-      }
-    }
-  }
+  // transposed planes start as zero: rows beyond this tile's Kd / BN stay zero for the whole kernel
+  for (int i = threadIdx.x; i < 2 * PLANES_BYTES / 16; i += TC_THREADS)
+    reinterpret_cast<float4*>(planes)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
                  "r"(TMEM_COLS) : "memory");
@@ -707,11 +716,13 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  const int n_pieces = n_pieces_s;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   int my_tiles = 0;
   for (int t = blockIdx.x; t < p.total_ptiles; t += gridDim.x) ++my_tiles;
 
   if (warp == 0) {
+    // ================= TMA producer =================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -719,100 +730,120 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
         const int n = t / tiles_per_img;
         const int r = t - n * tiles_per_img;
         const int ty0 = (r / p.tiles_x) * p.TH, tx0 = (r % p.tiles_x) * p.TW;
-        mbar_wait(bar_empty(stage), phase ^ 1);
-        mbar_expect_tx(bar_full(stage), n_active * TILE_A + NG * TILE_G);
-        const uint32_t base = smem_base + (uint32_t)stage * STAGE_BYTES;
-        for (int gi = 0; gi < n_active; ++gi) {
-          const int g = g0 + gi;
-          const int tap = g / p.chunks_per_tap;
-          int ch = g - tap * p.chunks_per_tap;
-          int s = 0;
-          while (s < p.nseg - 1 && ch >= p.seg_chunks[s]) { ch -= p.seg_chunks[s]; ++s; }
-          const int uy = tap / p.ntap_x, ux = tap - uy * p.ntap_x;
-          if (p.mode_patch)
-            tma_load_5d(base + gi * TILE_A, &maps.a[s], bar_full(stage), ch * KBW, ux, tx0, uy, n * p.Hs + ty0);
-          else
-            tma_load_4d(base + gi * TILE_A, &maps.a[s], bar_full(stage), ch * KBW, tx0 + ux * p.ux_step + p.x_off,
-                        ty0 + uy * p.uy_step + p.y_off, n);
+        mbar_wait(bar_rempty(stage), phase ^ 1);
+        mbar_expect_tx(bar_rfull(stage), (uint32_t)raw_bytes_s);
+        const uint32_t base = raw_u32 + (uint32_t)stage * p.raw_stage_bytes;
+        for (int i = 0; i < n_pieces; ++i) {
+          const WgPiece pc = pieces[i];
+          if (pc.is_g) {
+            if (p.g_patch)
+              tma_load_5d(base + pc.raw_off, &maps.g, bar_rfull(stage), pc.c0, p.g_px, tx0, p.g_py, n * p.g_Hs + ty0);
+            else
+              tma_load_4d(base + pc.raw_off, &maps.g, bar_rfull(stage), pc.c0, tx0, ty0, n);
+          } else {
+            const CUtensorMap* m = &maps.a[pc.seg][wg_wclass(pc.w)];
+            if (p.mode_patch)
+              tma_load_5d(base + pc.raw_off, m, bar_rfull(stage), pc.c0, pc.ux, tx0, pc.uy, n * p.Hs + ty0);
+            else
+              tma_load_4d(base + pc.raw_off, m, bar_rfull(stage), pc.c0, tx0 + pc.ux * p.ux_step + p.x_off,
+                          ty0 + pc.uy * p.uy_step + p.y_off, n);
+          }
         }
-        for (int gi = 0; gi < NG; ++gi) {
-          const int c0 = ntile * BN + gi * GCW;
-          if (p.g_patch)
-            tma_load_5d(base + MT * TILE_A + gi * TILE_G, &maps.g, bar_full(stage), c0, p.g_px, tx0, p.g_py,
-                        n * p.g_Hs + ty0);
-          else
-            tma_load_4d(base + MT * TILE_A + gi * TILE_G, &maps.g, bar_full(stage), c0, tx0, ty0, n);
-        }
-        if (++stage == stages) { stage = 0; phase ^= 1; }
+        if (++stage == S) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
+    // ================= MMA issuer =================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
       for (int i = 0; i < my_tiles; ++i) {
-        mbar_wait(bar_ready(stage), phase);
+        const int b = i & 1;
+        mbar_wait(bar_tready(b), (uint32_t)(i >> 1) & 1);
         tc_fence_after();
-        const uint32_t base = smem_base + (uint32_t)stage * STAGE_BYTES;
-        const uint32_t ahi = base, ghi = base + MT * TILE_A, alo = base + HI_BYTES, glo = alo + MT * TILE_A;
+        const uint32_t ahi = planes_u32 + (uint32_t)b * PLANES_BYTES, alo = ahi + WG_PLANE_A;
+        const uint32_t ghi = alo + WG_PLANE_A, glo = ghi + PLANE_G;
 #pragma unroll
         for (int ks = 0; ks < WG_PT / 8; ++ks) {
-          const uint32_t ao = ks * 8 * ROWA, go = ks * 8 * ROWG;
-          const uint64_t dah = umma_desc_mnmajor<ROWA>(ahi + ao, TILE_A), dal = umma_desc_mnmajor<ROWA>(alo + ao, TILE_A);
-          const uint64_t dgh = umma_desc_mnmajor<ROWG>(ghi + go, TILE_G), dgl = umma_desc_mnmajor<ROWG>(glo + go, TILE_G);
+          const uint64_t dah = umma_desc_kmajor<128>(ahi + ks * 32), dal = umma_desc_kmajor<128>(alo + ks * 32);
+          const uint64_t dgh = umma_desc_kmajor<128>(ghi + ks * 32), dgl = umma_desc_kmajor<128>(glo + ks * 32);
           tc_mma_tf32(tmem_base, dal, dgh, IDESC, (i | ks) != 0);
           tc_mma_tf32(tmem_base, dah, dgl, IDESC, 1);
           tc_mma_tf32(tmem_base, dah, dgh, IDESC, 1);
         }
-        tc_commit(bar_empty(stage));
+        tc_commit(bar_tempty(b));
         if (i == my_tiles - 1) tc_commit(bar_accf);
-        if (++stage == stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp < 6) {
-    const int t = threadIdx.x - 64;
+    // ================= transpose + split =================
+    const int t = threadIdx.x - 64;               // 0..127 ; pixel = t % 32, channel-quad lane = t / 32
+    const int px = t & 31, ql = t >> 5;
+    float gsum[GI][4];
+#pragma unroll
+    for (int i = 0; i < GI; ++i) { gsum[i][0] = gsum[i][1] = gsum[i][2] = gsum[i][3] = 0.f; }
     int stage = 0;
     uint32_t phase = 0;
-    // only the TMA-written part is split: active A tiles and the G tiles
-    const int a_chunks = n_active * TILE_A / 16, g_first = MT * TILE_A / 16, g_chunks = NG * TILE_G / 16;
-    for (int i = 0; i < my_tiles; ++i) {
-      mbar_wait(bar_full(stage), phase);
-      float4* hi = reinterpret_cast<float4*>(smem + (size_t)stage * STAGE_BYTES);
-      float4* lo = reinterpret_cast<float4*>(smem + (size_t)stage * STAGE_BYTES + HI_BYTES);
-      for (int q = t; q < a_chunks + g_chunks; q += 128) {
-        const int idx = q < a_chunks ? q : g_first + (q - a_chunks);
-        const float4 v = hi[idx];
-        float4 h, l;
-        h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-        l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-        hi[idx] = h;
-        lo[idx] = l;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int b = it & 1;
+      mbar_wait(bar_rfull(stage), phase);
+      mbar_wait(bar_tempty(b), ((uint32_t)(it >> 1) & 1) ^ 1);   // MMAs of two stages ago are done with planes b
+      const uint8_t* rbase = raw + (size_t)stage * p.raw_stage_bytes;
+      uint8_t* pl = planes + (size_t)b * PLANES_BYTES;
+      for (int i = 0; i < n_pieces; ++i) {
+        const WgPiece pc = pieces[i];
+        const int nq = pc.w >> 2;                                 // channel quads of this piece
+        uint8_t* hi = pl + (pc.is_g ? 2 * WG_PLANE_A : 0);
+        const int lo_off = pc.is_g ? PLANE_G : WG_PLANE_A;
+        for (int cq = ql; cq < nq; cq += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(rbase + pc.raw_off + (size_t)px * pc.w * 4 +
+                                                            wg_raw_chunk(pc.w, px, cq) * 16);
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+          if (pc.is_g) {
+            const int gi = ((pc.row >> 2) + cq) >> 2;             // this thread's quads are ql, ql+4, ...
+#pragma unroll
+            for (int i = 0; i < GI; ++i)
+              if (gi == i) { gsum[i][0] += v.x; gsum[i][1] += v.y; gsum[i][2] += v.z; gsum[i][3] += v.w; }
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int row = pc.row + cq * 4 + e;
+            // K-major SWIZZLE_128B: 16-byte chunk index XOR (row % 8)
+            const int o = row * 128 + ((((px >> 2) ^ (row & 7)) << 4) | ((px & 3) << 2));
+            const float h = tf32_rna(vv[e]);
+            *reinterpret_cast<float*>(hi + o) = h;
+            *reinterpret_cast<float*>(hi + lo_off + o) = tf32_rna(vv[e] - h);
+          }
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(bar_ready(stage));
-      if (++stage == stages) { stage = 0; phase ^= 1; }
+      mbar_arrive(bar_tready(b));
+      mbar_arrive(bar_rempty(stage));
+      if (++stage == S) { stage = 0; phase ^= 1; }
     }
+    // bias partial: reduce the 32 pixel lanes of each warp in a fixed butterfly order
+#pragma unroll
+    for (int i = 0; i < GI; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float v = gsum[i][e];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const int q = ql + 4 * i;                                 // this thread's i-th G quad
+        if (px == 0 && q < GQ) bias_part[0][q * 4 + e] = v;
+      }
   } else {
-    // epilogue: one fp32 partial [128 x BN] per CTA -> workspace rows in the reduce kernel's numbering
+    // epilogue warps idle until the accumulation is complete
+  }
+  // ---- all partials are ready: accumulator (after accf) and bias sums ----
+  __syncthreads();
+  if (warp >= 6) {
     const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;            // M row
-    const int gi = r / KBW, j = r - gi * KBW;
-    int row = -1;
-    if (gi < n_active) {
-      const int g = g0 + gi;
-      const int tap = g / p.chunks_per_tap;
-      int ch = g - tap * p.chunks_per_tap;
-      int s = 0;
-      while (s < p.nseg - 1 && ch >= p.seg_chunks[s]) { ch -= p.seg_chunks[s]; ++s; }
-      row = tap * p.ctot + p.seg_coff[s] + ch * KBW + j;
-    } else if (has_bias && gi == n_active && j == 0) {
-      row = p.bias_row;
-    }
+    const int r = quarter * 32 + lane;            // accumulator row
+    const int k = k_lo + r;
     if (my_tiles > 0) {
       mbar_wait(bar_accf, 0);
       tc_fence_after();
     }
-    float* dst = p.ws + ((size_t)blockIdx.x * p.KD_pad + (row >= 0 ? row : 0)) * p.ld + ntile * BN;
+    float* dst = p.ws + ((size_t)blockIdx.x * p.KD_pad + (k < k_hi ? k : 0)) * p.ld + ntile * BN;
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 16) {
@@ -823,7 +854,7 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
 #pragma unroll
         for (int e = 0; e < 16; ++e) v[e] = 0u;
       }
-      if (row >= 0) {
+      if (k < k_hi) {
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4)
           *reinterpret_cast<float4*>(dst + c0 + q4 * 4) =
@@ -831,6 +862,8 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
                           __uint_as_float(v[q4 * 4 + 3]));
       }
     }
+    if (mtile == 0 && r < BN)
+      p.ws[((size_t)blockIdx.x * p.KD_pad + p.bias_row) * p.ld + ntile * BN + r] = my_tiles > 0 ? bias_part[0][r] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -842,7 +875,7 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
 
 struct WgPlan {
   bool ok;
-  int bn, kbw, gcw;
+  int bn;
   WgParams p;
   size_t smem_bytes;
   int nsplit;
@@ -851,18 +884,15 @@ struct WgPlan {
 static WgPlan wg_plan(const GConvK& k) {
   WgPlan pl;
   memset(&pl, 0, sizeof(pl));
-  if (k.d2s || k.M == 0 || k.Cout % 16 != 0 || k.Cout > 512) return pl;
-  pl.kbw = 32;
+  if (k.d2s || k.M == 0 || k.Cout % 16 != 0) return pl;
   int ctot = 0;
   for (int s = 0; s < k.nseg; ++s) {
     const Seg& sg = k.seg[s];
-    if (sg.C % 16 != 0 || sg.sub != nullptr || sg.bcast || !aligned16(sg.ptr)) return pl;
-    if (sg.C % 32 != 0) pl.kbw = 16;
+    if (sg.C % 4 != 0 || sg.sub != nullptr || sg.bcast || !aligned16(sg.ptr)) return pl;
     ctot += sg.C;
   }
   if (k.ay.nu < 1 || k.ax.nu < 1) return pl;
-  pl.gcw = (k.Cout % 32 == 0) ? 32 : 16;
-  pl.bn = k.Cout % 128 == 0 ? 128 : k.Cout % 64 == 0 ? 64 : k.Cout % 32 == 0 ? 32 : 16;
+  pl.bn = k.Cout % 64 == 0 ? 64 : k.Cout % 32 == 0 ? 32 : 16;
   WgParams& p = pl.p;
   p.N = k.N; p.Hl = k.ay.nt; p.Wl = k.ax.nt;
   if (p.Wl >= WG_PT) {
@@ -875,7 +905,7 @@ static WgPlan wg_plan(const GConvK& k) {
   }
   p.tiles_x = p.Wl / p.TW; p.tiles_y = p.Hl / p.TH;
   const long long tt = (long long)p.N * p.tiles_x * p.tiles_y;
-  if (tt > (1ll << 30) || tt < 8) return pl;
+  if (tt > (1ll << 30) || tt < 4) return pl;
   p.total_ptiles = (int)tt;
   const bool stride1 = (k.ay.it == 1 && k.ax.it == 1);
   const bool patch = (k.ay.it > 1 && k.ay.it == k.ax.it && k.ay.iu == 1 && k.ax.iu == 1 && k.ay.i0 == 0 && k.ax.i0 == 0 &&
@@ -884,7 +914,6 @@ static WgPlan wg_plan(const GConvK& k) {
   p.mode_patch = patch ? 1 : 0;
   p.ux_step = k.ax.iu; p.x_off = k.ax.i0; p.uy_step = k.ay.iu; p.y_off = k.ay.i0;
   p.Hs = patch ? k.Hin / k.ay.it : 0;
-  // G (= dz) lives on the output grid; the lattice is that grid (os == 1) or a strided sub-grid (phases)
   if (k.ay.os != k.ax.os) return pl;
   if (k.ay.os == 1) {
     if (k.ay.o0 != 0 || k.ax.o0 != 0 || k.Hout != p.Hl || k.Wout != p.Wl) return pl;
@@ -894,33 +923,52 @@ static WgPlan wg_plan(const GConvK& k) {
     if (k.Hout != p.Hl * os || k.Wout != p.Wl * os) return pl;
     p.g_patch = 1; p.g_py = k.ay.o0; p.g_px = k.ax.o0; p.g_Hs = k.Hout / os;
   }
-  p.ntap_x = k.ax.nu;
-  p.nseg = k.nseg;
-  p.chunks_per_tap = 0;
+  p.ntap_x = k.ax.nu; p.nseg = k.nseg; p.ctot = ctot;
+  p.Kd = k.ay.nu * k.ax.nu * ctot;
+  if (p.Kd < 16) return pl;
   int coff = 0;
-  for (int s = 0; s < k.nseg; ++s) {
-    p.seg_chunks[s] = k.seg[s].C / pl.kbw; p.chunks_per_tap += p.seg_chunks[s];
-    p.seg_coff[s] = coff; coff += k.seg[s].C;
-  }
-  p.ctot = ctot;
-  p.n_groups = k.ay.nu * k.ax.nu * p.chunks_per_tap;
-  p.mt_groups = TC_BM / pl.kbw;
-  p.n_mtiles = (p.n_groups + 1 + p.mt_groups - 1) / p.mt_groups;     // +1: the all-ones (bias) group
-  p.ng = pl.bn / pl.gcw;
+  for (int s = 0; s < k.nseg; ++s) { p.seg_C[s] = k.seg[s].C; p.seg_coff[s] = coff; coff += k.seg[s].C; }
+  p.n_mtiles = (p.Kd + TC_BM - 1) / TC_BM;
   p.n_ntiles = k.Cout / pl.bn;
   p.Cout = k.Cout; p.ld = k.Cout;
-  p.bias_row = k.ay.nu * k.ax.nu * ctot;
-  p.KD_pad = p.bias_row + 4;
-  const size_t stage_bytes = 2 * ((size_t)p.mt_groups * WG_PT * pl.kbw * 4 + (size_t)p.ng * WG_PT * pl.gcw * 4);
-  int st = (int)((227 * 1024 - 2048) / stage_bytes);
+  p.bias_row = p.Kd; p.KD_pad = p.Kd + 4;
+  // raw stage: worst case 32 A pieces of 4 channels (1 KB each after rounding) or 4 of 32 (4 KB each): <= 32 KB; G <= 8 KB
+  p.raw_stage_bytes = 32 * 1024 + 8 * 1024;
+  {
+    // tighter bound: pieces never exceed max(16 KB of payload, #pieces KB); recompute exactly for M tile 0 (the fullest)
+    int bytes = 0, kk = 0;
+    const int k_hi = p.Kd < TC_BM ? p.Kd : TC_BM;
+    int worst = 0;
+    for (int mt = 0; mt < p.n_mtiles; ++mt) {
+      bytes = 0; kk = mt * TC_BM;
+      const int hi = (kk + TC_BM < p.Kd) ? kk + TC_BM : p.Kd;
+      while (kk < hi) {
+        const int tap = kk / ctot, c = kk - tap * ctot;
+        int s = 0;
+        while (s < k.nseg - 1 && c >= p.seg_coff[s] + p.seg_C[s]) ++s;
+        int w = p.seg_C[s] - (c - p.seg_coff[s]);
+        if (w > 32) w = 32;
+        if (w > hi - kk) w = hi - kk;
+        w = w >= 32 ? 32 : w >= 16 ? 16 : w >= 8 ? 8 : 4;
+        bytes += (WG_PT * w * 4 + 1023) & ~1023;
+        kk += w;
+      }
+      if (bytes > worst) worst = bytes;
+    }
+    (void)k_hi;
+    const int gw = pl.bn < 32 ? pl.bn : 32;
+    worst += (pl.bn / gw) * ((WG_PT * gw * 4 + 1023) & ~1023);
+    p.raw_stage_bytes = worst;
+  }
+  const size_t planes = 2 * (2 * (size_t)WG_PLANE_A + 2 * (size_t)pl.bn * 128);
+  int st = (int)((227 * 1024 - 2048 - (long long)planes - 4096) / p.raw_stage_bytes);
   if (st > TC_MAX_STAGES) st = TC_MAX_STAGES;
   if (st < 2) return pl;
-  p.stages = st;
-  pl.smem_bytes = (size_t)st * stage_bytes + 1024;
-  // pixel split: fill the machine, at least 8 pixel tiles per CTA
+  p.raw_stages = st;
+  pl.smem_bytes = planes + (size_t)st * p.raw_stage_bytes + 1024;
   long long want = 148 / ((long long)p.n_mtiles * p.n_ntiles);
   if (want < 1) want = 1;
-  if (want > tt / 8) want = tt / 8;
+  if (want > tt / 4) want = tt / 4;
   if (want < 1) want = 1;
   pl.nsplit = (int)want;
   if (get_encode() == nullptr) return pl;
@@ -935,20 +983,42 @@ size_t tc_wgrad_ws_floats(const GConvK& k) {
   return pl.ok ? (size_t)pl.nsplit * pl.p.KD_pad * pl.p.ld : 0;
 }
 
-template <int BN, int KBW, int GCW>
+template <int BN>
 static int wg_launch(const WgMaps& maps, const WgPlan& pl, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<BN, KBW, GCW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024 - 1024);
+    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096);
     if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   dim3 grid(pl.nsplit, pl.p.n_mtiles, pl.p.n_ntiles);
-  tc_wgrad_kernel<BN, KBW, GCW><<<grid, TC_THREADS, pl.smem_bytes, st>>>(maps, pl.p);
+  tc_wgrad_kernel<BN><<<grid, TC_THREADS, pl.smem_bytes, st>>>(maps, pl.p);
   NLT_CUDA_LAUNCH_CHECK("tc_wgrad_kernel");
   __atomic_add_fetch(&g_tc_launches, 1ull, __ATOMIC_RELAXED);
   return NLT_OK;
+}
+
+// raw [pixels x w channels] tile of an NHWC tensor, swizzled by its row bytes (bank-conflict-free transposing reads)
+static CUresult wg_encode(EncodeTiledFn enc, CUtensorMap* m, const float* ptr, int C, int W, int H, int N, int w, int TW,
+                          int TH, int patch_s) {
+  const CUtensorMapSwizzle swz = w == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : w == 16 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                 : w == 8 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  const cuuint64_t c = C, ww = W, h = H, n = N;
+  if (patch_s > 1) {
+    const cuuint64_t st_ = patch_s;
+    cuuint64_t dims[5] = {c, st_, ww / st_, st_, n * (h / st_)};
+    cuuint64_t strides[4] = {c * 4, st_ * c * 4, ww * c * 4, st_ * ww * c * 4};
+    cuuint32_t box[5] = {(cuuint32_t)w, 1, (cuuint32_t)TW, 1, (cuuint32_t)TH};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  cuuint64_t dims[4] = {c, ww, h, n};
+  cuuint64_t strides[3] = {c * 4, ww * c * 4, h * ww * c * 4};
+  cuuint32_t box[4] = {(cuuint32_t)w, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
 int launch_tc_wgrad(const GConvK& k, const float* G, float* ws, WgradK* w, size_t* KD_pad, cudaStream_t st) {
@@ -957,66 +1027,32 @@ int launch_tc_wgrad(const GConvK& k, const float* G, float* ws, WgradK* w, size_
   NLT_CHECK_ARG(aligned16(G), "dz must be 16-byte aligned");
   EncodeTiledFn enc = get_encode();
   WgMaps maps;
+  memset(&maps, 0, sizeof(maps));
   const WgParams& p = pl.p;
-  for (int s = 0; s < k.nseg; ++s) {
-    const Seg& sg = k.seg[s];
-    const cuuint64_t C = sg.C, W = k.Win, H = k.Hin, N = k.N;
-    const CUtensorMapSwizzle swz = pl.kbw == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-    CUresult r;
-    if (p.mode_patch) {
-      const cuuint64_t st_ = k.ay.it;
-      cuuint64_t dims[5] = {C, st_, W / st_, st_, N * (H / st_)};
-      cuuint64_t strides[4] = {C * 4, st_ * C * 4, W * C * 4, st_ * W * C * 4};
-      cuuint32_t box[5] = {(cuuint32_t)pl.kbw, 1, (cuuint32_t)p.TW, 1, (cuuint32_t)p.TH};
-      cuuint32_t es[5] = {1, 1, 1, 1, 1};
-      r = enc(&maps.a[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)sg.ptr, dims, strides, box, es,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    } else {
-      cuuint64_t dims[4] = {C, W, H, N};
-      cuuint64_t strides[3] = {C * 4, W * C * 4, H * W * C * 4};
-      cuuint32_t box[4] = {(cuuint32_t)pl.kbw, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
-      cuuint32_t es[4] = {1, 1, 1, 1};
-      r = enc(&maps.a[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)sg.ptr, dims, strides, box, es,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  static const int widths[4] = {4, 8, 16, 32};
+  for (int s = 0; s < k.nseg; ++s)
+    for (int wi = 0; wi < 4; ++wi) {
+      if (widths[wi] > k.seg[s].C) continue;
+      CUresult r = wg_encode(enc, &maps.a[s][wi], k.seg[s].ptr, k.seg[s].C, k.Win, k.Hin, k.N, widths[wi], p.TW, p.TH,
+                             p.mode_patch ? k.ay.it : 1);
+      if (r != CUDA_SUCCESS) return set_err(NLT_ERR_CUDA, "cuTensorMapEncodeTiled(wgrad A %d/%d) failed: %d", s, widths[wi], (int)r);
     }
-    if (r != CUDA_SUCCESS) return set_err(NLT_ERR_CUDA, "cuTensorMapEncodeTiled(wgrad A %d) failed: %d", s, (int)r);
-  }
   {
-    const cuuint64_t C = k.Cout, W = k.Wout, H = k.Hout, N = k.N;
-    const CUtensorMapSwizzle swz = pl.gcw == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-    CUresult r;
-    if (p.g_patch) {
-      const cuuint64_t st_ = k.ay.os;
-      cuuint64_t dims[5] = {C, st_, W / st_, st_, N * (H / st_)};
-      cuuint64_t strides[4] = {C * 4, st_ * C * 4, W * C * 4, st_ * W * C * 4};
-      cuuint32_t box[5] = {(cuuint32_t)pl.gcw, 1, (cuuint32_t)p.TW, 1, (cuuint32_t)p.TH};
-      cuuint32_t es[5] = {1, 1, 1, 1, 1};
-      r = enc(&maps.g, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)G, dims, strides, box, es,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    } else {
-      cuuint64_t dims[4] = {C, W, H, N};
-      cuuint64_t strides[3] = {C * 4, W * C * 4, H * W * C * 4};
-      cuuint32_t box[4] = {(cuuint32_t)pl.gcw, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
-      cuuint32_t es[4] = {1, 1, 1, 1};
-      r = enc(&maps.g, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)G, dims, strides, box, es,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    }
+    const int gw = pl.bn < 32 ? pl.bn : 32;
+    CUresult r = wg_encode(enc, &maps.g, G, k.Cout, k.Wout, k.Hout, k.N, gw, p.TW, p.TH, p.g_patch ? k.ay.os : 1);
     if (r != CUDA_SUCCESS) return set_err(NLT_ERR_CUDA, "cuTensorMapEncodeTiled(wgrad G) failed: %d", (int)r);
   }
   pl.p.ws = ws;
-  // descriptor for the shared reduce stage
   w->g = k;
   w->GS = p.ctot / 4;
   w->KG = k.ay.nu * k.ax.nu * w->GS + 1;
   w->ld = p.ld; w->nsplit = pl.nsplit; w->pix_per_split = 0;
   *KD_pad = (size_t)p.KD_pad;
-#define NLT_WG(BN_, KBW_, GCW_) return wg_launch<BN_, KBW_, GCW_>(maps, pl, st)
-  if (pl.kbw == 32) {
-    switch (pl.bn) { case 128: NLT_WG(128, 32, 32); case 64: NLT_WG(64, 32, 32); case 32: NLT_WG(32, 32, 32); default: NLT_WG(16, 32, 16); }
-  } else {
-    switch (pl.bn) { case 128: NLT_WG(128, 16, 32); case 64: NLT_WG(64, 16, 32); case 32: NLT_WG(32, 16, 32); default: NLT_WG(16, 16, 16); }
+  switch (pl.bn) {
+    case 64: return wg_launch<64>(maps, pl, st);
+    case 32: return wg_launch<32>(maps, pl, st);
+    default: return wg_launch<16>(maps, pl, st);
   }
-#undef NLT_WG
 }
 
 bool tc_applicable(const GConvK& k) { return tc_plan(k).ok; }

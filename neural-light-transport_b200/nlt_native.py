@@ -42,6 +42,7 @@ _lib = None
 _SIGS = {
     'nlt_version': (C.c_char_p, []),
     'nlt_last_error': (C.c_char_p, []),
+    'nlt_set_option': (C.c_int, [C.c_char_p, C.c_int]),
     'nlt_launch_count': (C.c_uint64, []),
     'nlt_tc_launch_count': (C.c_uint64, []),
     'nlt_gconv_fwd': (C.c_int, [C.POINTER(GConvDesc), C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int,
@@ -114,3 +115,8 @@ def launch_count():
 def tc_launch_count():
     """tcgen05 tensor-core kernel launches so far."""
     return int(lib().nlt_tc_launch_count())
+
+
+def set_option(name, value):
+    """'tc' / 'tc_wgrad': 1 = tcgen05 3xTF32 kernels where eligible (default), 0 = fp32-FMA kernels only."""
+    check(lib().nlt_set_option(name.encode(), int(value)))

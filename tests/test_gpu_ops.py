@@ -117,6 +117,45 @@ def test_gconv_forward_backward(kind, k, s, H, W, segc, cout, act):
         _close(a.grad, want, rtol=1e-4, atol=1e-4)
 
 
+TC_SHAPES = [g for g in GEOMS if all(c % 16 == 0 for c in g[5]) and g[6] % 16 == 0 and g[3] * g[4] >= 256]
+
+
+@pytest.mark.parametrize('kind,k,s,H,W,segc,cout', TC_SHAPES)
+def test_tensor_core_vs_fp32_kernels(kind, k, s, H, W, segc, cout):
+    """A/B on identical inputs: tcgen05 3xTF32 kernels (forward, input gradients with beta + mask, weight /
+    bias gradients) against the fp32-FMA kernels of the same library: relative Frobenius error <= 5e-6."""
+    engine, nat = _mods()
+    dev = torch.device('cuda')
+    torch.manual_seed(3)
+    N = 2
+    xs = [torch.randn(N, H, W, c, device=dev) for c in segc]
+    dzs = None
+    res = {}
+    for mode in ('tc', 'fp32'):
+        nat.set_option('tc', 1 if mode == 'tc' else 0)
+        L = engine.ConvLayer(kind, k, s, cout, 'leakyrelu')
+        L.build(sum(segc), dev, torch.Generator().manual_seed(1))
+        L.bias.copy_(torch.linspace(-0.1, 0.1, cout, device=dev))
+        acts = [engine.Act(x, act='leakyrelu', needs_grad=True) for x in xs]
+        tape = engine.Tape()
+        t0 = nat.tc_launch_count()
+        y = L.forward([engine.Seg(a) for a in acts], tape)
+        if dzs is None:
+            dzs = torch.randn_like(y.t)
+        y.grad = dzs.clone()
+        tape.backward()
+        res[mode] = dict(y=y.t.clone(), gk=L.gkernel.clone(), gb=L.gbias.clone(), gx=[a.grad.clone() for a in acts],
+                         tc=nat.tc_launch_count() - t0)
+    nat.set_option('tc', 1)
+    assert res['fp32']['tc'] == 0 and res['tc']['tc'] >= 1, res['tc']['tc']
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+    assert rel(res['tc']['y'], res['fp32']['y']) <= 5e-6
+    assert rel(res['tc']['gk'], res['fp32']['gk']) <= 5e-6
+    assert rel(res['tc']['gb'], res['fp32']['gb']) <= 5e-6
+    for a, b in zip(res['tc']['gx'], res['fp32']['gx']):
+        assert rel(a, b) <= 5e-6
+
+
 def test_tensor_core_path_is_taken_and_matches_fp32_path():
     """Eligible shapes must run on the tcgen05 kernel (launch counter moves) and agree with the
     fp32-FMA kernel of the same library to 3xTF32 accuracy (<= 4e-6 relative to the output scale)."""
