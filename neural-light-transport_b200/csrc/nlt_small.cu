@@ -26,25 +26,26 @@ constexpr int PW_KMAX = 64;
 constexpr int PW_THREADS = 256;
 
 bool pw_conv_applicable(const GConvK& k) {
-  if (k.d2s) return false;
   if (k.ay.nu != 1 || k.ax.nu != 1) return false;
-  // identity pixel map: input coordinate == lattice coordinate == output coordinate
+  // identity pixel map: input coordinate == lattice coordinate (== output coordinate unless depth-to-space)
   const AxisMap* ax[2] = {&k.ay, &k.ax};
   for (int i = 0; i < 2; ++i) {
     const AxisMap& a = *ax[i];
-    if (a.it != 1 || a.i0 + a.iu * 0 != 0 || a.o0 != 0 || a.os != 1) return false;
+    if (a.it != 1 || a.i0 != 0 || a.o0 != 0 || a.os != 1) return false;
   }
-  if (k.ay.nt != k.Hin || k.ax.nt != k.Win || k.Hout != k.Hin || k.Wout != k.Win) return false;
+  if (k.ay.nt != k.Hin || k.ax.nt != k.Win) return false;
+  if (!k.d2s && (k.Hout != k.Hin || k.Wout != k.Win)) return false;
   int ctot = 0;
   for (int s = 0; s < k.nseg; ++s) ctot += k.seg[s].C;
-  return ctot <= PW_KMAX && k.Cout <= 16;
+  // GEMM columns: Cout (d2s: k*k*cout_true, a multiple of 4)
+  return ctot <= PW_KMAX && k.Cout <= 64 && (k.Cout <= 16 || k.Cout % 4 == 0);
 }
 
 template <int NQ, int R>
 __global__ void __launch_bounds__(PW_THREADS)
 pw_conv_kernel(const GConvK g, const float* __restrict__ bias, const int act, const float beta,
                const float* __restrict__ mask_y, const int mask_act, float* __restrict__ out) {
-  __shared__ float4 Ws[PW_KMAX * NQ];   // [k][quad] : 4 consecutive output channels
+  __shared__ float4 Ws[PW_KMAX * NQ];   // [k][quad] : 4 consecutive GEMM columns
   const int tid = threadIdx.x;
   const int tap = (g.ay.d0) * g.kw + g.ax.d0;
   int K = 0;
@@ -55,7 +56,9 @@ pw_conv_kernel(const GConvK g, const float* __restrict__ bias, const int act, co
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int n = q * 4 + e;
-      v[e] = n < g.Cout ? __ldg(g.w + (long long)tap * g.wt + (long long)k * g.wc + (long long)n * g.wn) : 0.f;
+      int t = tap, nn = n;
+      if (g.d2s) { t = n / g.cout_true; nn = n - t * g.cout_true; }
+      v[e] = n < g.Cout ? __ldg(g.w + (long long)t * g.wt + (long long)k * g.wc + (long long)nn * g.wn) : 0.f;
     }
     Ws[idx] = make_float4(v[0], v[1], v[2], v[3]);
   }
@@ -65,9 +68,19 @@ pw_conv_kernel(const GConvK g, const float* __restrict__ bias, const int act, co
   const int q = tid % NQ;
   const uint32_t pbase = (uint32_t)blockIdx.x * (PPB * R) + tid / NQ;
   const uint32_t hw = g.div_yx.d;
+  // destination channel quad / tap of this thread's GEMM columns
+  int qtap = 0, qcb = q * 4;
+  if (g.d2s) { qtap = (q * 4) / g.cout_true; qcb = q * 4 - qtap * g.cout_true; }
+  const int qdy = g.d2s ? qtap / g.d2s_s : 0, qdx = g.d2s ? qtap - qdy * g.d2s_s : 0;
   float b4[4];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) b4[e] = (bias != nullptr && q * 4 + e < g.Cout) ? __ldg(bias + q * 4 + e) : 0.f;
+  for (int e = 0; e < 4; ++e) b4[e] = (bias != nullptr && q * 4 + e < g.Cout) ? __ldg(bias + qcb + e) : 0.f;
+  auto out_off = [&](uint32_t pp) -> size_t {
+    if (!g.d2s) return (size_t)pp * g.Cout + q * 4;
+    int n, ty, tx;
+    decode_pixel(g, pp, n, ty, tx);
+    return (((size_t)n * g.Hout + ty * g.d2s_s + qdy) * g.Wout + tx * g.d2s_s + qdx) * g.cout_true + qcb;
+  };
 
   uint32_t p[R];
   bool ok[R];
@@ -138,14 +151,14 @@ pw_conv_kernel(const GConvK g, const float* __restrict__ bias, const int act, co
     }
   }
 
-  const bool vec_out = (g.Cout % 4 == 0) && aligned16(out) && (mask_y == nullptr || aligned16(mask_y));
+  const bool vec_out = (g.cout_true % 4 == 0) && aligned16(out) && (mask_y == nullptr || aligned16(mask_y));
   float4 oldv[R], yv[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {   // batch the read-modify-write operands before the first store
     oldv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
     yv[r] = make_float4(1.f, 1.f, 1.f, 1.f);
     if (ok[r] && q * 4 < g.Cout && vec_out) {
-      const size_t ob = (size_t)p[r] * g.Cout + q * 4;
+      const size_t ob = out_off(p[r]);
       if (beta != 0.f) oldv[r] = *reinterpret_cast<const float4*>(out + ob);
       if (mask_y != nullptr) yv[r] = ld4(mask_y + ob);
     }
@@ -153,7 +166,7 @@ pw_conv_kernel(const GConvK g, const float* __restrict__ bias, const int act, co
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     if (!ok[r] || q * 4 >= g.Cout) continue;
-    const size_t ob = (size_t)p[r] * g.Cout + q * 4;
+    const size_t ob = out_off(p[r]);
     float v[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) v[e] = act_fwd(acc[r][e], act);
@@ -188,9 +201,15 @@ int launch_pw_conv(const GConvK& k, const float* bias, int act, float beta, cons
   } else if (nq == 2) {
     const unsigned grid = (k.M + PW_THREADS / 2 * R - 1) / (PW_THREADS / 2 * R);
     pw_conv_kernel<2, R><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
-  } else {
+  } else if (nq <= 4) {
     const unsigned grid = (k.M + PW_THREADS / 4 * R - 1) / (PW_THREADS / 4 * R);
     pw_conv_kernel<4, R><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
+  } else if (nq <= 8) {
+    const unsigned grid = (k.M + PW_THREADS / 8 * R - 1) / (PW_THREADS / 8 * R);
+    pw_conv_kernel<8, R><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
+  } else {
+    const unsigned grid = (k.M + PW_THREADS / 16 * R - 1) / (PW_THREADS / 16 * R);
+    pw_conv_kernel<16, R><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
   }
   NLT_CUDA_LAUNCH_CHECK("pw_conv_kernel");
   return NLT_OK;

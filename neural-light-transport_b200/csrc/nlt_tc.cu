@@ -490,7 +490,8 @@ static TcPlan tc_plan(const GConvK& k) {
   }
   const int TC_KB = pl.kbw;
   if (!aligned16(k.w)) { /* weights are only read by the pack kernel: no alignment needed */ }
-  if (k.ay.nu * k.ax.nu * ctot < 16) return pl;
+  // with less than 64 contraction terms the op is a pure stream: the pointwise / fp32 kernels are faster there
+  if (k.ay.nu * k.ax.nu * ctot < 64) return pl;
   if (k.ay.nu < 1 || k.ax.nu < 1) return pl;
   TcParams& p = pl.p;
   p.N = k.N; p.Hl = k.ay.nt; p.Wl = k.ax.nt;
@@ -925,7 +926,7 @@ static WgPlan wg_plan(const GConvK& k) {
   }
   p.ntap_x = k.ax.nu; p.nseg = k.nseg; p.ctot = ctot;
   p.Kd = k.ay.nu * k.ax.nu * ctot;
-  if (p.Kd < 16) return pl;
+  if (p.Kd < 128) return pl;      // measured: below one full M tile the warp-stream fp32 kernel wins
   int coff = 0;
   for (int s = 0; s < k.nseg; ++s) { p.seg_C[s] = k.seg[s].C; p.seg_coff[s] = coff; coff += k.seg[s].C; }
   p.n_mtiles = (p.Kd + TC_BM - 1) / TC_BM;
