@@ -195,7 +195,7 @@ def run_b200(args):
     graphed = None if args.no_graph else trainvali.GraphedTrainStep(strategy, model, opt, global_bs)
 
     def step(batch):
-        if graphed is not None and not engine.PROF.enabled:
+        if graphed is not None and not getattr(engine.PROF, 'force_eager', False):
             return graphed(batch)
         return trainvali.distributed_train_step(strategy, model, batch, opt, global_bs)
 
@@ -261,10 +261,13 @@ def run_b200(args):
 
     # ---- roofline leg: per-call CUDA events (separate pass, not the timed value) ----
     roof = None
+    # every rank runs these steps (they contain the gradient all-reduce); only rank 0 records events
+    engine.PROF.enabled = (rank == 0)
+    engine.PROF.force_eager = True
+    for i in range(2):
+        step(resident[i % 2])
+    engine.PROF.force_eager = False
     if rank == 0:
-        engine.PROF.enabled = True
-        for i in range(2):
-            step(resident[i % 2])
         summ = engine.PROF.summary()
         engine.PROF.enabled = False
         total_ms = sum(v['ms'] for v in summ.values())
