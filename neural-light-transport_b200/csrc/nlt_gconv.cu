@@ -527,14 +527,21 @@ __global__ void gconv_wgrad_reduce_kernel(const WgradK w, const float* __restric
     decode_kgroup(w, kg, uy, ux, s, c);
     float* dst = nullptr;
     int accumulate = acc_w;
+    int ntaps_sum = 1;                 // d2s bias: one output channel collects its column in every tap
     if (s == -1) {
-      if (e == 0 && db != nullptr) { dst = db + n; accumulate = acc_b; }
+      if (e == 0 && db != nullptr && (!w.g.d2s || n < w.g.cout_true)) {
+        dst = db + n; accumulate = acc_b;
+        if (w.g.d2s) ntaps_sum = w.g.d2s_s * w.g.d2s_s;
+      }
     } else if (s >= 0 && c + e < w.g.seg[s].C) {
-      const int tap = (w.g.ay.d0 + w.g.ay.ds * uy) * w.g.kw + (w.g.ax.d0 + w.g.ax.ds * ux);
-      dst = dW + (long long)tap * w.g.wt + (long long)(w.g.seg[s].coff + c + e) * w.g.wc + (long long)n * w.g.wn;
+      int tap = (w.g.ay.d0 + w.g.ay.ds * uy) * w.g.kw + (w.g.ax.d0 + w.g.ax.ds * ux), nn = n;
+      if (w.g.d2s) { tap = n / w.g.cout_true; nn = n - tap * w.g.cout_true; }
+      dst = dW + (long long)tap * w.g.wt + (long long)(w.g.seg[s].coff + c + e) * w.g.wc + (long long)nn * w.g.wn;
     }
     if (dst == nullptr) continue;
-    const float* src = ws + (size_t)k * w.ld + n;
+    float total_sum = 0.f;
+    for (int tp = 0; tp < ntaps_sum; ++tp) {
+    const float* src = ws + (size_t)k * w.ld + n + tp * w.g.cout_true;
     const size_t stride = KD_pad * w.ld;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     int sp = 0;
@@ -543,7 +550,9 @@ __global__ void gconv_wgrad_reduce_kernel(const WgradK w, const float* __restric
       s2 += src[(size_t)(sp + 2) * stride]; s3 += src[(size_t)(sp + 3) * stride];
     }
     for (; sp < w.nsplit; ++sp) s0 += src[(size_t)sp * stride];
-    const float sum = (s0 + s1) + (s2 + s3);
+    total_sum += (s0 + s1) + (s2 + s3);
+    }
+    const float sum = total_sum;
     *dst = accumulate ? (*dst + sum) : sum;
   }
 }
@@ -657,7 +666,8 @@ int nlt_gconv_fwd(const nlt_gconv_desc* d, const float* bias, int act, float bet
 int64_t nlt_gconv_wgrad_workspace_bytes(const nlt_gconv_desc* d) {
   GConvK ph[16];
   int np = 0;
-  if (build_phases(d, ph, &np) != NLT_OK) return -1;
+  if (build_phases(d, ph, &np, /*allow_d2s=*/true) != NLT_OK) return -1;
+  if (np == 1 && ph[0].d2s && !wgrad_small_applicable(ph[0]) && build_phases(d, ph, &np, false) != NLT_OK) return -1;
   size_t mx = 0;
   for (int i = 0; i < np; ++i) {
     if (ph[i].M == 0) continue;
@@ -673,7 +683,9 @@ int nlt_gconv_wgrad(const nlt_gconv_desc* d, const float* G, float* dW, float* d
                     void* workspace, int64_t workspace_bytes, void* stream) {
   GConvK ph[16];
   int np = 0;
-  int rc = build_phases(d, ph, &np);
+  int rc = build_phases(d, ph, &np, /*allow_d2s=*/true);
+  if (rc != NLT_OK) return rc;
+  if (np == 1 && ph[0].d2s && !wgrad_small_applicable(ph[0])) rc = build_phases(d, ph, &np, false);
   if (rc != NLT_OK) return rc;
   NLT_CHECK_ARG(G != nullptr && dW != nullptr && workspace != nullptr, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;

@@ -229,8 +229,10 @@ struct WsPlan {
 };
 
 static bool ws_plan(const GConvK& k, WsPlan& pl) {
-  if (k.d2s || k.Cout > 16 || k.M == 0) return false;
-  pl.nq = k.Cout <= 4 ? 1 : k.Cout <= 8 ? 2 : 4;
+  // depth-to-space form (transposed op with k == stride): ONE pass over the input lattice with
+  // N' = k*k*Cout gradient columns, instead of k*k phases that each re-read the whole input
+  if (k.Cout > 32 || k.M == 0 || (!k.d2s && k.Cout > 16)) return false;
+  pl.nq = k.Cout <= 4 ? 1 : k.Cout <= 8 ? 2 : k.Cout <= 16 ? 4 : 8;
   pl.kq = 32 / pl.nq;
   pl.GS = 0;
   for (int s = 0; s < k.nseg; ++s) pl.GS += (k.seg[s].C + 3) / 4;
@@ -238,8 +240,8 @@ static bool ws_plan(const GConvK& k, WsPlan& pl) {
   const int real = pl.KG - 1;
   int p = (real + pl.kq - 1) / pl.kq;
   if (p < 1) p = 1;
-  // instantiated: NQ=4: P in {1,2,4,5}; NQ=2: {1,2}; NQ=1: {1,2}
-  if (pl.nq == 4) { if (p == 3) p = 4; if (p > 5) return false; }
+  // instantiated: NQ=8: P in {1,2,4,5}; NQ=4: P in {1,2,4,5}; NQ=2: {1,2}; NQ=1: {1,2}
+  if (pl.nq >= 4) { if (p == 3) p = 4; if (p > 5) return false; }
   else if (p > 2) return false;
   pl.p = p;
   pl.ld = pl.nq * 4;
@@ -292,7 +294,7 @@ wgrad_small_kernel(const WgradK w, const float* __restrict__ G, float* __restric
       jflag[j] = (sg.vec ? 1 : 2) | (sg.bcast ? 4 : 0);
     }
   }
-  const bool g_vec = (g.Cout % 4 == 0) && aligned16(G);
+  const bool g_vec = (g.cout_true % 4 == 0) && aligned16(G);
 
   float acc[P][4][4];
   float gsum[4] = {0.f, 0.f, 0.f, 0.f};
@@ -313,8 +315,14 @@ wgrad_small_kernel(const WgradK w, const float* __restrict__ G, float* __restric
     if (m >= p_end) return;
     int n, ty, tx;
     decode_pixel(g, m, n, ty, tx);
-    const int oy = g.ay.o0 + g.ay.os * ty, ox = g.ax.o0 + g.ax.os * tx;
-    const size_t goff = (((size_t)n * g.Hout + oy) * g.Wout + ox) * g.Cout + nq * 4;
+    int oy = g.ay.o0 + g.ay.os * ty, ox = g.ax.o0 + g.ax.os * tx, cb = nq * 4;
+    if (g.d2s) {      // gradient column quad -> (tap, channel quad) of the up-sampled output pixel
+      const int tap = (nq * 4) / g.cout_true;
+      cb = nq * 4 - tap * g.cout_true;
+      const int dy = tap / g.d2s_s;
+      oy = ty * g.d2s_s + dy; ox = tx * g.d2s_s + (tap - dy * g.d2s_s);
+    }
+    const size_t goff = (((size_t)n * g.Hout + oy) * g.Wout + ox) * g.cout_true + cb;
     if (nq * 4 < g.Cout) {
       if (g_vec) {
         gv = ld4(G + goff);
@@ -628,7 +636,9 @@ int launch_wgrad_small(const GConvK& k, const float* G, float* ws, WgradK* w, si
   *KD_pad = pl.KD_pad;
   const unsigned grid = pl.nsplit;
 #define NLT_WS(NQ_, P_) wgrad_small_kernel<NQ_, P_, (P_ == 1 ? 8 : P_ == 2 ? 4 : 2)><<<grid, WS_THREADS, 0, st>>>(*w, G, ws)
-  if (pl.nq == 4) {
+  if (pl.nq == 8) {
+    if (pl.p == 1) NLT_WS(8, 1); else if (pl.p == 2) NLT_WS(8, 2); else if (pl.p == 4) NLT_WS(8, 4); else NLT_WS(8, 5);
+  } else if (pl.nq == 4) {
     if (pl.p == 1) NLT_WS(4, 1); else if (pl.p == 2) NLT_WS(4, 2); else if (pl.p == 4) NLT_WS(4, 4); else NLT_WS(4, 5);
   } else if (pl.nq == 2) {
     if (pl.p == 1) NLT_WS(2, 1); else NLT_WS(2, 2);
