@@ -514,46 +514,59 @@ gconv_wgrad_kernel(const WgradK w, const float* __restrict__ G, float* __restric
     }
 }
 
-// second stage: fixed-order sum over splits, scatter to the weight layout
-__global__ void gconv_wgrad_reduce_kernel(const WgradK w, const float* __restrict__ ws, size_t KD_pad,
-                                          float* __restrict__ dW, float* __restrict__ db, int acc_w, int acc_b) {
+// second stage: fixed-order sum over splits, scatter to the weight layout.
+// 256 threads = 32 split lanes x 8 outputs: every output is summed by 32 lanes (each over its own residue
+// class of splits, 2 independent chains), then combined in a fixed order through smem -> deterministic,
+// and the latency of walking up to ~1000 partials is spread over 32 lanes instead of one thread.
+__global__ void __launch_bounds__(256)
+gconv_wgrad_reduce_kernel(const WgradK w, const float* __restrict__ ws, size_t KD_pad,
+                          float* __restrict__ dW, float* __restrict__ db, int acc_w, int acc_b) {
+  __shared__ float red[32][9];
+  const int lane_o = threadIdx.x & 7, lane_s = threadIdx.x >> 3;
   const size_t total = (size_t)w.KG * 4 * w.g.Cout;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (size_t)gridDim.x * blockDim.x) {
-    const int n = (int)(idx % w.g.Cout);
-    const int k = (int)(idx / w.g.Cout);
-    const int kg = k >> 2, e = k & 3;
-    int uy, ux, s, c;
-    decode_kgroup(w, kg, uy, ux, s, c);
+  const size_t stride = KD_pad * w.ld;
+  for (size_t base = (size_t)blockIdx.x * 8; base < total; base += (size_t)gridDim.x * 8) {
+    const size_t idx = base + lane_o;
     float* dst = nullptr;
-    int accumulate = acc_w;
-    int ntaps_sum = 1;                 // d2s bias: one output channel collects its column in every tap
-    if (s == -1) {
-      if (e == 0 && db != nullptr && (!w.g.d2s || n < w.g.cout_true)) {
-        dst = db + n; accumulate = acc_b;
-        if (w.g.d2s) ntaps_sum = w.g.d2s_s * w.g.d2s_s;
+    int accumulate = acc_w, ntaps_sum = 1, n = 0, k = 0;
+    if (idx < total) {
+      n = (int)(idx % w.g.Cout);
+      k = (int)(idx / w.g.Cout);
+      const int kg = k >> 2, e = k & 3;
+      int uy, ux, s, c;
+      decode_kgroup(w, kg, uy, ux, s, c);
+      if (s == -1) {
+        // d2s bias: one output channel collects its column in every tap
+        if (e == 0 && db != nullptr && (!w.g.d2s || n < w.g.cout_true)) {
+          dst = db + n; accumulate = acc_b;
+          if (w.g.d2s) ntaps_sum = w.g.d2s_s * w.g.d2s_s;
+        }
+      } else if (s >= 0 && c + e < w.g.seg[s].C) {
+        int tap = (w.g.ay.d0 + w.g.ay.ds * uy) * w.g.kw + (w.g.ax.d0 + w.g.ax.ds * ux), nn = n;
+        if (w.g.d2s) { tap = n / w.g.cout_true; nn = n - tap * w.g.cout_true; }
+        dst = dW + (long long)tap * w.g.wt + (long long)(w.g.seg[s].coff + c + e) * w.g.wc + (long long)nn * w.g.wn;
       }
-    } else if (s >= 0 && c + e < w.g.seg[s].C) {
-      int tap = (w.g.ay.d0 + w.g.ay.ds * uy) * w.g.kw + (w.g.ax.d0 + w.g.ax.ds * ux), nn = n;
-      if (w.g.d2s) { tap = n / w.g.cout_true; nn = n - tap * w.g.cout_true; }
-      dst = dW + (long long)tap * w.g.wt + (long long)(w.g.seg[s].coff + c + e) * w.g.wc + (long long)nn * w.g.wn;
     }
-    if (dst == nullptr) continue;
-    float total_sum = 0.f;
-    for (int tp = 0; tp < ntaps_sum; ++tp) {
-    const float* src = ws + (size_t)k * w.ld + n + tp * w.g.cout_true;
-    const size_t stride = KD_pad * w.ld;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int sp = 0;
-    for (; sp + 4 <= w.nsplit; sp += 4) {
-      s0 += src[(size_t)(sp + 0) * stride]; s1 += src[(size_t)(sp + 1) * stride];
-      s2 += src[(size_t)(sp + 2) * stride]; s3 += src[(size_t)(sp + 3) * stride];
+    float part = 0.f;
+    if (dst != nullptr) {
+      for (int tp = 0; tp < ntaps_sum; ++tp) {
+        const float* src = ws + (size_t)k * w.ld + n + tp * w.g.cout_true;
+        float s0 = 0.f, s1 = 0.f;
+        int sp = lane_s;
+        for (; sp + 32 < w.nsplit; sp += 64) { s0 += src[(size_t)sp * stride]; s1 += src[(size_t)(sp + 32) * stride]; }
+        if (sp < w.nsplit) s0 += src[(size_t)sp * stride];
+        part += s0 + s1;
+      }
     }
-    for (; sp < w.nsplit; ++sp) s0 += src[(size_t)sp * stride];
-    total_sum += (s0 + s1) + (s2 + s3);
+    red[lane_s][lane_o] = part;
+    __syncthreads();
+    if (lane_s == 0 && dst != nullptr) {
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sum += red[i][lane_o];
+      *dst = accumulate ? (*dst + sum) : sum;
     }
-    const float sum = total_sum;
-    *dst = accumulate ? (*dst + sum) : sum;
+    __syncthreads();
   }
 }
 
@@ -727,8 +740,8 @@ int nlt_gconv_wgrad(const nlt_gconv_desc* d, const float* G, float* dW, float* d
     // every phase sees a disjoint subset of lattice pixels, so the bias gradient
     // accumulates across phases; taps are disjoint across phases.
     const size_t total = (size_t)w.KG * 4 * k.Cout;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    int blocks = (int)((total + 7) / 8);
+    if (blocks > 148 * 16) blocks = 148 * 16;
     gconv_wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(w, ws, KD_pad, dW, db, accumulate,
                                                       bias_done ? 1 : accumulate);
     NLT_CUDA_LAUNCH_CHECK("gconv_wgrad_reduce_kernel");

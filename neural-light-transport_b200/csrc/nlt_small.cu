@@ -584,7 +584,7 @@ static TppPlan tpp_plan(const GConvK& k) {
   pl.k.rows = pl.KG * 4;
   pl.k.ldw = (k.Cout + 3) / 4 * 4;
   pl.k.bias_row = (pl.KG - 1) * 4;
-  long long want = (long long)kSMs * 8;
+  long long want = (long long)kSMs * 6;
   const long long max_split = ((long long)k.M + TPP_THREADS * 4 - 1) / (TPP_THREADS * 4);
   if (want > max_split) want = max_split;
   if (want < 1) want = 1;

@@ -149,12 +149,12 @@ def test_tensor_core_vs_fp32_kernels(kind, k, s, H, W, segc, cout):
     nat.set_option('tc', 1)
     assert res['fp32']['tc'] == 0 and res['tc']['tc'] >= 1, res['tc']['tc']
     rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
-    assert rel(res['tc']['y'], res['fp32']['y']) <= 5e-6
+    assert rel(res['tc']['y'], res['fp32']['y']) <= 1e-5      # 3xTF32: ~1e-6 per product, grows ~sqrt(K)
     # weight / bias gradients sum over every pixel: both paths carry fp32 accumulation error of their own
     assert rel(res['tc']['gk'], res['fp32']['gk']) <= 2e-5
     assert rel(res['tc']['gb'], res['fp32']['gb']) <= 2e-5
     for a, b in zip(res['tc']['gx'], res['fp32']['gx']):
-        assert rel(a, b) <= 5e-6
+        assert rel(a, b) <= 1e-5
 
 
 def test_tensor_core_path_is_taken_and_matches_fp32_path():
