@@ -492,6 +492,8 @@ static TcPlan tc_plan(const GConvK& k) {
   if (!aligned16(k.w)) { /* weights are only read by the pack kernel: no alignment needed */ }
   // with less than 64 contraction terms the op is a pure stream: the pointwise / fp32 kernels are faster there
   if (k.ay.nu * k.ax.nu * ctot < 64) return pl;
+  // measured: 16-channel (64-byte-row) K-blocks only pay off from K = 128 up
+  if (pl.kbw == 16 && k.ay.nu * k.ax.nu * ctot < 128) return pl;
   if (k.ay.nu < 1 || k.ax.nu < 1) return pl;
   TcParams& p = pl.p;
   p.N = k.N; p.Hl = k.ay.nt; p.Wl = k.ax.nt;
