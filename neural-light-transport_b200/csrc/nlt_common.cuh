@@ -134,6 +134,9 @@ __device__ __forceinline__ void decode_kgroup(const WgradK& w, int kg, int& uy, 
 bool pw_conv_applicable(const GConvK& k);
 int launch_pw_conv(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
                    float* out, cudaStream_t st);
+bool dconv_small_applicable(const GConvK& k);
+int launch_dconv_small(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
+                       float* out, cudaStream_t st);
 bool wgrad_small_applicable(const GConvK& k);
 size_t wgrad_small_ws_floats(const GConvK& k);
 // fills w (nsplit, pix_per_split, ld, KG, GS) and *KD_pad for the reduce stage

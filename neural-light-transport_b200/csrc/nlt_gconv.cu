@@ -661,6 +661,7 @@ int nlt_gconv_fwd_ws(const nlt_gconv_desc* d, const float* bias, int act, float 
     const GConvK& k = ph[i];
     if (k.M == 0) continue;
     if (pw_conv_applicable(k)) rc = launch_pw_conv(k, bias, act, beta, mask_y, mask_act, out, st);
+    else if (dconv_small_applicable(k)) rc = launch_dconv_small(k, bias, act, beta, mask_y, mask_act, out, st);
     else if (k.Cout > 32) rc = launch_fwd<128, 64, 8, 8>(k, bias, act, beta, mask_y, mask_act, out, st);
     else if (k.Cout > 16) rc = launch_fwd<128, 32, 8, 4>(k, bias, act, beta, mask_y, mask_act, out, st);
     else if (k.Cout > 8) rc = launch_fwd<256, 16, 8, 4>(k, bias, act, beta, mask_y, mask_act, out, st);

@@ -26,13 +26,205 @@ constexpr int PW_KMAX = 64;
 constexpr int PW_THREADS = 256;
 
 bool pw_conv_applicable(const GConvK& k) {
+  if (k.ay.nu != 1 || k.ax.nu != 1) return false;
+  // identity pixel map: input coordinate == lattice coordinate (== output coordinate unless depth-to-space)
+  const AxisMap* ax[2] = {&k.ay, &k.ax};
+  for (int i = 0; i < 2; ++i) {
+    const AxisMap& a = *ax[i];
+    if (a.it != 1 || a.i0 != 0 || a.o0 != 0 || a.os != 1) return false;
+  }
+  if (k.ay.nt != k.Hin || k.ax.nt != k.Win) return false;
+  if (!k.d2s && (k.Hout != k.Hin || k.Wout != k.Win)) return false;
+  int ctot = 0;
+  for (int s = 0; s < k.nseg; ++s) ctot += k.seg[s].C;
+  // GEMM columns: Cout (d2s: k*k*cout_true, a multiple of 4)
+  return ctot <= PW_KMAX && k.Cout <= 64 && (k.Cout <= 16 || k.Cout % 4 == 0);
+}
+
+template <int NQ, int R>
+__global__ void __launch_bounds__(PW_THREADS)
+pw_conv_kernel(const GConvK g, const float* __restrict__ bias, const int act, const float beta,
+               const float* __restrict__ mask_y, const int mask_act, float* __restrict__ out) {
+  __shared__ float4 Ws[PW_KMAX * NQ];   // [k][quad] : 4 consecutive GEMM columns
+  const int tid = threadIdx.x;
+  const int tap = (g.ay.d0) * g.kw + g.ax.d0;
+  int K = 0;
+  for (int s = 0; s < g.nseg; ++s) K += g.seg[s].C;
+  for (int idx = tid; idx < K * NQ; idx += PW_THREADS) {
+    const int k = idx / NQ, q = idx - k * NQ;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int n = q * 4 + e;
+      int t = tap, nn = n;
+      if (g.d2s) { t = n / g.cout_true; nn = n - t * g.cout_true; }
+      v[e] = n < g.Cout ? __ldg(g.w + (long long)t * g.wt + (long long)k * g.wc + (long long)nn * g.wn) : 0.f;
+    }
+    Ws[idx] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  __syncthreads();
+
+  constexpr int PPB = PW_THREADS / NQ;     // pixels per pass
+  const int q = tid % NQ;
+  const uint32_t pbase = (uint32_t)blockIdx.x * (PPB * R) + tid / NQ;
+  const uint32_t hw = g.div_yx.d;
+  // destination channel quad / tap of this thread's GEMM columns
+  int qtap = 0, qcb = q * 4;
+  if (g.d2s) { qtap = (q * 4) / g.cout_true; qcb = q * 4 - qtap * g.cout_true; }
+  const int qdy = g.d2s ? qtap / g.d2s_s : 0, qdx = g.d2s ? qtap - qdy * g.d2s_s : 0;
+  float b4[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) b4[e] = (bias != nullptr && q * 4 + e < g.Cout) ? __ldg(bias + qcb + e) : 0.f;
+  auto out_off = [&](uint32_t pp) -> size_t {
+    if (!g.d2s) return (size_t)pp * g.Cout + q * 4;
+    int n, ty, tx;
+    decode_pixel(g, pp, n, ty, tx);
+    return (((size_t)n * g.Hout + ty * g.d2s_s + qdy) * g.Wout + tx * g.d2s_s + qdx) * g.cout_true + qcb;
+  };
+
+  uint32_t p[R];
+  bool ok[R];
+  float acc[R][4];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    p[r] = pbase + r * PPB;
+    ok[r] = p[r] < g.M;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[r][e] = b4[e];
+  }
+
+  int k = 0;
+  for (int s = 0; s < g.nseg; ++s) {
+    const Seg sg = g.seg[s];
+    size_t po[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      uint32_t pp = p[r];
+      if (sg.bcast) pp -= fdiv(pp, g.div_yx) * hw;   // batch-broadcast source: pixel index inside the image
+      po[r] = (size_t)pp * sg.C;
+    }
+    if (sg.vec) {
+      for (int c = 0; c < sg.C; c += 4) {
+        float4 a[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          a[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok[r]) {
+            a[r] = ld4(sg.ptr + po[r] + c);
+            if (sg.sub) { const float4 u = ld4(sg.sub + po[r] + c); a[r].x -= u.x; a[r].y -= u.y; a[r].z -= u.z; a[r].w -= u.w; }
+          }
+        }
+        const float4 w0 = Ws[(k + 0) * NQ + q], w1 = Ws[(k + 1) * NQ + q], w2 = Ws[(k + 2) * NQ + q],
+                     w3 = Ws[(k + 3) * NQ + q];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          acc[r][0] = fmaf(a[r].x, w0.x, acc[r][0]); acc[r][1] = fmaf(a[r].x, w0.y, acc[r][1]);
+          acc[r][2] = fmaf(a[r].x, w0.z, acc[r][2]); acc[r][3] = fmaf(a[r].x, w0.w, acc[r][3]);
+          acc[r][0] = fmaf(a[r].y, w1.x, acc[r][0]); acc[r][1] = fmaf(a[r].y, w1.y, acc[r][1]);
+          acc[r][2] = fmaf(a[r].y, w1.z, acc[r][2]); acc[r][3] = fmaf(a[r].y, w1.w, acc[r][3]);
+          acc[r][0] = fmaf(a[r].z, w2.x, acc[r][0]); acc[r][1] = fmaf(a[r].z, w2.y, acc[r][1]);
+          acc[r][2] = fmaf(a[r].z, w2.z, acc[r][2]); acc[r][3] = fmaf(a[r].z, w2.w, acc[r][3]);
+          acc[r][0] = fmaf(a[r].w, w3.x, acc[r][0]); acc[r][1] = fmaf(a[r].w, w3.y, acc[r][1]);
+          acc[r][2] = fmaf(a[r].w, w3.z, acc[r][2]); acc[r][3] = fmaf(a[r].w, w3.w, acc[r][3]);
+        }
+        k += 4;
+      }
+    } else {
+      for (int c = 0; c < sg.C; ++c) {
+        float a[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          a[r] = 0.f;
+          if (ok[r]) {
+            a[r] = __ldg(sg.ptr + po[r] + c);
+            if (sg.sub) a[r] -= __ldg(sg.sub + po[r] + c);
+          }
+        }
+        const float4 w0 = Ws[k * NQ + q];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          acc[r][0] = fmaf(a[r], w0.x, acc[r][0]); acc[r][1] = fmaf(a[r], w0.y, acc[r][1]);
+          acc[r][2] = fmaf(a[r], w0.z, acc[r][2]); acc[r][3] = fmaf(a[r], w0.w, acc[r][3]);
+        }
+        ++k;
+      }
+    }
+  }
+
+  const bool vec_out = (g.cout_true % 4 == 0) && aligned16(out) && (mask_y == nullptr || aligned16(mask_y));
+  float4 oldv[R], yv[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {   // batch the read-modify-write operands before the first store
+    oldv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    yv[r] = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (ok[r] && q * 4 < g.Cout && vec_out) {
+      const size_t ob = out_off(p[r]);
+      if (beta != 0.f) oldv[r] = *reinterpret_cast<const float4*>(out + ob);
+      if (mask_y != nullptr) yv[r] = ld4(mask_y + ob);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (!ok[r] || q * 4 >= g.Cout) continue;
+    const size_t ob = out_off(p[r]);
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = act_fwd(acc[r][e], act);
+    if (vec_out) {
+      const float4 o = oldv[r], y = yv[r];
+      v[0] += beta * o.x; v[1] += beta * o.y; v[2] += beta * o.z; v[3] += beta * o.w;
+      if (mask_y != nullptr) {
+        v[0] *= act_bwd_from_y(y.x, mask_act); v[1] *= act_bwd_from_y(y.y, mask_act);
+        v[2] *= act_bwd_from_y(y.z, mask_act); v[3] *= act_bwd_from_y(y.w, mask_act);
+      }
+      *reinterpret_cast<float4*>(out + ob) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (q * 4 + e >= g.Cout) continue;
+        float t = v[e];
+        if (beta != 0.f) t += beta * out[ob + e];
+        if (mask_y != nullptr) t *= act_bwd_from_y(__ldg(mask_y + ob + e), mask_act);
+        out[ob + e] = t;
+      }
+    }
+  }
+}
+
+int launch_pw_conv(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
+                   float* out, cudaStream_t st) {
+  constexpr int R = 4;
+  const int nq = (k.Cout + 3) / 4;
+  if (nq <= 1) {
+    const unsigned grid = (k.M + PW_THREADS * R - 1) / (PW_THREADS * R);
+    pw_conv_kernel<1, R><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
+  } else if (nq == 2) {
+    const unsigned grid = (k.M + PW_THREADS / 2 * R - 1) / (PW_THREADS / 2 * R);
+    pw_conv_kernel<2, R><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
+  } else if (nq <= 4) {
+    const unsigned grid = (k.M + PW_THREADS / 4 * R - 1) / (PW_THREADS / 4 * R);
+    pw_conv_kernel<4, R><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
+  } else if (nq <= 8) {
+    const unsigned grid = (k.M + PW_THREADS / 8 * R - 1) / (PW_THREADS / 8 * R);
+    pw_conv_kernel<8, R><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
+  } else {
+    const unsigned grid = (k.M + PW_THREADS / 16 * R - 1) / (PW_THREADS / 16 * R);
+    pw_conv_kernel<16, R><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
+  }
+  NLT_CUDA_LAUNCH_CHECK("pw_conv_kernel");
+  return NLT_OK;
+}
+
+// ---- general small direct convolution (taps, strided / phase maps) -----------------
+bool dconv_small_applicable(const GConvK& k) {
   // small direct convolution: every (tap, source channel) weight row fits the smem table
   int ctot = 0;
   for (int s = 0; s < k.nseg; ++s) ctot += k.seg[s].C;
   const int ktot = k.ay.nu * k.ax.nu * ctot;
   if (ktot < 1 || ktot > PW_KMAX) return false;
-  // GEMM columns: Cout (d2s: k*k*cout_true, a multiple of 4)
-  return k.Cout <= 64 && (k.Cout <= 16 || k.Cout % 4 == 0);
+  // measured against the tiled kernel: wins for the 4..16-channel stencils (K <= 32), and up to K = 64
+  // when there are at most 8 output channels
+  return (k.Cout <= 16 && ktot <= 32) || (k.Cout <= 8 && ktot <= 64);
 }
 
 // One thread = one lattice pixel x one quad of GEMM columns; R pixels per thread in flight; the weight
@@ -40,8 +232,8 @@ bool pw_conv_applicable(const GConvK& k) {
 // pixel map of GConvK, so it also covers the 2x2/stride-1 stencils of the 4..16-channel full-resolution
 // layers and the phase-decomposed / depth-to-space transposed convs.
 template <int NQ, int R>
-__global__ void __launch_bounds__(PW_THREADS, (R <= 4 ? 3 : 2))
-pw_conv_kernel(const GConvK g, const float* __restrict__ bias, const int act, const float beta,
+__global__ void __launch_bounds__(PW_THREADS, 3)
+dconv_small_kernel(const GConvK g, const float* __restrict__ bias, const int act, const float beta,
                const float* __restrict__ mask_y, const int mask_act, float* __restrict__ out) {
   __shared__ float4 Ws[PW_KMAX * NQ];   // [k][quad] : 4 consecutive GEMM columns
   const int tid = threadIdx.x;
@@ -203,25 +395,25 @@ pw_conv_kernel(const GConvK g, const float* __restrict__ bias, const int act, co
 }
 
 template <int NQ, int R>
-static void pw_launch(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
+static void dconv_launch(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
                       float* out, cudaStream_t st) {
   constexpr int PPB = PW_THREADS / NQ * R;
   const unsigned grid = (k.M + PPB - 1) / PPB;
-  pw_conv_kernel<NQ, R><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
+  dconv_small_kernel<NQ, R><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
 }
 
-int launch_pw_conv(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
+int launch_dconv_small(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
                    float* out, cudaStream_t st) {
   const int nq = (k.Cout + 3) / 4;
   int ctot = 0;
   for (int s = 0; s < k.nseg; ++s) ctot += k.seg[s].C;
-  const bool tiny = k.ay.nu * k.ax.nu * ctot <= 8;   // few bytes per pixel: more pixels in flight per thread
-  if (nq <= 1) { if (tiny) pw_launch<1, 8>(k, bias, act, beta, mask_y, mask_act, out, st); else pw_launch<1, 4>(k, bias, act, beta, mask_y, mask_act, out, st); }
-  else if (nq == 2) pw_launch<2, 4>(k, bias, act, beta, mask_y, mask_act, out, st);
-  else if (nq <= 4) { if (tiny) pw_launch<4, 8>(k, bias, act, beta, mask_y, mask_act, out, st); else pw_launch<4, 4>(k, bias, act, beta, mask_y, mask_act, out, st); }
-  else if (nq <= 8) pw_launch<8, 4>(k, bias, act, beta, mask_y, mask_act, out, st);
-  else pw_launch<16, 4>(k, bias, act, beta, mask_y, mask_act, out, st);
-  NLT_CUDA_LAUNCH_CHECK("pw_conv_kernel");
+  (void)ctot;
+  if (nq <= 1) dconv_launch<1, 4>(k, bias, act, beta, mask_y, mask_act, out, st);
+  else if (nq == 2) dconv_launch<2, 4>(k, bias, act, beta, mask_y, mask_act, out, st);
+  else if (nq <= 4) dconv_launch<4, 4>(k, bias, act, beta, mask_y, mask_act, out, st);
+  else if (nq <= 8) dconv_launch<8, 4>(k, bias, act, beta, mask_y, mask_act, out, st);
+  else dconv_launch<16, 4>(k, bias, act, beta, mask_y, mask_act, out, st);
+  NLT_CUDA_LAUNCH_CHECK("dconv_small_kernel");
   return NLT_OK;
 }
 
