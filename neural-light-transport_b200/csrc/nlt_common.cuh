@@ -36,23 +36,19 @@ __device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
 }
 
 // ---- activation ---------------------------------------------------------------
-// forward (nlt/networks/elements.py:69-78)
+// forward (nlt/networks/elements.py:69-78).  `act` is warp-uniform: the piecewise-linear cases cost
+// three instructions per value; ELU (expm1f) sits behind a real call so that its ~30 instructions are
+// not if-converted into every epilogue (they were: ncu showed the epilogues dominating the small kernels).
+static __device__ __noinline__ float elu_slow(float x) { return x > 0.f ? x : expm1f(x); }
 __device__ __forceinline__ float act_fwd(float x, int act) {
-  switch (act) {
-    case NLT_ACT_RELU: return x > 0.f ? x : 0.f;
-    case NLT_ACT_LEAKYRELU: return x > 0.f ? x : 0.3f * x;
-    case NLT_ACT_ELU: return x > 0.f ? x : expm1f(x);
-    default: return x;
-  }
+  if (act == NLT_ACT_ELU) return elu_slow(x);
+  const float neg = act == NLT_ACT_LEAKYRELU ? 0.3f : (act == NLT_ACT_RELU ? 0.f : 1.f);
+  return x > 0.f ? x : neg * x;
 }
 // derivative recovered from the saved OUTPUT y (no pre-activation is stored)
 __device__ __forceinline__ float act_bwd_from_y(float y, int act) {
-  switch (act) {
-    case NLT_ACT_RELU: return y > 0.f ? 1.f : 0.f;
-    case NLT_ACT_LEAKYRELU: return y > 0.f ? 1.f : 0.3f;
-    case NLT_ACT_ELU: return y > 0.f ? 1.f : y + 1.f;
-    default: return 1.f;
-  }
+  const float neg = act == NLT_ACT_LEAKYRELU ? 0.3f : (act == NLT_ACT_RELU ? 0.f : 1.f);
+  return y > 0.f ? 1.f : (act == NLT_ACT_ELU ? y + 1.f : neg);
 }
 
 // One axis of the (phase-decomposed) gather map.
