@@ -41,56 +41,56 @@ bool pw_conv_applicable(const GConvK& k) {
   return ctot <= PW_KMAX && k.Cout <= 64 && (k.Cout <= 16 || k.Cout % 4 == 0);
 }
 
-template <int NQ, int R>
+// One thread = one pixel x QT consecutive quads of GEMM columns (QT*4 outputs), R pixels in flight.
+// QT = 4 means a thread owns 16 output channels of a pixel: every input value is loaded once per 64 FMAs
+// and the thread stores 64 contiguous bytes (ncu showed the QT = 1 form issue-bound: ~14 overhead
+// instructions per FMA).
+template <int NQ, int QT, int R>
 __global__ void __launch_bounds__(PW_THREADS)
 pw_conv_kernel(const GConvK g, const float* __restrict__ bias, const int act, const float beta,
                const float* __restrict__ mask_y, const int mask_act, float* __restrict__ out) {
-  __shared__ float4 Ws[PW_KMAX * NQ];   // [k][quad] : 4 consecutive GEMM columns
+  static_assert(NQ % QT == 0, "quads per thread");
+  constexpr int LPP = NQ / QT;            // lanes per pixel
+  __shared__ float4 Ws[PW_KMAX * NQ];     // [k][quad] : 4 consecutive GEMM columns
   const int tid = threadIdx.x;
   const int tap = (g.ay.d0) * g.kw + g.ax.d0;
   int K = 0;
   for (int s = 0; s < g.nseg; ++s) K += g.seg[s].C;
   for (int idx = tid; idx < K * NQ; idx += PW_THREADS) {
     const int k = idx / NQ, q = idx - k * NQ;
+    int t = tap, nn0 = q * 4;
+    if (g.d2s) { t = (q * 4) / g.cout_true; nn0 = q * 4 - t * g.cout_true; }   // cout_true % 4 == 0: a quad stays in one tap
     float v[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int n = q * 4 + e;
-      int t = tap, nn = n;
-      if (g.d2s) { t = n / g.cout_true; nn = n - t * g.cout_true; }
-      v[e] = n < g.Cout ? __ldg(g.w + (long long)t * g.wt + (long long)k * g.wc + (long long)nn * g.wn) : 0.f;
-    }
+    for (int e = 0; e < 4; ++e)
+      v[e] = q * 4 + e < g.Cout ? __ldg(g.w + (long long)t * g.wt + (long long)k * g.wc + (long long)(nn0 + e) * g.wn) : 0.f;
     Ws[idx] = make_float4(v[0], v[1], v[2], v[3]);
   }
   __syncthreads();
 
-  constexpr int PPB = PW_THREADS / NQ;     // pixels per pass
-  const int q = tid % NQ;
-  const uint32_t pbase = (uint32_t)blockIdx.x * (PPB * R) + tid / NQ;
+  constexpr int PPB = PW_THREADS / LPP;    // pixels per pass
+  const int q0 = (tid % LPP) * QT;         // first quad of this thread
+  const uint32_t pbase = (uint32_t)blockIdx.x * (PPB * R) + tid / LPP;
   const uint32_t hw = g.div_yx.d;
-  // destination channel quad / tap of this thread's GEMM columns
-  int qtap = 0, qcb = q * 4;
-  if (g.d2s) { qtap = (q * 4) / g.cout_true; qcb = q * 4 - qtap * g.cout_true; }
-  const int qdy = g.d2s ? qtap / g.d2s_s : 0, qdx = g.d2s ? qtap - qdy * g.d2s_s : 0;
-  float b4[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) b4[e] = (bias != nullptr && q * 4 + e < g.Cout) ? __ldg(bias + qcb + e) : 0.f;
-  auto out_off = [&](uint32_t pp) -> size_t {
-    if (!g.d2s) return (size_t)pp * g.Cout + q * 4;
-    int n, ty, tx;
-    decode_pixel(g, pp, n, ty, tx);
-    return (((size_t)n * g.Hout + ty * g.d2s_s + qdy) * g.Wout + tx * g.d2s_s + qdx) * g.cout_true + qcb;
-  };
 
   uint32_t p[R];
   bool ok[R];
-  float acc[R][4];
+  float acc[R][QT][4];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     p[r] = pbase + r * PPB;
     ok[r] = p[r] < g.M;
+  }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) acc[r][e] = b4[e];
+  for (int j = 0; j < QT; ++j) {
+    int cb = (q0 + j) * 4;
+    if (g.d2s) cb -= (cb / g.cout_true) * g.cout_true;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float b = (bias != nullptr && (q0 + j) * 4 + e < g.Cout) ? __ldg(bias + cb + e) : 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r][j][e] = b;
+    }
   }
 
   int k = 0;
@@ -105,27 +105,27 @@ pw_conv_kernel(const GConvK g, const float* __restrict__ bias, const int act, co
     }
     if (sg.vec) {
       for (int c = 0; c < sg.C; c += 4) {
-        float4 a[R];
+        float a[R][4];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          a[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
           if (ok[r]) {
-            a[r] = ld4(sg.ptr + po[r] + c);
-            if (sg.sub) { const float4 u = ld4(sg.sub + po[r] + c); a[r].x -= u.x; a[r].y -= u.y; a[r].z -= u.z; a[r].w -= u.w; }
+            v = ld4(sg.ptr + po[r] + c);
+            if (sg.sub) { const float4 u = ld4(sg.sub + po[r] + c); v.x -= u.x; v.y -= u.y; v.z -= u.z; v.w -= u.w; }
           }
+          a[r][0] = v.x; a[r][1] = v.y; a[r][2] = v.z; a[r][3] = v.w;
         }
-        const float4 w0 = Ws[(k + 0) * NQ + q], w1 = Ws[(k + 1) * NQ + q], w2 = Ws[(k + 2) * NQ + q],
-                     w3 = Ws[(k + 3) * NQ + q];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          acc[r][0] = fmaf(a[r].x, w0.x, acc[r][0]); acc[r][1] = fmaf(a[r].x, w0.y, acc[r][1]);
-          acc[r][2] = fmaf(a[r].x, w0.z, acc[r][2]); acc[r][3] = fmaf(a[r].x, w0.w, acc[r][3]);
-          acc[r][0] = fmaf(a[r].y, w1.x, acc[r][0]); acc[r][1] = fmaf(a[r].y, w1.y, acc[r][1]);
-          acc[r][2] = fmaf(a[r].y, w1.z, acc[r][2]); acc[r][3] = fmaf(a[r].y, w1.w, acc[r][3]);
-          acc[r][0] = fmaf(a[r].z, w2.x, acc[r][0]); acc[r][1] = fmaf(a[r].z, w2.y, acc[r][1]);
-          acc[r][2] = fmaf(a[r].z, w2.z, acc[r][2]); acc[r][3] = fmaf(a[r].z, w2.w, acc[r][3]);
-          acc[r][0] = fmaf(a[r].w, w3.x, acc[r][0]); acc[r][1] = fmaf(a[r].w, w3.y, acc[r][1]);
-          acc[r][2] = fmaf(a[r].w, w3.z, acc[r][2]); acc[r][3] = fmaf(a[r].w, w3.w, acc[r][3]);
+        for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+          for (int j = 0; j < QT; ++j) {
+            const float4 w = Ws[(k + kk) * NQ + q0 + j];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              acc[r][j][0] = fmaf(a[r][kk], w.x, acc[r][j][0]); acc[r][j][1] = fmaf(a[r][kk], w.y, acc[r][j][1]);
+              acc[r][j][2] = fmaf(a[r][kk], w.z, acc[r][j][2]); acc[r][j][3] = fmaf(a[r][kk], w.w, acc[r][j][3]);
+            }
+          }
         }
         k += 4;
       }
@@ -140,11 +140,14 @@ pw_conv_kernel(const GConvK g, const float* __restrict__ bias, const int act, co
             if (sg.sub) a[r] -= __ldg(sg.sub + po[r] + c);
           }
         }
-        const float4 w0 = Ws[k * NQ + q];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          acc[r][0] = fmaf(a[r], w0.x, acc[r][0]); acc[r][1] = fmaf(a[r], w0.y, acc[r][1]);
-          acc[r][2] = fmaf(a[r], w0.z, acc[r][2]); acc[r][3] = fmaf(a[r], w0.w, acc[r][3]);
+        for (int j = 0; j < QT; ++j) {
+          const float4 w = Ws[k * NQ + q0 + j];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            acc[r][j][0] = fmaf(a[r], w.x, acc[r][j][0]); acc[r][j][1] = fmaf(a[r], w.y, acc[r][j][1]);
+            acc[r][j][2] = fmaf(a[r], w.z, acc[r][j][2]); acc[r][j][3] = fmaf(a[r], w.w, acc[r][j][3]);
+          }
         }
         ++k;
       }
@@ -152,65 +155,79 @@ pw_conv_kernel(const GConvK g, const float* __restrict__ bias, const int act, co
   }
 
   const bool vec_out = (g.cout_true % 4 == 0) && aligned16(out) && (mask_y == nullptr || aligned16(mask_y));
-  float4 oldv[R], yv[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {   // batch the read-modify-write operands before the first store
-    oldv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-    yv[r] = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (ok[r] && q * 4 < g.Cout && vec_out) {
-      const size_t ob = out_off(p[r]);
-      if (beta != 0.f) oldv[r] = *reinterpret_cast<const float4*>(out + ob);
-      if (mask_y != nullptr) yv[r] = ld4(mask_y + ob);
-    }
-  }
+  const bool rmw = (beta != 0.f) || (mask_y != nullptr);
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    if (!ok[r] || q * 4 >= g.Cout) continue;
-    const size_t ob = out_off(p[r]);
-    float v[4];
+    if (!ok[r]) continue;
+    // destination of quad (q0 + j): consecutive quads are consecutive channels of one output pixel
+    size_t ob[QT];
+    int n = 0, ty = 0, tx = 0;
+    if (g.d2s) decode_pixel(g, p[r], n, ty, tx);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) v[e] = act_fwd(acc[r][e], act);
-    if (vec_out) {
-      const float4 o = oldv[r], y = yv[r];
-      v[0] += beta * o.x; v[1] += beta * o.y; v[2] += beta * o.z; v[3] += beta * o.w;
-      if (mask_y != nullptr) {
-        v[0] *= act_bwd_from_y(y.x, mask_act); v[1] *= act_bwd_from_y(y.y, mask_act);
-        v[2] *= act_bwd_from_y(y.z, mask_act); v[3] *= act_bwd_from_y(y.w, mask_act);
+    for (int j = 0; j < QT; ++j) {
+      const int col = (q0 + j) * 4;
+      if (g.d2s) {
+        const int t = col / g.cout_true, cb = col - t * g.cout_true;
+        const int dy = t / g.d2s_s, dx = t - dy * g.d2s_s;
+        ob[j] = (((size_t)n * g.Hout + ty * g.d2s_s + dy) * g.Wout + tx * g.d2s_s + dx) * g.cout_true + cb;
+      } else {
+        ob[j] = (size_t)p[r] * g.Cout + col;
       }
-      *reinterpret_cast<float4*>(out + ob) = make_float4(v[0], v[1], v[2], v[3]);
-    } else {
+    }
+    float4 oldv[QT], yv[QT];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (q * 4 + e >= g.Cout) continue;
-        float t = v[e];
-        if (beta != 0.f) t += beta * out[ob + e];
-        if (mask_y != nullptr) t *= act_bwd_from_y(__ldg(mask_y + ob + e), mask_act);
-        out[ob + e] = t;
+    for (int j = 0; j < QT; ++j) {        // batch the read-modify-write operands before the first store
+      oldv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      yv[j] = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (rmw && vec_out && (q0 + j) * 4 < g.Cout) {
+        if (beta != 0.f) oldv[j] = *reinterpret_cast<const float4*>(out + ob[j]);
+        if (mask_y != nullptr) yv[j] = ld4(mask_y + ob[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < QT; ++j) {
+      if ((q0 + j) * 4 >= g.Cout) continue;
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = act_fwd(acc[r][j][e], act);
+      if (vec_out) {
+        const float4 o = oldv[j], y = yv[j];
+        v[0] += beta * o.x; v[1] += beta * o.y; v[2] += beta * o.z; v[3] += beta * o.w;
+        if (mask_y != nullptr) {
+          v[0] *= act_bwd_from_y(y.x, mask_act); v[1] *= act_bwd_from_y(y.y, mask_act);
+          v[2] *= act_bwd_from_y(y.z, mask_act); v[3] *= act_bwd_from_y(y.w, mask_act);
+        }
+        *reinterpret_cast<float4*>(out + ob[j]) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if ((q0 + j) * 4 + e >= g.Cout) continue;
+          float t = v[e];
+          if (beta != 0.f) t += beta * out[ob[j] + e];
+          if (mask_y != nullptr) t *= act_bwd_from_y(__ldg(mask_y + ob[j] + e), mask_act);
+          out[ob[j] + e] = t;
+        }
       }
     }
   }
 }
 
+template <int NQ, int QT, int R>
+static void pw_launch(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
+                      float* out, cudaStream_t st) {
+  constexpr int PPB = PW_THREADS / (NQ / QT) * R;
+  const unsigned grid = (k.M + PPB - 1) / PPB;
+  pw_conv_kernel<NQ, QT, R><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
+}
+
 int launch_pw_conv(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
                    float* out, cudaStream_t st) {
-  constexpr int R = 4;
   const int nq = (k.Cout + 3) / 4;
-  if (nq <= 1) {
-    const unsigned grid = (k.M + PW_THREADS * R - 1) / (PW_THREADS * R);
-    pw_conv_kernel<1, R><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
-  } else if (nq == 2) {
-    const unsigned grid = (k.M + PW_THREADS / 2 * R - 1) / (PW_THREADS / 2 * R);
-    pw_conv_kernel<2, R><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
-  } else if (nq <= 4) {
-    const unsigned grid = (k.M + PW_THREADS / 4 * R - 1) / (PW_THREADS / 4 * R);
-    pw_conv_kernel<4, R><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
-  } else if (nq <= 8) {
-    const unsigned grid = (k.M + PW_THREADS / 8 * R - 1) / (PW_THREADS / 8 * R);
-    pw_conv_kernel<8, R><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
-  } else {
-    const unsigned grid = (k.M + PW_THREADS / 16 * R - 1) / (PW_THREADS / 16 * R);
-    pw_conv_kernel<16, R><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
-  }
+  if (nq <= 1) pw_launch<1, 1, 4>(k, bias, act, beta, mask_y, mask_act, out, st);
+  else if (nq == 2) pw_launch<2, 2, 4>(k, bias, act, beta, mask_y, mask_act, out, st);
+  else if (nq <= 4) pw_launch<4, 4, 2>(k, bias, act, beta, mask_y, mask_act, out, st);
+  else if (nq <= 8) pw_launch<8, 4, 2>(k, bias, act, beta, mask_y, mask_act, out, st);
+  else pw_launch<16, 4, 2>(k, bias, act, beta, mask_y, mask_act, out, st);
   NLT_CUDA_LAUNCH_CHECK("pw_conv_kernel");
   return NLT_OK;
 }
