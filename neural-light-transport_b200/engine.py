@@ -95,6 +95,8 @@ class Tape:
         for fn in reversed(self.ops):
             fn()
         self.ops = []
+        if USE_SIDE_STREAM and torch.cuda.is_available():
+            torch.cuda.current_stream().wait_stream(side_stream())   # join the weight-gradient branch
 
 
 class Workspace:
@@ -110,6 +112,21 @@ class Workspace:
 
 
 _WS = Workspace()
+_WS_SIDE = Workspace()       # scratch of the weight-gradient stream
+_SIDE = {}                   # device index -> side stream
+
+
+def side_stream():
+    """Weight gradients do not feed the input-gradient chain: they run on a second stream (a parallel
+    branch of the captured CUDA graph), which hides the launch/latency-bound deep-level launches behind
+    the main chain.  Joined back in Tape.backward()."""
+    dev = torch.cuda.current_device()
+    if dev not in _SIDE:
+        _SIDE[dev] = torch.cuda.Stream(device=dev)
+    return _SIDE[dev]
+
+
+USE_SIDE_STREAM = True
 
 
 def gconv_fwd(d, bias, act, beta, mask, mask_act, out):
@@ -269,11 +286,22 @@ class ConvLayer:
         need = lib.nlt_gconv_wgrad_workspace_bytes(C.byref(d))
         if need < 0:
             nat.check(-1)
-        ws = _WS.get(need, dz.device)
         nb = 4 * (sum(sg.a.t.numel() * (2 if sg.sub is not None else 1) for sg in segs) + dz.numel())
-        PROF.run('wgrad ' + self.name, nb, lambda: nat.check(lib.nlt_gconv_wgrad(
-            C.byref(d), nat.ptr(dz), nat.ptr(self.gkernel), nat.ptr(self.gbias),
-            1 if self.grad_written else 0, nat.ptr(ws), ws.numel() * 4, nat.stream())))
+        acc = 1 if self.grad_written else 0
+        if USE_SIDE_STREAM:
+            main, side = torch.cuda.current_stream(), side_stream()
+            side.wait_stream(main)                      # dz (and the inputs) are complete on the main stream
+            with torch.cuda.stream(side):
+                ws = _WS_SIDE.get(need, dz.device)
+                PROF.run('wgrad ' + self.name, nb, lambda: nat.check(lib.nlt_gconv_wgrad(
+                    C.byref(d), nat.ptr(dz), nat.ptr(self.gkernel), nat.ptr(self.gbias), acc, nat.ptr(ws),
+                    ws.numel() * 4, nat.stream())))
+            dz.record_stream(side)                      # dz is released below while the side stream may still read it
+        else:
+            ws = _WS.get(need, dz.device)
+            PROF.run('wgrad ' + self.name, nb, lambda: nat.check(lib.nlt_gconv_wgrad(
+                C.byref(d), nat.ptr(dz), nat.ptr(self.gkernel), nat.ptr(self.gbias), acc, nat.ptr(ws),
+                ws.numel() * 4, nat.stream())))
         self.grad_written = True
         # input gradients, one adjoint launch per differentiable segment
         coff = 0
