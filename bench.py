@@ -264,8 +264,10 @@ def run_b200(args):
     # every rank runs these steps (they contain the gradient all-reduce); only rank 0 records events
     engine.PROF.enabled = (rank == 0)
     engine.PROF.force_eager = True
+    engine.USE_SIDE_STREAM = False        # one stream: per-kernel times without concurrent-branch interference
     for i in range(2):
         step(resident[i % 2])
+    engine.USE_SIDE_STREAM = True
     engine.PROF.force_eager = False
     if rank == 0:
         summ = engine.PROF.summary()
