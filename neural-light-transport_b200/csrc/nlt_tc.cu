@@ -654,8 +654,9 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
   __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 5];
   __shared__ uint32_t tmem_base_smem;
   __shared__ WgPiece pieces[WG_MAX_PIECES];
-  __shared__ int n_pieces_s, raw_bytes_s;
-  __shared__ float bias_part[4][64];
+  __shared__ uint16_t items[64];            // work items of the transform: (piece << 8) | channel quad
+  __shared__ int n_pieces_s, n_items_s, raw_bytes_s;
+  __shared__ float bias_part[64];
 
   const int S = p.raw_stages;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -698,11 +699,15 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
       off += (WG_PT * gw * 4 + 1023) & ~1023;
     }
     n_pieces_s = np;
-    int bytes = 0;
-    for (int i = 0; i < np; ++i) bytes += WG_PT * pieces[i].w * 4;
+    int bytes = 0, ni = 0;
+    for (int i = 0; i < np; ++i) {
+      bytes += WG_PT * pieces[i].w * 4;
+      for (int cq = 0; cq < pieces[i].w / 4; ++cq) items[ni++] = (uint16_t)((i << 8) | cq);
+    }
+    n_items_s = ni;
     raw_bytes_s = bytes;
-    for (int s = 0; s < S; ++s) { mbar_init(bar_rfull(s), 1); mbar_init(bar_rempty(s), 128); }
-    for (int b = 0; b < 2; ++b) { mbar_init(bar_tready(b), 128); mbar_init(bar_tempty(b), 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(bar_rfull(s), 1); mbar_init(bar_rempty(s), 256); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_tready(b), 256); mbar_init(bar_tempty(b), 1); }
     mbar_init(bar_accf, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -776,13 +781,18 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
         if (i == my_tiles - 1) tc_commit(bar_accf);
       }
     }
-  } else if (warp < 6) {
-    // ================= transpose + split =================
-    const int t = threadIdx.x - 64;               // 0..127 ; pixel = t % 32, channel-quad lane = t / 32
+  } else {
+    // ================= transpose + split: all eight remaining warps (2..9) =================
+    // ncu: with four warps this role ran one warp per scheduler at ~0.3 IPC (dependent LDS -> cvt -> STS
+    // chains) and set the stage time; eight warps and two independent items per thread hide that latency.
+    const int t = threadIdx.x - 64;               // 0..255 ; pixel = t % 32, item lane = t / 32
     const int px = t & 31, ql = t >> 5;
-    float gsum[GI][4];
+    const int n_items = n_items_s;
+    constexpr int MAXI = 6;                       // items per thread: 48 items / 8 lanes
+    float gsum[MAXI][4];
 #pragma unroll
-    for (int i = 0; i < GI; ++i) { gsum[i][0] = gsum[i][1] = gsum[i][2] = gsum[i][3] = 0.f; }
+    for (int i = 0; i < MAXI; ++i) { gsum[i][0] = gsum[i][1] = gsum[i][2] = gsum[i][3] = 0.f; }
+    const int pxc = px >> 2, pxo = (px & 3) << 2;
     int stage = 0;
     uint32_t phase = 0;
     for (int it = 0; it < my_tiles; ++it) {
@@ -791,30 +801,28 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
       mbar_wait(bar_tempty(b), ((uint32_t)(it >> 1) & 1) ^ 1);   // MMAs of two stages ago are done with planes b
       const uint8_t* rbase = raw + (size_t)stage * p.raw_stage_bytes;
       uint8_t* pl = planes + (size_t)b * PLANES_BYTES;
-      for (int i = 0; i < n_pieces; ++i) {
-        const WgPiece pc = pieces[i];
-        const int nq = pc.w >> 2;                                 // channel quads of this piece
+#pragma unroll
+      for (int i = 0; i < MAXI; ++i) {
+        const int j = ql + 8 * i;
+        if (j >= n_items) break;
+        const int itm = items[j];
+        const WgPiece pc = pieces[itm >> 8];
+        const int cq = itm & 0xff;
         uint8_t* hi = pl + (pc.is_g ? 2 * WG_PLANE_A : 0);
         const int lo_off = pc.is_g ? PLANE_G : WG_PLANE_A;
-        for (int cq = ql; cq < nq; cq += 4) {
-          const float4 v = *reinterpret_cast<const float4*>(rbase + pc.raw_off + (size_t)px * pc.w * 4 +
-                                                            wg_raw_chunk(pc.w, px, cq) * 16);
-          const float vv[4] = {v.x, v.y, v.z, v.w};
-          if (pc.is_g) {
-            const int gi = ((pc.row >> 2) + cq) >> 2;             // this thread's quads are ql, ql+4, ...
+        const float4 v = *reinterpret_cast<const float4*>(rbase + pc.raw_off + (size_t)px * pc.w * 4 +
+                                                          wg_raw_chunk(pc.w, px, cq) * 16);
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+        if (pc.is_g) { gsum[i][0] += v.x; gsum[i][1] += v.y; gsum[i][2] += v.z; gsum[i][3] += v.w; }
+        const int row0 = pc.row + cq * 4;           // multiple of 4: (row0 + e) & 7 == (row0 & 7) + e
+        const int r7 = row0 & 7;
 #pragma unroll
-            for (int i = 0; i < GI; ++i)
-              if (gi == i) { gsum[i][0] += v.x; gsum[i][1] += v.y; gsum[i][2] += v.z; gsum[i][3] += v.w; }
-          }
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int row = pc.row + cq * 4 + e;
-            // K-major SWIZZLE_128B: 16-byte chunk index XOR (row % 8)
-            const int o = row * 128 + ((((px >> 2) ^ (row & 7)) << 4) | ((px & 3) << 2));
-            const float h = tf32_rna(vv[e]);
-            *reinterpret_cast<float*>(hi + o) = h;
-            *reinterpret_cast<float*>(hi + lo_off + o) = tf32_rna(vv[e] - h);
-          }
+        for (int e = 0; e < 4; ++e) {
+          // K-major SWIZZLE_128B: 16-byte chunk index XOR (row % 8)
+          const int o = (row0 + e) * 128 + (((pxc ^ (r7 + e)) << 4) | pxo);
+          const float h = tf32_rna(vv[e]);
+          *reinterpret_cast<float*>(hi + o) = h;
+          *reinterpret_cast<float*>(hi + lo_off + o) = tf32_rna(vv[e] - h);
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -824,17 +832,20 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
     }
     // bias partial: reduce the 32 pixel lanes of each warp in a fixed butterfly order
 #pragma unroll
-    for (int i = 0; i < GI; ++i)
+    for (int i = 0; i < MAXI; ++i) {
+      const int j = ql + 8 * i;
+      const bool isg = j < n_items && pieces[items[j < n_items ? j : 0] >> 8].is_g;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         float v = gsum[i][e];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        const int q = ql + 4 * i;                                 // this thread's i-th G quad
-        if (px == 0 && q < GQ) bias_part[0][q * 4 + e] = v;
+        if (isg && px == 0) {
+          const int itm = items[j];
+          bias_part[pieces[itm >> 8].row + (itm & 0xff) * 4 + e] = v;
+        }
       }
-  } else {
-    // epilogue warps idle until the accumulation is complete
+    }
   }
   // ---- all partials are ready: accumulator (after accf) and bias sums ----
   __syncthreads();
@@ -866,7 +877,7 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
       }
     }
     if (mtile == 0 && r < BN)
-      p.ws[((size_t)blockIdx.x * p.KD_pad + p.bias_row) * p.ld + ntile * BN + r] = my_tiles > 0 ? bias_part[0][r] : 0.f;
+      p.ws[((size_t)blockIdx.x * p.KD_pad + p.bias_row) * p.ld + ntile * BN + r] = my_tiles > 0 ? bias_part[r] : 0.f;
   }
   tc_fence_before();
   __syncthreads();

@@ -258,3 +258,30 @@ def test_model_api_surface():
     assert m.trainable_variables == []       # lazily built, like Keras
     m.build()
     assert sum(v.numel() for v in m.trainable_variables) == 3368071
+
+
+def test_cfg5_relight_sweep_psnr_vs_oracle(path):
+    """cfg5 in miniature: a relight/view sweep is forward-only inference with the cached
+    observation features (nlt_test.py semantics), samples sharded round-robin over ranks; quality is
+    reported as PSNR(new output, restated-reference output) with xiuminglib's luma PSNR: >= 80 dB."""
+    import nlt_test
+    from util import synth
+    m, cfg = make_model(uvh=64, uvw=64, imh=64, imw=64)
+    oc = ocfg(cfg)
+    params = O.init_params(oc, seed=17, dtype=torch.float64)
+    m.build(5, 3)
+    m.load_params(params)
+    feat = nlt_test.extract_feat(m, [synth.make_batch(2, 64, 64, seed=31)])
+    want_feat = O.extract_feat(params, oc, [(b[1].double(), b[5].double()) for b in [synth.make_batch(2, 64, 64, seed=31)]])
+    world = 2                                   # two virtual ranks, round-robin sample ownership
+    samples = [synth.make_batch(1, 64, 64, seed=200 + i) for i in range(6)]
+    worst = 1e9
+    for rank in range(world):
+        mine = samples[rank::world]
+        outs = nlt_test.infer(m, mine, feat)
+        for bt, got in zip(mine, outs):
+            with torch.no_grad():
+                ref, _, _, _ = O.model_call(params, oc, tuple(t.double() if torch.is_tensor(t) else t for t in bt),
+                                            'test', obs_override=want_feat)
+            worst = min(worst, O.psnr_luma(got[0].cpu().numpy(), ref[0].numpy()))
+    assert worst >= 80.0, worst
