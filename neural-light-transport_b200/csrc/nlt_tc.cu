@@ -28,7 +28,8 @@ constexpr int TC_BM = 128;
 // channels per K-block: 32 (128-byte rows, SWIZZLE_128B) or 16 (64-byte rows, SWIZZLE_64B)
 constexpr int TC_EPI_PAD = 36;                  // floats per staging row (32 columns + 4 pad: conflict-free)
 constexpr int TC_EPI_BYTES = 4 * 32 * TC_EPI_PAD * 4;   // epilogue staging: 4 warps x 32 rows
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 320;               // wgrad kernel: TMA + MMA + 8 transform warps (4 of them double as epilogue)
+constexpr int TCF_THREADS = 448;              // forward kernel: TMA + MMA + 4 transform + 4 epilogue + 4 more transform warps
 constexpr uint32_t TC_SPIN_LIMIT = 1u << 28;    // watchdog: trap instead of hanging the GPU
 unsigned long long g_tc_launches = 0;           // tensor-core kernel launches (diagnostic)
 
@@ -181,7 +182,7 @@ struct TcMaps {
 };
 
 template <int BN, int KBW>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TCF_THREADS, 1)
 tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   constexpr int ROWB = KBW * 4;                   // bytes per operand row
   constexpr int TC_KB = KBW;
@@ -214,7 +215,7 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(bar_full(s), 1);
-      mbar_init(bar_ready(s), 128);
+      mbar_init(bar_ready(s), 256);
       mbar_init(bar_empty(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -294,9 +295,10 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         }
       }
     }
-  } else if (warp < 6) {
-    // ================= operand transform: fp32 -> (hi, lo) TF32 planes =================
-    const int t = threadIdx.x - 64;   // 0..127
+  } else if (warp < 6 || warp >= 10) {
+    // ================= operand transform: fp32 -> (hi, lo) TF32 planes (warps 2-5 and 10-13) =================
+    // eight warps: with four, one warp per scheduler ran this dependent LDS -> cvt -> STS chain at ~0.3 IPC
+    const int t = warp < 6 ? threadIdx.x - 64 : threadIdx.x - 320 + 128;   // 0..255
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -305,8 +307,8 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         float4* ah = reinterpret_cast<float4*>(smem + (size_t)stage * STAGE_BYTES);
         float4* al = reinterpret_cast<float4*>(smem + (size_t)stage * STAGE_BYTES + TC_A_BYTES);
 #pragma unroll
-        for (int i = 0; i < TC_A_BYTES / 16 / 128; ++i) {
-          const int q = t + i * 128;              // physical 16-byte chunk: elementwise, swizzle-agnostic
+        for (int i = 0; i < TC_A_BYTES / 16 / 256; ++i) {
+          const int q = t + i * 256;              // physical 16-byte chunk: elementwise, swizzle-agnostic
           const float4 v = ah[q];
           float4 h, l;
           h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
@@ -1086,7 +1088,7 @@ static int tc_launch_bn(const TcMaps& maps, const TcPlan& pl, cudaStream_t st) {
     attr_set = true;
   }
   const int grid = pl.p.total_tiles < 148 ? pl.p.total_tiles : 148;
-  tc_gconv_kernel<BN, KBW><<<grid, TC_THREADS, pl.smem_bytes, st>>>(maps, pl.p);
+  tc_gconv_kernel<BN, KBW><<<grid, TCF_THREADS, pl.smem_bytes, st>>>(maps, pl.p);
   NLT_CUDA_LAUNCH_CHECK("tc_gconv_kernel");
   __atomic_add_fetch(&g_tc_launches, 1ull, __ATOMIC_RELAXED);
   return NLT_OK;
