@@ -941,7 +941,7 @@ static WgPlan wg_plan(const GConvK& k) {
   }
   p.ntap_x = k.ax.nu; p.nseg = k.nseg; p.ctot = ctot;
   p.Kd = k.ay.nu * k.ax.nu * ctot;
-  if (p.Kd < 64) return pl;       // below half an M tile the warp-stream fp32 kernels win
+  if (p.Kd < 128) return pl;      // measured (also with 8 transform warps): below one full M tile the warp-stream fp32 kernel wins
   int coff = 0;
   for (int s = 0; s < k.nseg; ++s) { p.seg_C[s] = k.seg[s].C; p.seg_coff[s] = coff; coff += k.seg[s].C; }
   p.n_mtiles = (p.Kd + TC_BM - 1) / TC_BM;
