@@ -133,6 +133,13 @@ __device__ __forceinline__ float tf32_rna(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+// Round-to-nearest TF32 in two integer instructions (cvt.rna.tf32 expands to ~8 SASS instructions with its
+// inf/nan handling; ncu showed the operand split bound by exactly that).  Adding half an ulp to the bit
+// pattern and clearing the low 13 mantissa bits rounds the magnitude to nearest (ties away), carries into
+// the exponent correctly, and is only wrong for inf/nan, which the split does not need to preserve.
+__device__ __forceinline__ float tf32_round(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
 // K-major swizzled operand tile: rows of ROWB bytes (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B), 8-row atoms.
 template <int ROWB>
 __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
@@ -194,7 +201,8 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // offset arithmetic on the __shared__ array keeps the address space (LDS/STS instead of generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ __align__(8) uint64_t bars[3 * TC_MAX_STAGES + 4];
   const int TC_STAGES = p.stages;
   __shared__ uint32_t tmem_base_smem;
@@ -311,8 +319,8 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           const int q = t + i * 256;              // physical 16-byte chunk: elementwise, swizzle-agnostic
           const float4 v = ah[q];
           float4 h, l;
-          h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-          l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+          h.x = tf32_round(v.x); h.y = tf32_round(v.y); h.z = tf32_round(v.z); h.w = tf32_round(v.w);
+          l.x = tf32_round(v.x - h.x); l.y = tf32_round(v.y - h.y); l.z = tf32_round(v.z - h.z); l.w = tf32_round(v.w - h.w);
           ah[q] = h;
           al[q] = l;
         }
@@ -652,7 +660,8 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
   constexpr int GI = (GQ + 3) / 4;              // G quads per transform thread
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // offset arithmetic on the __shared__ array keeps the address space (LDS/STS instead of generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 5];
   __shared__ uint32_t tmem_base_smem;
   __shared__ WgPiece pieces[WG_MAX_PIECES];
@@ -822,9 +831,9 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
         for (int e = 0; e < 4; ++e) {
           // K-major SWIZZLE_128B: 16-byte chunk index XOR (row % 8)
           const int o = (row0 + e) * 128 + (((pxc ^ (r7 + e)) << 4) | pxo);
-          const float h = tf32_rna(vv[e]);
+          const float h = tf32_round(vv[e]);
           *reinterpret_cast<float*>(hi + o) = h;
-          *reinterpret_cast<float*>(hi + lo_off + o) = tf32_rna(vv[e] - h);
+          *reinterpret_cast<float*>(hi + lo_off + o) = tf32_round(vv[e] - h);
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
