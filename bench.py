@@ -155,7 +155,7 @@ def run_reference(args):
                          'kind': 'port', 'sample': sample},
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world):
@@ -326,9 +326,28 @@ def run_b200(args):
                     'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4},
             'gpu_launches': launches, 'tcgen05_launches': tc_launches, 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+_JSON_OUT = None
+
+
+def _guard_stdout():
+    """Keep stdout to the ONE JSON line of the contract: native libraries write banners to fd 1
+    (NCCL prints its version there on the first communicator), so fd 1 is pointed at stderr and the
+    result line goes to a private duplicate of the original stdout."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
 
 
 def main():
@@ -345,6 +364,7 @@ def main():
     ap.add_argument('--no-graph', dest='no_graph', action='store_true', help='launch kernels eagerly (no CUDA graph)')
     ap.add_argument('--profile-out', dest='profile_out', default=None, help='write the per-op device-time table here')
     args = ap.parse_args()
+    _guard_stdout()
     if args.impl == 'reference':
         run_reference(args)
     else:
