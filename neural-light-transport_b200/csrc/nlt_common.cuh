@@ -133,6 +133,8 @@ int launch_pw_conv(const GConvK& k, const float* bias, int act, float beta, cons
 bool dconv_small_applicable(const GConvK& k);
 int launch_dconv_small(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
                        float* out, cudaStream_t st);
+// 1: row-run warp-stream wgrad where float4 access allows it (default), 0: flat-pixel kernel only
+extern int g_opt_wgrad_rows;
 bool wgrad_small_applicable(const GConvK& k);
 size_t wgrad_small_ws_floats(const GConvK& k);
 // fills w (nsplit, pix_per_split, ld, KG, GS) and *KD_pad for the reduce stage

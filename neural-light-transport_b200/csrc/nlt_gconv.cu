@@ -633,6 +633,7 @@ int nlt_set_option(const char* name, int value) {
   NLT_CHECK_ARG(name != nullptr, "null option name");
   if (strcmp(name, "tc") == 0) { g_opt_tc = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "tc_wgrad") == 0) { g_opt_tc_wgrad = value ? 1 : 0; return NLT_OK; }
+  if (strcmp(name, "wgrad_rows") == 0) { nlt::g_opt_wgrad_rows = value ? 1 : 0; return NLT_OK; }
   return set_err(NLT_ERR_INVALID, "unknown option '%s'", name);
 }
 

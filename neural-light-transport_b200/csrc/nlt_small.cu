@@ -627,6 +627,152 @@ wgrad_small_kernel(const WgradK w, const float* __restrict__ G, float* __restric
 }
 
 // -----------------------------------------------------------------------------
+// Row-run form of the warp-stream wgrad.  ncu on wgrad_small_kernel<4,2,4>: ~170 warp instructions per
+// pixel for 36 FMAs -- the flat pixel index is decoded and every source address rebuilt from scratch for
+// every pixel.  Here a warp owns a run of WR_CHUNK consecutive lattice pixels of one row: (n, ty) and all
+// base pointers are set up once per run and the pixel loop only adds constant strides.  Requires float4
+// access everywhere (all segments vec, no subtracted source, gradient channels % 4 == 0); same workspace layout and the same
+// fixed-order reduction as wgrad_small_kernel, so the two are interchangeable.
+// -----------------------------------------------------------------------------
+constexpr int WR_CHUNK = 64;
+
+template <int NQ, int P, int U>
+__global__ void __launch_bounds__(WS_THREADS)
+wgrad_rows_kernel(const WgradK w, const float* __restrict__ G, float* __restrict__ ws, const uint32_t cpr,
+                  const uint32_t nchunks) {
+  constexpr int KQ = 32 / NQ;
+  constexpr int ROWS = (P * KQ + 1) * 4;
+  constexpr int LD = NQ * 4;
+  __shared__ float tile[ROWS * LD];
+
+  const GConvK& g = w.g;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int kq = lane / NQ, nq = lane % NQ;
+
+  const float* jptr[P];
+  int jstr[P], jdy[P], jdx[P], jimg[P];   // pixel stride (floats), tap offsets, image stride (0: broadcast)
+  bool jlive[P];
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    int uy, ux, s, c;
+    decode_kgroup(w, kq + j * KQ, uy, ux, s, c);
+    jptr[j] = nullptr; jstr[j] = 0; jdy[j] = 0; jdx[j] = 0; jimg[j] = 0; jlive[j] = false;
+    if (s >= 0) {
+      const Seg sg = g.seg[s];
+      jptr[j] = sg.ptr + c;
+      jstr[j] = sg.C;
+      jdy[j] = uy * g.ay.iu + g.ay.i0; jdx[j] = ux * g.ax.iu + g.ax.i0;
+      jimg[j] = sg.bcast ? 0 : 1;
+      jlive[j] = true;
+    }
+  }
+  // gradient column quad of this lane -> fixed (dy, dx, channel) inside the output pixel block
+  int g_dy = 0, g_dx = 0, g_cb = nq * 4, g_sy = g.ay.os, g_sx = g.ax.os, g_y0 = g.ay.o0, g_x0 = g.ax.o0;
+  if (g.d2s) {
+    const int tap = (nq * 4) / g.cout_true;
+    g_cb = nq * 4 - tap * g.cout_true;
+    g_dy = tap / g.d2s_s; g_dx = tap - g_dy * g.d2s_s;
+    g_sy = g.d2s_s; g_sx = g.d2s_s; g_y0 = 0; g_x0 = 0;
+  }
+  const bool g_live = nq * 4 < g.Cout;
+  const int g_str = g_sx * g.cout_true;
+
+  float acc[P][4][4];
+  float gsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < P; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+      for (int f = 0; f < 4; ++f) acc[j][e][f] = 0.f;
+
+  const int ntx = g.ax.nt, nty = g.ay.nt;
+  for (uint32_t ch = blockIdx.x * WS_WARPS + warp; ch < nchunks; ch += gridDim.x * WS_WARPS) {
+    const uint32_t row = ch / cpr;
+    const int x0 = (int)(ch - row * cpr) * WR_CHUNK;
+    const int xend = min(ntx, x0 + WR_CHUNK);
+    const int n = (int)(row / (uint32_t)nty), ty = (int)(row - (uint32_t)n * nty);
+
+    const float* gp = G + (((size_t)n * g.Hout + (g_y0 + g_sy * ty + g_dy)) * g.Wout + (g_x0 + g_dx)) * g.cout_true + g_cb;
+    const float* pa[P];
+    bool oky[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const int iy = ty * g.ay.it + jdy[j];
+      oky[j] = jlive[j] && (unsigned)iy < (unsigned)g.Hin;
+      const long long off = (((long long)(jimg[j] ? n : 0) * g.Hin + iy) * g.Win + jdx[j]) * jstr[j];
+      pa[j] = jptr[j] + off;
+    }
+
+    for (int x = x0; x < xend; x += U) {
+      float4 a[U][P], gv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int xx = x + u;
+        const bool in = xx < xend;
+        gv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (in && g_live) gv[u] = ld4(gp + (long long)xx * g_str);
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+          const int ix = xx * g.ax.it;
+          const bool ok = in && oky[j] && (unsigned)(ix + jdx[j]) < (unsigned)g.Win;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok) v = ld4(pa[j] + (long long)ix * jstr[j]);
+          a[u][j] = v;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float gg[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+#pragma unroll
+        for (int f = 0; f < 4; ++f) gsum[f] += gg[f];
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+          const float aa[4] = {a[u][j].x, a[u][j].y, a[u][j].z, a[u][j].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int f = 0; f < 4; ++f) acc[j][e][f] = fmaf(aa[e], gg[f], acc[j][e][f]);
+        }
+      }
+    }
+  }
+
+  for (int i = tid; i < ROWS * LD; i += WS_THREADS) tile[i] = 0.f;
+  __syncthreads();
+  const int bias_row = (w.KG - 1) * 4;
+  for (int wi = 0; wi < WS_WARPS; ++wi) {
+    if (warp == wi) {
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        if (!jlive[j]) continue;
+        const int kg = kq + j * KQ;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+          for (int f = 0; f < 4; ++f) tile[(kg * 4 + e) * LD + nq * 4 + f] += acc[j][e][f];
+      }
+      if (kq == 0) {
+#pragma unroll
+        for (int f = 0; f < 4; ++f) tile[bias_row * LD + nq * 4 + f] += gsum[f];
+      }
+    }
+    __syncthreads();
+  }
+  float* dst = ws + (size_t)blockIdx.x * ROWS * LD;
+  for (int i = tid; i < ROWS * LD; i += WS_THREADS) dst[i] = tile[i];
+}
+
+int g_opt_wgrad_rows = 1;
+
+static bool wgrad_rows_ok(const GConvK& k, const float* G) {
+  if (k.cout_true % 4 != 0 || k.Cout % 4 != 0 || !aligned16(G)) return false;
+  for (int s = 0; s < k.nseg; ++s)
+    if (!k.seg[s].vec || k.seg[s].sub != nullptr) return false;
+  return true;
+}
+
+// -----------------------------------------------------------------------------
 // thread-per-pixel wgrad for tiny results (K*N <= ~128: level-0 convs, final
 // conv, the 4->4 full-resolution deconv).  Every THREAD owns a pixel stream and
 // the complete dW tile in registers, so per pixel it costs only the loads and
@@ -854,7 +1000,17 @@ int launch_wgrad_small(const GConvK& k, const float* G, float* ws, WgradK* w, si
   w->g = k; w->GS = pl.GS; w->KG = pl.KG; w->ld = pl.ld; w->nsplit = pl.nsplit; w->pix_per_split = pl.pps;
   *KD_pad = pl.KD_pad;
   const unsigned grid = pl.nsplit;
-#define NLT_WS(NQ_, P_) wgrad_small_kernel<NQ_, P_, (P_ == 1 ? 8 : P_ == 2 ? 4 : 2)><<<grid, WS_THREADS, 0, st>>>(*w, G, ws)
+  const bool rows = g_opt_wgrad_rows == 1 && wgrad_rows_ok(k, G);
+  const uint32_t cpr = ((uint32_t)k.ax.nt + WR_CHUNK - 1) / WR_CHUNK;
+  const uint32_t nchunks = (uint32_t)k.N * (uint32_t)k.ay.nt * cpr;
+#define NLT_WS(NQ_, P_)                                                                                        \
+  do {                                                                                                         \
+    if (rows)                                                                                                  \
+      wgrad_rows_kernel<NQ_, P_, (P_ == 1 ? 8 : P_ == 2 ? 4 : 2)><<<grid, WS_THREADS, 0, st>>>(*w, G, ws, cpr, \
+                                                                                               nchunks);       \
+    else                                                                                                       \
+      wgrad_small_kernel<NQ_, P_, (P_ == 1 ? 8 : P_ == 2 ? 4 : 2)><<<grid, WS_THREADS, 0, st>>>(*w, G, ws);   \
+  } while (0)
   if (pl.nq == 8) {
     if (pl.p == 1) NLT_WS(8, 1); else if (pl.p == 2) NLT_WS(8, 2); else if (pl.p == 4) NLT_WS(8, 4); else NLT_WS(8, 5);
   } else if (pl.nq == 4) {

@@ -73,6 +73,11 @@ GEOMS = [
     ('conv', 2, 2, 32, 32, [16, 16], 16),       # level-1 query conv shape
     ('conv', 2, 1, 16, 16, [16], 16),
     ('deconv', 2, 2, 16, 16, [16, 32, 32], 8),  # level-11 up-conv shape: N' = 32
+    # row-run weight-gradient kernel: runs of 64 lattice pixels, ragged last run, SAME padding on both sides
+    ('conv', 2, 1, 8, 72, [16], 16),
+    ('conv', 3, 1, 9, 70, [8], 8),
+    ('deconv', 2, 2, 8, 40, [8, 32], 4),
+    ('conv', 2, 2, 6, 200, [16, 16], 16),
     ('deconv', 2, 1, 32, 16, [16], 16),
     ('conv', 2, 2, 64, 64, [32, 16], 32),       # mixed 32/16 sources -> 16-wide blocks
 ]
@@ -157,6 +162,42 @@ def test_tensor_core_vs_fp32_kernels(kind, k, s, H, W, segc, cout):
     assert rel(res['tc']['gb'], res['fp32']['gb']) <= 2e-5
     for a, b in zip(res['tc']['gx'], res['fp32']['gx']):
         assert rel(a, b) <= 1e-5
+
+
+ROWS_SHAPES = [g for g in GEOMS if all(c % 4 == 0 for c in g[5]) and g[6] % 4 == 0 and g[6] <= 16]
+
+
+@pytest.mark.parametrize('kind,k,s,H,W,segc,cout', ROWS_SHAPES)
+def test_wgrad_row_run_vs_flat_pixel_kernel(kind, k, s, H, W, segc, cout):
+    """A/B on identical inputs: the row-run warp-stream weight-gradient kernel against the flat-pixel form of
+    the same library (option "wgrad_rows"); both accumulate in fp32 in different orders."""
+    engine, nat = _mods()
+    dev = torch.device('cuda')
+    torch.manual_seed(11)
+    N = 3
+    xs = [torch.randn(N, H, W, c, device=dev) for c in segc]
+    dzs = None
+    res = {}
+    nat.set_option('tc', 0)
+    try:
+        for mode in (1, 0):
+            nat.set_option('wgrad_rows', mode)
+            L = engine.ConvLayer(kind, k, s, cout, 'leakyrelu')
+            L.build(sum(segc), dev, torch.Generator().manual_seed(1))
+            acts = [engine.Act(x, act='leakyrelu', needs_grad=True) for x in xs]
+            tape = engine.Tape()
+            y = L.forward([engine.Seg(a) for a in acts], tape)
+            if dzs is None:
+                dzs = torch.randn_like(y.t)
+            y.grad = dzs.clone()
+            tape.backward()
+            res[mode] = (L.gkernel.clone(), L.gbias.clone())
+    finally:
+        nat.set_option('wgrad_rows', 1)
+        nat.set_option('tc', 1)
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+    assert rel(res[1][0], res[0][0]) <= 1e-5
+    assert rel(res[1][1], res[0][1]) <= 1e-5
 
 
 def test_tensor_core_path_is_taken_and_matches_fp32_path():
