@@ -636,8 +636,8 @@ wgrad_small_kernel(const WgradK w, const float* __restrict__ G, float* __restric
 // -----------------------------------------------------------------------------
 constexpr int WR_CHUNK = 64;
 
-template <int NQ, int P, int U>
-__global__ void __launch_bounds__(WS_THREADS)
+template <int NQ, int P, int U, int MINB>
+__global__ void __launch_bounds__(WS_THREADS, MINB)
 wgrad_rows_kernel(const WgradK w, const float* __restrict__ G, float* __restrict__ ws, const uint32_t cpr,
                   const uint32_t nchunks) {
   constexpr int KQ = 32 / NQ;
@@ -1003,13 +1003,16 @@ int launch_wgrad_small(const GConvK& k, const float* G, float* ws, WgradK* w, si
   const bool rows = g_opt_wgrad_rows == 1 && wgrad_rows_ok(k, G);
   const uint32_t cpr = ((uint32_t)k.ax.nt + WR_CHUNK - 1) / WR_CHUNK;
   const uint32_t nchunks = (uint32_t)k.N * (uint32_t)k.ay.nt * cpr;
+  // measured on B200 (profiles/r1_h): P <= 2 wants occupancy (128 registers, 4 CTAs per SM), the wide
+  // P >= 4 tiles want more pixels in flight instead (they spill below ~220 registers)
 #define NLT_WS(NQ_, P_)                                                                                        \
   do {                                                                                                         \
+    constexpr int U0 = (P_ == 1 ? 8 : P_ == 2 ? 4 : 2);                                                        \
     if (rows)                                                                                                  \
-      wgrad_rows_kernel<NQ_, P_, (P_ == 1 ? 8 : P_ == 2 ? 4 : 2)><<<grid, WS_THREADS, 0, st>>>(*w, G, ws, cpr, \
-                                                                                               nchunks);       \
+      wgrad_rows_kernel<NQ_, P_, (P_ <= 2 ? U0 : 2 * U0), (P_ <= 2 ? 4 : 1)>                                   \
+          <<<grid, WS_THREADS, 0, st>>>(*w, G, ws, cpr, nchunks);                                              \
     else                                                                                                       \
-      wgrad_small_kernel<NQ_, P_, (P_ == 1 ? 8 : P_ == 2 ? 4 : 2)><<<grid, WS_THREADS, 0, st>>>(*w, G, ws);   \
+      wgrad_small_kernel<NQ_, P_, U0><<<grid, WS_THREADS, 0, st>>>(*w, G, ws);                                 \
   } while (0)
   if (pl.nq == 8) {
     if (pl.p == 1) NLT_WS(8, 1); else if (pl.p == 2) NLT_WS(8, 2); else if (pl.p == 4) NLT_WS(8, 4); else NLT_WS(8, 5);
