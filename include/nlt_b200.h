@@ -97,6 +97,27 @@ int nlt_gconv_fwd_ws(const nlt_gconv_desc* d, const float* bias, int act,
                      float beta, const float* mask_y, int mask_act, float* out,
                      void* workspace, int64_t workspace_bytes, void* stream);
 
+/* A second, pointwise term fused into the epilogue of a pointwise op (1x1 stride-1 conv, or a
+ * k == stride transposed conv in its depth-to-space form):
+ *   out[n,y,x,c] = mask( act(conv_d(...)[n,y,x,c] + bias[c]) + sum_k x[n,y,x,k] * w[k*w_k_stride + c*w_n_stride]
+ *                        + beta * out[n,y,x,c] )
+ * x has the spatial shape of `out` and K <= 4 channels.  Use: the input gradient of the final 1x1 conv
+ * (networks/convnet.py:65-70, 36 -> 3) w.r.t. the level-0 skip tensors rides on the launch of the level-1
+ * down-conv's input gradient, which writes the same tensor -- one write + one read-modify-write pass over a
+ * full-resolution 16-channel tensor less per skip.  _supported() returns 1 when the op is served by the
+ * pointwise kernel with float4 stores (else 0); _fused() returns NLT_ERR_UNSUPPORTED in that case and the
+ * caller issues the two ops separately. */
+typedef struct nlt_pw_term {
+  const float* x;
+  int32_t K;
+  const float* w;
+  int64_t w_k_stride, w_n_stride;
+} nlt_pw_term;
+int nlt_gconv_fwd_fused_supported(const nlt_gconv_desc* d, const nlt_pw_term* term,
+                                  const float* mask_y, const float* out);
+int nlt_gconv_fwd_fused(const nlt_gconv_desc* d, const nlt_pw_term* term, const float* bias, int act,
+                        float beta, const float* mask_y, int mask_act, float* out, void* stream);
+
 /* Weight/bias gradient of the op described by d:
  *   dW[tap,c,n] (+)= sum_p A[map(p,tap),c] * G[p,n],   db[n] (+)= sum_p G[p,n]
  * written with the same strides as d->w.  Deterministic (two-stage split

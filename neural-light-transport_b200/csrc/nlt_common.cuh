@@ -127,9 +127,18 @@ __device__ __forceinline__ void decode_kgroup(const WgradK& w, int kg, int& uy, 
 }
 
 // specialised small-channel kernels (nlt_small.cu); return NLT_OK or an error
+// second, pointwise term of the pointwise kernel's epilogue (see pw_conv_kernel)
+constexpr int PW_EX_KMAX = 4;
+struct PwExtra {
+  const float* x;      // [output pixels][K]
+  int K;
+  const float* w;      // w[k * wk + c * wn], c < cout_true
+  long long wk, wn;
+};
 bool pw_conv_applicable(const GConvK& k);
+bool pw_extra_applicable(const GConvK& k, const PwExtra& ex, const float* out, const float* mask_y);
 int launch_pw_conv(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
-                   float* out, cudaStream_t st);
+                   float* out, cudaStream_t st, const PwExtra* ex = nullptr);
 bool dconv_small_applicable(const GConvK& k);
 int launch_dconv_small(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
                        float* out, cudaStream_t st);

@@ -117,7 +117,7 @@ __device__ __forceinline__ void chunk_advance(const GConvK& g, ChunkIt& it) {
 
 
 template <int TM, int TN, int RM, int RN, int NTHR>
-__global__ void __launch_bounds__(NTHR)
+__global__ void __launch_bounds__(NTHR, 3)   // 3 CTAs per SM measured best (2: latency-bound, 4: spills)
 gconv_kernel(const GConvK g, const float* __restrict__ bias, const int act, const float beta,
              const float* __restrict__ mask_y, const int mask_act, float* __restrict__ out) {
   constexpr int TNT = TN / RN;          // threads along n
@@ -671,6 +671,41 @@ int nlt_gconv_fwd_ws(const nlt_gconv_desc* d, const float* bias, int act, float 
     if (rc != NLT_OK) return rc;
   }
   return NLT_OK;
+}
+
+static int pw_term_phase(const nlt_gconv_desc* d, const nlt_pw_term* term, GConvK* k, PwExtra* ex) {
+  GConvK ph[16];
+  int np = 0;
+  int rc = build_phases(d, ph, &np, /*allow_d2s=*/true);
+  if (rc != NLT_OK) return rc;
+  NLT_CHECK_ARG(term != nullptr && term->x != nullptr && term->w != nullptr, "null pointwise term");
+  if (np != 1) return NLT_ERR_UNSUPPORTED;
+  *k = ph[0];
+  ex->x = term->x; ex->K = term->K; ex->w = term->w; ex->wk = term->w_k_stride; ex->wn = term->w_n_stride;
+  return NLT_OK;
+}
+
+int nlt_gconv_fwd_fused_supported(const nlt_gconv_desc* d, const nlt_pw_term* term, const float* mask_y,
+                                  const float* out) {
+  GConvK k;
+  PwExtra ex;
+  if (pw_term_phase(d, term, &k, &ex) != NLT_OK) return 0;
+  return (k.M > 0 && pw_extra_applicable(k, ex, out, mask_y)) ? 1 : 0;
+}
+
+int nlt_gconv_fwd_fused(const nlt_gconv_desc* d, const nlt_pw_term* term, const float* bias, int act, float beta,
+                        const float* mask_y, int mask_act, float* out, void* stream) {
+  GConvK k;
+  PwExtra ex;
+  int rc = pw_term_phase(d, term, &k, &ex);
+  if (rc == NLT_ERR_UNSUPPORTED) return set_err(NLT_ERR_UNSUPPORTED, "fused pointwise term: op is not a single-phase pointwise op");
+  if (rc != NLT_OK) return rc;
+  NLT_CHECK_ARG(out != nullptr, "null output");
+  NLT_CHECK_ARG(act >= 0 && act <= 3 && mask_act >= 0 && mask_act <= 3, "bad activation code");
+  NLT_CHECK_ARG(beta == 0.f || beta == 1.f, "beta must be 0 or 1");
+  if (k.M == 0 || !pw_extra_applicable(k, ex, out, mask_y))
+    return set_err(NLT_ERR_UNSUPPORTED, "fused pointwise term: shape not served by the pointwise kernel");
+  return launch_pw_conv(k, bias, act, beta, mask_y, mask_act, out, (cudaStream_t)stream, &ex);
 }
 
 int nlt_gconv_fwd(const nlt_gconv_desc* d, const float* bias, int act, float beta, const float* mask_y,

@@ -45,14 +45,34 @@ bool pw_conv_applicable(const GConvK& k) {
 // QT = 4 means a thread owns 16 output channels of a pixel: every input value is loaded once per 64 FMAs
 // and the thread stores 64 contiguous bytes (ncu showed the QT = 1 form issue-bound: ~14 overhead
 // instructions per FMA).
-template <int NQ, int QT, int R>
-__global__ void __launch_bounds__(PW_THREADS)
+// 4 CTAs per SM (64 registers, a few spilled words outside the k loop): the kernel is latency-bound, and
+// measured 3-8 % faster per launch than the 2-3 CTAs the unconstrained allocation (90+ registers) allows.
+//
+// EX: a second, pointwise term on the OUTPUT lattice is added in the epilogue,
+//   out[pix, c] += sum_k ex.x[pix, k] * ex.w[k * wk + c * wn]        (k < ex.K <= PW_EX_KMAX)
+// which lets the input gradient of a 1x1 conv ride on the launch that writes the same tensor (no extra
+// write + read-modify-write pass over it).
+template <int NQ, int QT, int R, int EXM>
+__global__ void __launch_bounds__(PW_THREADS, 4)
 pw_conv_kernel(const GConvK g, const float* __restrict__ bias, const int act, const float beta,
-               const float* __restrict__ mask_y, const int mask_act, float* __restrict__ out) {
+               const float* __restrict__ mask_y, const int mask_act, float* __restrict__ out, const PwExtra ex) {
   static_assert(NQ % QT == 0, "quads per thread");
   constexpr int LPP = NQ / QT;            // lanes per pixel
+  constexpr bool EX = EXM != 0;           // fused pointwise term; EXM: 1 same pixel, 2 lane-per-tap shuffle, 3 per quad
+  static_assert(EXM != 2 || (LPP > 1 && LPP == QT), "shuffle mode: one lane per tap");
   __shared__ float4 Ws[PW_KMAX * NQ];     // [k][quad] : 4 consecutive GEMM columns
+  __shared__ float4 Wx[EX ? PW_EX_KMAX * 16 : 1];   // [k][channel quad of the output pixel] (cout_true <= 64)
   const int tid = threadIdx.x;
+  if (EX) {
+    const int cq = g.cout_true >> 2;
+    for (int idx = tid; idx < ex.K * cq; idx += PW_THREADS) {
+      const int k = idx / cq, q = idx - k * cq;
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = __ldg(ex.w + (long long)k * ex.wk + (long long)(q * 4 + e) * ex.wn);
+      Wx[idx] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
   const int tap = (g.ay.d0) * g.kw + g.ax.d0;
   int K = 0;
   for (int s = 0; s < g.nseg; ++s) K += g.seg[s].C;
@@ -69,7 +89,12 @@ pw_conv_kernel(const GConvK g, const float* __restrict__ bias, const int act, co
   __syncthreads();
 
   constexpr int PPB = PW_THREADS / LPP;    // pixels per pass
-  const int q0 = (tid % LPP) * QT;         // first quad of this thread
+  // quad j of this thread is QD(j) = qa + j * LPP: the LPP lanes of a pixel hold ADJACENT quads, so each
+  // 16-byte load / store instruction of the epilogue covers LPP*16 contiguous bytes per pixel (whole
+  // 32-byte sectors) instead of 16 bytes out of every QT*16
+  const int qa = tid % LPP;
+  const int lane_in_warp = tid & 31;
+#define QD(j_) (qa + (j_) * LPP)
   const uint32_t pbase = (uint32_t)blockIdx.x * (PPB * R) + tid / LPP;
   const uint32_t hw = g.div_yx.d;
 
@@ -83,16 +108,40 @@ pw_conv_kernel(const GConvK g, const float* __restrict__ bias, const int act, co
   }
 #pragma unroll
   for (int j = 0; j < QT; ++j) {
-    int cb = (q0 + j) * 4;
+    int cb = QD(j) * 4;
     if (g.d2s) cb -= (cb / g.cout_true) * g.cout_true;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float b = (bias != nullptr && (q0 + j) * 4 + e < g.Cout) ? __ldg(bias + cb + e) : 0.f;
+      const float b = (bias != nullptr && QD(j) * 4 + e < g.Cout) ? __ldg(bias + cb + e) : 0.f;
 #pragma unroll
       for (int r = 0; r < R; ++r) acc[r][j][e] = b;
     }
   }
 
+  // fused pointwise term: its K inputs per output pixel are fetched BEFORE the k loop, so that their latency
+  // overlaps the main loads (fetched in the epilogue they add an exposed memory round trip to a
+  // latency-bound kernel: measured +25 % per launch).  Modes (chosen by the host, pw_extra_mode):
+  //   1 (not depth-to-space): all quads of the thread belong to output pixel p.
+  //   2 (depth-to-space, one tap = 4*LPP channels, QT taps): quad j of every lane of the pixel's lane
+  //     group belongs to tap j; lane a fetches tap a's pixel and the epilogue reads it by shuffle.
+  //   3: anything else -- fetched per quad in the epilogue.
+  constexpr int ex_mode = EXM == 3 ? 0 : EXM;
+  float xs[EX ? R : 1][PW_EX_KMAX];
+  if (EX && ex_mode != 0) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      size_t pix = p[r];
+      if (ex_mode == 2) {
+        int n, ty, tx;
+        decode_pixel(g, p[r], n, ty, tx);
+        const int dy = qa / g.d2s_s, dx = qa - dy * g.d2s_s;     // tap index == lane index in the group
+        pix = ((size_t)n * g.Hout + ty * g.d2s_s + dy) * g.Wout + tx * g.d2s_s + dx;
+      }
+#pragma unroll
+      for (int k2 = 0; k2 < PW_EX_KMAX; ++k2)
+        xs[r][k2] = (ok[r] && k2 < ex.K) ? __ldg(ex.x + pix * ex.K + k2) : 0.f;
+    }
+  }
   int k = 0;
   for (int s = 0; s < g.nseg; ++s) {
     const Seg sg = g.seg[s];
@@ -119,7 +168,7 @@ pw_conv_kernel(const GConvK g, const float* __restrict__ bias, const int act, co
         for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
           for (int j = 0; j < QT; ++j) {
-            const float4 w = Ws[(k + kk) * NQ + q0 + j];
+            const float4 w = Ws[(k + kk) * NQ + QD(j)];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
               acc[r][j][0] = fmaf(a[r][kk], w.x, acc[r][j][0]); acc[r][j][1] = fmaf(a[r][kk], w.y, acc[r][j][1]);
@@ -142,7 +191,7 @@ pw_conv_kernel(const GConvK g, const float* __restrict__ bias, const int act, co
         }
 #pragma unroll
         for (int j = 0; j < QT; ++j) {
-          const float4 w = Ws[k * NQ + q0 + j];
+          const float4 w = Ws[k * NQ + QD(j)];
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             acc[r][j][0] = fmaf(a[r], w.x, acc[r][j][0]); acc[r][j][1] = fmaf(a[r], w.y, acc[r][j][1]);
@@ -154,80 +203,138 @@ pw_conv_kernel(const GConvK g, const float* __restrict__ bias, const int act, co
     }
   }
 
-  const bool vec_out = (g.cout_true % 4 == 0) && aligned16(out) && (mask_y == nullptr || aligned16(mask_y));
+  // the fused instantiations are only launched on the float4 output path (pw_extra_applicable)
+  const bool vec_out = EX || ((g.cout_true % 4 == 0) && aligned16(out) && (mask_y == nullptr || aligned16(mask_y)));
   const bool rmw = (beta != 0.f) || (mask_y != nullptr);
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     if (!ok[r]) continue;
-    // destination of quad (q0 + j): consecutive quads are consecutive channels of one output pixel
+    // destination of quad QD(j): consecutive quads are consecutive channels of one output pixel
     size_t ob[QT];
+    uint32_t opx[EX ? QT : 1];     // output pixel / channel quad of each column quad (fused pointwise term)
+    int ocq[EX ? QT : 1];
     int n = 0, ty = 0, tx = 0;
     if (g.d2s) decode_pixel(g, p[r], n, ty, tx);
 #pragma unroll
     for (int j = 0; j < QT; ++j) {
-      const int col = (q0 + j) * 4;
+      const int col = QD(j) * 4;
       if (g.d2s) {
         const int t = col / g.cout_true, cb = col - t * g.cout_true;
         const int dy = t / g.d2s_s, dx = t - dy * g.d2s_s;
-        ob[j] = (((size_t)n * g.Hout + ty * g.d2s_s + dy) * g.Wout + tx * g.d2s_s + dx) * g.cout_true + cb;
+        const size_t pix = ((size_t)n * g.Hout + ty * g.d2s_s + dy) * g.Wout + tx * g.d2s_s + dx;
+        ob[j] = pix * g.cout_true + cb;
+        if (EX) { opx[j] = (uint32_t)pix; ocq[j] = cb >> 2; }
       } else {
         ob[j] = (size_t)p[r] * g.Cout + col;
+        if (EX) { opx[j] = p[r]; ocq[j] = col >> 2; }
       }
     }
-    float4 oldv[QT], yv[QT];
+    // read-modify-write operands are fetched EB quads at a time before the first store of the group
+    // (all QT at once costs 8 more registers per quad and a whole CTA per SM of occupancy)
+    constexpr int EB = QT >= 2 ? 2 : 1;
 #pragma unroll
-    for (int j = 0; j < QT; ++j) {        // batch the read-modify-write operands before the first store
-      oldv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      yv[j] = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (rmw && vec_out && (q0 + j) * 4 < g.Cout) {
-        if (beta != 0.f) oldv[j] = *reinterpret_cast<const float4*>(out + ob[j]);
-        if (mask_y != nullptr) yv[j] = ld4(mask_y + ob[j]);
-      }
-    }
+    for (int j0 = 0; j0 < QT; j0 += EB) {
+      float4 oldv[EB], yv[EB];
 #pragma unroll
-    for (int j = 0; j < QT; ++j) {
-      if ((q0 + j) * 4 >= g.Cout) continue;
-      float v[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) v[e] = act_fwd(acc[r][j][e], act);
-      if (vec_out) {
-        const float4 o = oldv[j], y = yv[j];
-        v[0] += beta * o.x; v[1] += beta * o.y; v[2] += beta * o.z; v[3] += beta * o.w;
-        if (mask_y != nullptr) {
-          v[0] *= act_bwd_from_y(y.x, mask_act); v[1] *= act_bwd_from_y(y.y, mask_act);
-          v[2] *= act_bwd_from_y(y.z, mask_act); v[3] *= act_bwd_from_y(y.w, mask_act);
+      for (int jj = 0; jj < EB; ++jj) {
+        const int j = j0 + jj;
+        oldv[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+        yv[jj] = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (rmw && vec_out && QD(j) * 4 < g.Cout) {
+          if (beta != 0.f) oldv[jj] = *reinterpret_cast<const float4*>(out + ob[j]);
+          if (mask_y != nullptr) yv[jj] = ld4(mask_y + ob[j]);
         }
-        *reinterpret_cast<float4*>(out + ob[j]) = make_float4(v[0], v[1], v[2], v[3]);
-      } else {
+      }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if ((q0 + j) * 4 + e >= g.Cout) continue;
-          float t = v[e];
-          if (beta != 0.f) t += beta * out[ob[j] + e];
-          if (mask_y != nullptr) t *= act_bwd_from_y(__ldg(mask_y + ob[j] + e), mask_act);
-          out[ob[j] + e] = t;
+      for (int jj = 0; jj < EB; ++jj) {
+        const int j = j0 + jj;
+        if (QD(j) * 4 >= g.Cout) continue;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = act_fwd(acc[r][j][e], act);
+        if (EX) {     // host guarantees the float4 output path (cout_true % 4 == 0)
+          if (ex_mode != 0) {
+#pragma unroll
+            for (int k2 = 0; k2 < PW_EX_KMAX; ++k2) {
+              float a2 = xs[r][k2];
+              if (LPP > 1 && ex_mode == 2)       // tap j's pixel was fetched by lane j of this pixel's lane group
+                a2 = __shfl_sync(((1u << LPP) - 1u) << (lane_in_warp & ~(LPP - 1)), a2, j, LPP);
+              if (k2 < ex.K) {
+                const float4 wv = Wx[k2 * (g.cout_true >> 2) + ocq[j]];
+                v[0] = fmaf(a2, wv.x, v[0]); v[1] = fmaf(a2, wv.y, v[1]);
+                v[2] = fmaf(a2, wv.z, v[2]); v[3] = fmaf(a2, wv.w, v[3]);
+              }
+            }
+          } else {
+            const float* xp = ex.x + (size_t)opx[j] * ex.K;
+            for (int k2 = 0; k2 < ex.K; ++k2) {
+              const float a2 = __ldg(xp + k2);
+              const float4 wv = Wx[k2 * (g.cout_true >> 2) + ocq[j]];
+              v[0] = fmaf(a2, wv.x, v[0]); v[1] = fmaf(a2, wv.y, v[1]);
+              v[2] = fmaf(a2, wv.z, v[2]); v[3] = fmaf(a2, wv.w, v[3]);
+            }
+          }
+        }
+        if (vec_out) {
+          const float4 o = oldv[jj], y = yv[jj];
+          v[0] += beta * o.x; v[1] += beta * o.y; v[2] += beta * o.z; v[3] += beta * o.w;
+          if (mask_y != nullptr) {
+            v[0] *= act_bwd_from_y(y.x, mask_act); v[1] *= act_bwd_from_y(y.y, mask_act);
+            v[2] *= act_bwd_from_y(y.z, mask_act); v[3] *= act_bwd_from_y(y.w, mask_act);
+          }
+          *reinterpret_cast<float4*>(out + ob[j]) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (QD(j) * 4 + e >= g.Cout) continue;
+            float t = v[e];
+            if (beta != 0.f) t += beta * out[ob[j] + e];
+            if (mask_y != nullptr) t *= act_bwd_from_y(__ldg(mask_y + ob[j] + e), mask_act);
+            out[ob[j] + e] = t;
+          }
         }
       }
     }
   }
 }
 
+#undef QD
+
+// mode of the fused pointwise term for this op (see pw_conv_kernel)
+static int pw_extra_mode(const GConvK& k, int lpp, int qt) {
+  if (!k.d2s) return 1;
+  if (lpp > 1 && lpp == qt && k.cout_true == 4 * lpp && k.d2s_s * k.d2s_s == qt) return 2;
+  return 3;
+}
+
 template <int NQ, int QT, int R>
 static void pw_launch(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
-                      float* out, cudaStream_t st) {
-  constexpr int PPB = PW_THREADS / (NQ / QT) * R;
+                      float* out, const PwExtra* ex, cudaStream_t st) {
+  constexpr int LPP = NQ / QT;
+  constexpr int PPB = PW_THREADS / LPP * R;
   const unsigned grid = (k.M + PPB - 1) / PPB;
-  pw_conv_kernel<NQ, QT, R><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
+#define NLT_PW(M_, EX_) pw_conv_kernel<NQ, QT, R, M_><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out, EX_)
+  if (ex == nullptr) { NLT_PW(0, PwExtra{}); return; }
+  const int mode = pw_extra_mode(k, LPP, QT);
+  if (mode == 1) NLT_PW(1, *ex);
+  else if (mode == 2) { if constexpr (LPP > 1 && LPP == QT) NLT_PW(2, *ex); }
+  else NLT_PW(3, *ex);
+#undef NLT_PW
+}
+
+bool pw_extra_applicable(const GConvK& k, const PwExtra& ex, const float* out, const float* mask_y) {
+  return pw_conv_applicable(k) && ex.K >= 1 && ex.K <= PW_EX_KMAX && k.cout_true % 4 == 0 && k.cout_true <= 64 &&
+         aligned16(out) && (mask_y == nullptr || aligned16(mask_y));
 }
 
 int launch_pw_conv(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
-                   float* out, cudaStream_t st) {
+                   float* out, cudaStream_t st, const PwExtra* ex) {
   const int nq = (k.Cout + 3) / 4;
-  if (nq <= 1) pw_launch<1, 1, 4>(k, bias, act, beta, mask_y, mask_act, out, st);
-  else if (nq == 2) pw_launch<2, 2, 4>(k, bias, act, beta, mask_y, mask_act, out, st);
-  else if (nq <= 4) pw_launch<4, 4, 2>(k, bias, act, beta, mask_y, mask_act, out, st);
-  else if (nq <= 8) pw_launch<8, 4, 2>(k, bias, act, beta, mask_y, mask_act, out, st);
-  else pw_launch<16, 4, 2>(k, bias, act, beta, mask_y, mask_act, out, st);
+  if (nq <= 1) pw_launch<1, 1, 4>(k, bias, act, beta, mask_y, mask_act, out, ex, st);
+  else if (nq == 2) pw_launch<2, 2, 4>(k, bias, act, beta, mask_y, mask_act, out, ex, st);
+  else if (nq <= 4) pw_launch<4, 4, 2>(k, bias, act, beta, mask_y, mask_act, out, ex, st);
+  else if (nq <= 8) pw_launch<8, 4, 2>(k, bias, act, beta, mask_y, mask_act, out, ex, st);
+  else pw_launch<16, 4, 2>(k, bias, act, beta, mask_y, mask_act, out, ex, st);
   NLT_CUDA_LAUNCH_CHECK("pw_conv_kernel");
   return NLT_OK;
 }

@@ -9,6 +9,7 @@ device memory and streams.
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -59,7 +60,7 @@ def same_pad(n, k, s):
 
 class Act:
     """An activation tensor [N,H,W,C] plus the bookkeeping of its gradient."""
-    __slots__ = ('t', 'act', 'grad', 'n_cons', 'n_contrib', 'needs_grad')
+    __slots__ = ('t', 'act', 'grad', 'n_cons', 'n_contrib', 'needs_grad', 'pending')
 
     def __init__(self, t, act=None, needs_grad=False):
         self.t = t
@@ -68,6 +69,7 @@ class Act:
         self.n_cons = 0           # consumers that will contribute a gradient
         self.n_contrib = 0
         self.needs_grad = needs_grad
+        self.pending = None       # deferred pointwise contribution: (PwTerm, keep-alive tensors, write_fn)
 
 
 class Seg:
@@ -95,6 +97,8 @@ class Tape:
         for fn in reversed(self.ops):
             fn()
         self.ops = []
+        while _PARKED:                      # leaves whose parked contribution nobody took along
+            settle(_PARKED.pop())
         if USE_SIDE_STREAM and torch.cuda.is_available():
             torch.cuda.current_stream().wait_stream(side_stream())   # join the weight-gradient branch
 
@@ -145,9 +149,40 @@ def gconv_fwd(d, bias, act, beta, mask, mask_act, out):
                                        None, 0, nat.stream()))
 
 
-def contribute(target, write_fn):
+FUSE_POINTWISE_DGRAD = os.environ.get('NLT_FUSE_DGRAD', '1') != '0'
+_PARKED = []     # Acts holding a parked contribution (settled at the latest when the tape finishes)
+
+
+def contribute(target, write_fn, offer=None, can_fuse=None):
     """Adds one gradient contribution into target.grad.
-    write_fn(out, beta, mask_y, mask_act) launches the producing kernel."""
+    write_fn(out, beta, mask_y, mask_act, term) launches the producing kernel (term: a PwTerm to add in the
+    kernel's epilogue, or None).
+
+    offer = (PwTerm, keep-alive tensors): this contribution IS a small pointwise product (the input gradient
+    of the final 1x1 conv).  When it would be the first of several it is not launched but parked on the
+    target; the next contributor adds it in its own epilogue if its kernel can (can_fuse(term, out, mask) ->
+    bool, backed by nlt_gconv_fwd_fused_supported) -- the full-resolution gradient tensor is then written
+    once instead of written, re-read and re-written.  Otherwise the parked one is issued first, as usual."""
+    if target.pending is not None:
+        pterm, _keep, pwrite = target.pending
+        target.pending = None
+        target.grad = torch.empty_like(target.t)        # parked => nothing has been written yet
+        target.n_contrib += 1
+        last = target.n_contrib == target.n_cons
+        mask = target.t if (last and target.act is not None) else None
+        mask_act = nat.ACT_CODES[target.act] if mask is not None else 0
+        if can_fuse is not None and can_fuse(pterm, target.grad, mask):
+            write_fn(target.grad, 0.0, mask, mask_act, pterm)
+        else:
+            pwrite(target.grad, 0.0, None, 0, None)
+            write_fn(target.grad, 1.0, mask, mask_act, None)
+        return
+    if (FUSE_POINTWISE_DGRAD and offer is not None and target.grad is None
+            and target.n_cons - target.n_contrib >= 2):
+        target.pending = (offer[0], offer[1], write_fn)
+        target.n_contrib += 1
+        _PARKED.append(target)
+        return
     if target.grad is None:
         target.grad = torch.empty_like(target.t)
         beta = 0.0
@@ -156,7 +191,18 @@ def contribute(target, write_fn):
     target.n_contrib += 1
     last = target.n_contrib == target.n_cons
     mask = target.t if (last and target.act is not None) else None
-    write_fn(target.grad, beta, mask, nat.ACT_CODES[target.act] if mask is not None else 0)
+    write_fn(target.grad, beta, mask, nat.ACT_CODES[target.act] if mask is not None else 0, None)
+
+
+def settle(a):
+    """Issues a parked contribution of `a` on its own (no later contributor took it along)."""
+    if a.pending is not None:
+        _pterm, _keep, pwrite = a.pending
+        a.pending = None
+        a.grad = torch.empty_like(a.t)
+        last = a.n_contrib == a.n_cons
+        mask = a.t if (last and a.act is not None) else None
+        pwrite(a.grad, 0.0, mask, nat.ACT_CODES[a.act] if mask is not None else 0, None)
 
 
 class ConvLayer:
@@ -278,6 +324,7 @@ class ConvLayer:
 
     def _backward(self, segs, y, N, Hin, Win):
         lib = nat.lib()
+        settle(y)
         dz = y.grad
         if dz is None:
             return
@@ -304,15 +351,33 @@ class ConvLayer:
                 ws.numel() * 4, nat.stream())))
         self.grad_written = True
         # input gradients, one adjoint launch per differentiable segment
+        pointwise = self.kind == 'conv' and self.k == 1 and self.s == 1 and self.cout <= 4
         coff = 0
         for sg in segs:
             if sg.a.needs_grad:
                 dd = self._dgrad_desc(dz, N, Hin, Win, coff, sg.C)
 
-                def write(out, beta, mask, mask_act, dd=dd):
+                def write(out, beta, mask, mask_act, term, dd=dd):
                     nb = 4 * (dz.numel() + out.numel() * (1 + (beta != 0) + (mask is not None)))
-                    PROF.run('dgrad ' + self.name, nb, lambda: gconv_fwd(dd, None, 0, beta, mask, mask_act, out))
-                contribute(sg.a, write)
+                    if term is None:
+                        PROF.run('dgrad ' + self.name, nb, lambda: gconv_fwd(dd, None, 0, beta, mask, mask_act, out))
+                    else:
+                        PROF.run('dgrad ' + self.name, nb, lambda: nat.check(lib.nlt_gconv_fwd_fused(
+                            C.byref(dd), C.byref(term), None, 0, beta, nat.ptr(mask), mask_act, nat.ptr(out),
+                            nat.stream())))
+
+                def can_fuse(term, out, mask, dd=dd):
+                    return bool(lib.nlt_gconv_fwd_fused_supported(C.byref(dd), C.byref(term), nat.ptr(mask),
+                                                                  nat.ptr(out)))
+                offer = None
+                if pointwise:
+                    # d(input)[p, c] = sum_co dz[p, co] * W[coff + c, co]   (kernel layout (1,1,Ci,Co))
+                    term = nat.PwTerm()
+                    term.x, term.K = nat.ptr(dz), self.cout
+                    term.w = self.kernel.data_ptr() + 4 * coff * self.cout
+                    term.w_k_stride, term.w_n_stride = 1, self.cout
+                    offer = (term, (dz, self.kernel))
+                contribute(sg.a, write, offer, can_fuse)
             coff += sg.C
         y.grad = None   # dz is dead: release it
 
@@ -333,10 +398,11 @@ def kmean(obs_y, K, tape=None, weights=None):
         obs_y.n_cons += 1
 
         def bwd():
+            settle(agg)
             if agg.grad is None:
                 return
 
-            def write(o, beta, mask, mask_act):
+            def write(o, beta, mask, mask_act, term=None):
                 nat.check(lib.nlt_kmean_bwd(nat.ptr(agg.grad), nat.ptr(weights), K, B, per, beta, nat.ptr(mask),
                                             mask_act, nat.ptr(o), nat.stream()))
             contribute(obs_y, write)

@@ -33,6 +33,12 @@ class GConvDesc(C.Structure):
     ]
 
 
+class PwTerm(C.Structure):
+    """nlt_pw_term (include/nlt_b200.h): pointwise term fused into a pointwise op's epilogue."""
+    _fields_ = [('x', C.c_void_p), ('K', C.c_int32), ('w', C.c_void_p),
+                ('w_k_stride', C.c_int64), ('w_n_stride', C.c_int64)]
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -47,6 +53,9 @@ _SIGS = {
     'nlt_tc_launch_count': (C.c_uint64, []),
     'nlt_gconv_fwd': (C.c_int, [C.POINTER(GConvDesc), C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int,
                                 C.c_void_p, C.c_void_p]),
+    'nlt_gconv_fwd_fused_supported': (C.c_int, [C.POINTER(GConvDesc), C.POINTER(PwTerm), C.c_void_p, C.c_void_p]),
+    'nlt_gconv_fwd_fused': (C.c_int, [C.POINTER(GConvDesc), C.POINTER(PwTerm), C.c_void_p, C.c_int, C.c_float,
+                                      C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     'nlt_gconv_fwd_workspace_bytes': (C.c_int64, [C.POINTER(GConvDesc)]),
     'nlt_gconv_fwd_ws': (C.c_int, [C.POINTER(GConvDesc), C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -200,6 +200,66 @@ def test_wgrad_row_run_vs_flat_pixel_kernel(kind, k, s, H, W, segc, cout):
     assert rel(res[1][1], res[0][1]) <= 1e-5
 
 
+@pytest.mark.parametrize('H,W,c_skip,c_other,down_cout,dk', [
+    (16, 16, 16, 4, 16, 2), (8, 24, 16, 8, 32, 2), (6, 10, 12, 4, 8, 2),   # depth-to-space dgrad: shuffle / per-quad modes
+    (8, 8, 16, 4, 16, 1), (4, 12, 8, 4, 24, 1)])                            # 1x1 consumer: same-pixel mode
+def test_final_conv_input_gradient_rides_on_down_conv_dgrad(H, W, c_skip, c_other, down_cout, dk):
+    """Skip tensor consumed by a 2x2/s2 down-conv and, later, by the final 1x1 conv -> 3 (the level-0 skip
+    of the network): with fusion on, the 1x1 conv's input gradient is added in the epilogue of the
+    down-conv's input-gradient launch (nlt_gconv_fwd_fused).  Same result as the unfused engine and as
+    autograd (fp64), one launch less, parameter gradients untouched."""
+    engine, nat = _mods()
+    dev = torch.device('cuda')
+    torch.manual_seed(21)
+    N = 2
+    x_skip = torch.randn(N, H, W, c_skip, device=dev)
+    x_other = torch.randn(N, H, W, c_other, device=dev)
+    gen = lambda: torch.Generator().manual_seed(4)
+    res = {}
+    for fuse in (True, False):
+        engine.FUSE_POINTWISE_DGRAD = fuse
+        try:
+            down = engine.ConvLayer('conv', dk, dk, down_cout, 'leakyrelu')
+            down.build(c_skip, dev, gen())
+            final = engine.ConvLayer('conv', 1, 1, 3, None)
+            final.build(c_other + c_skip, dev, gen())
+            a_skip = engine.Act(x_skip, act='leakyrelu', needs_grad=True)
+            a_other = engine.Act(x_other, act='leakyrelu', needs_grad=True)
+            tape = engine.Tape()
+            y_down = down.forward([engine.Seg(a_skip)], tape)
+            y_fin = final.forward([engine.Seg(a_other), engine.Seg(a_skip)], tape)
+            torch.manual_seed(5)
+            y_down.grad = torch.randn_like(y_down.t)
+            y_fin.grad = torch.randn_like(y_fin.t)
+            g_down, g_fin = y_down.grad.clone(), y_fin.grad.clone()
+            n0 = nat.launch_count()
+            tape.backward()
+            res[fuse] = dict(gs=a_skip.grad.clone(), go=a_other.grad.clone(), gk=[down.gkernel.clone(), final.gkernel.clone()],
+                             launches=nat.launch_count() - n0)
+        finally:
+            engine.FUSE_POINTWISE_DGRAD = True
+    # fp64 autograd of the same graph
+    xs64 = x_skip.double().cpu().requires_grad_(True)
+    xo64 = x_other.double().cpu().requires_grad_(True)
+    # y.grad handed to the tape is the gradient of the PRE-activation output (see test_gconv_forward_backward)
+    pre = O.conv2d_same(xs64, down.kernel.double().cpu(), down.bias.double().cpu(), dk)
+    yf = O.conv2d_same(torch.cat([xo64, xs64], -1), final.kernel.double().cpu(), final.bias.double().cpu(), 1)
+    loss = (pre * g_down.double().cpu()).sum() + (yf * g_fin.double().cpu()).sum()
+    loss.backward()
+    want_s = xs64.grad * torch.where(xs64 > 0, 1.0, 0.3)
+    want_o = xo64.grad * torch.where(xo64 > 0, 1.0, 0.3)
+    for fuse in (True, False):
+        _close(res[fuse]['gs'], want_s, rtol=1e-4, atol=1e-4)
+        _close(res[fuse]['go'], want_o, rtol=1e-4, atol=1e-4)
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+    assert rel(res[True]['gs'], res[False]['gs']) <= 1e-6
+    assert rel(res[True]['go'], res[False]['go']) <= 1e-6
+    for a, b in zip(res[True]['gk'], res[False]['gk']):
+        assert torch.equal(a, b)
+    if c_skip % 4 == 0:
+        assert res[True]['launches'] == res[False]['launches'] - 1, (res[True]['launches'], res[False]['launches'])
+
+
 def test_tensor_core_path_is_taken_and_matches_fp32_path():
     """Eligible shapes must run on the tcgen05 kernel (launch counter moves) and agree with the
     fp32-FMA kernel of the same library to 3xTF32 accuracy (<= 4e-6 relative to the output scale)."""
