@@ -624,6 +624,14 @@ static bool tc_enabled() {
   return g_opt_tc == 1;
 }
 
+// tensor-core weight gradient for this phase?  Measured (profiles/r1_j): the row-run warp-stream kernel
+// beats the tcgen05 one when it applies at all (<= 16 gradient channels, K-depth <= 160: the level-1
+// 32 -> 16 down-conv, 0.70 vs 0.84 ms), the tcgen05 kernel wins everywhere else.
+static bool tc_wgrad_enabled();
+static bool use_tc_wgrad(const GConvK& k) {
+  return tc_wgrad_enabled() && tc_wgrad_applicable(k) && !wgrad_small_applicable(k);
+}
+
 static bool tc_wgrad_enabled() {
   if (g_opt_tc_wgrad < 0) { const char* e = getenv("NLT_DISABLE_TC_WGRAD"); g_opt_tc_wgrad = (e && e[0] == '1') ? 0 : 1; }
   return tc_enabled() && g_opt_tc_wgrad == 1;
@@ -721,7 +729,7 @@ int64_t nlt_gconv_wgrad_workspace_bytes(const nlt_gconv_desc* d) {
   size_t mx = 0;
   for (int i = 0; i < np; ++i) {
     if (ph[i].M == 0) continue;
-    size_t need = (tc_wgrad_enabled() && tc_wgrad_applicable(ph[i])) ? tc_wgrad_ws_floats(ph[i])
+    size_t need = use_tc_wgrad(ph[i]) ? tc_wgrad_ws_floats(ph[i])
                   : wgrad_tpp_applicable(ph[i]) ? wgrad_tpp_ws_floats(ph[i])
                   : wgrad_small_applicable(ph[i]) ? wgrad_small_ws_floats(ph[i]) : plan_wgrad(ph[i]).ws_floats;
     if (need > mx) mx = need;
@@ -746,7 +754,7 @@ int nlt_gconv_wgrad(const nlt_gconv_desc* d, const float* G, float* dW, float* d
     float* ws = (float*)workspace;
     WgradK w;
     size_t KD_pad = 0;
-    if (tc_wgrad_enabled() && tc_wgrad_applicable(k)) {
+    if (use_tc_wgrad(k)) {
       NLT_CHECK_ARG((int64_t)(tc_wgrad_ws_floats(k) * sizeof(float)) <= workspace_bytes, "workspace too small");
       rc = launch_tc_wgrad(k, G, ws, &w, &KD_pad, st);
       if (rc != NLT_OK) return rc;

@@ -920,6 +920,9 @@ wgrad_tpp_kernel(const TppK t, const float* __restrict__ G, float* __restrict__ 
 #pragma unroll
   for (int n = 0; n < N; ++n) gsum[n] = 0.f;
   const bool g_vec = (N % 4 == 0) && (g.Cout == N) && aligned16(G);
+  // K-split: blockIdx.y owns loads [l0, l0 + NL) of the pixel (its own rows of the result); every y
+  // re-reads the (narrow) gradient, y == 0 also produces the bias sums
+  const int l0 = blockIdx.y * NL;
 
   for (uint32_t m = blockIdx.x * TPP_THREADS + tid; m < g.M; m += gridDim.x * TPP_THREADS) {
     int n, ty, tx;
@@ -941,7 +944,7 @@ wgrad_tpp_kernel(const TppK t, const float* __restrict__ G, float* __restrict__ 
     const int by = ty * g.ay.it, bx = tx * g.ax.it;
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
-      const TppLoad L = t.ld[l];
+      const TppLoad L = t.ld[l0 + l];
       const int iy = by + L.dy, ix = bx + L.dx;
 #pragma unroll
       for (int e = 0; e < VEC; ++e) a[l * VEC + e] = 0.f;
@@ -985,10 +988,10 @@ wgrad_tpp_kernel(const TppK t, const float* __restrict__ G, float* __restrict__ 
     if (lane == 0) red[warp][R * N + e] = v;
   }
   __syncthreads();
-  float* dst = ws + (size_t)blockIdx.x * t.rows * t.ldw;
+  float* dst = ws + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * t.rows * t.ldw;
   for (int i = tid; i < t.rows * t.ldw; i += TPP_THREADS) dst[i] = 0.f;
   __syncthreads();
-  for (int i = tid; i < R * N + N; i += TPP_THREADS) {
+  for (int i = tid; i < R * N + (blockIdx.y == 0 ? N : 0); i += TPP_THREADS) {
     float v = 0.f;
 #pragma unroll
     for (int wi = 0; wi < NW; ++wi) v += red[wi][i];
@@ -996,7 +999,7 @@ wgrad_tpp_kernel(const TppK t, const float* __restrict__ G, float* __restrict__ 
     if (i < R * N) {
       const int r = i / N;
       col = i - r * N;
-      row = t.ld[r / VEC].row + (r % VEC);
+      row = t.ld[l0 + r / VEC].row + (r % VEC);
     } else {
       row = t.bias_row; col = i - R * N;
     }
@@ -1007,6 +1010,7 @@ wgrad_tpp_kernel(const TppK t, const float* __restrict__ G, float* __restrict__ 
 struct TppPlan {
   bool ok;
   int nl, vec, n;
+  int ksplit;      // blockIdx.y extent: the nl loads are split into ksplit groups of nl / ksplit
   int GS, KG, nsplit;
   TppK k;
 };
@@ -1061,6 +1065,11 @@ static TppPlan tpp_plan(const GConvK& k) {
   if (want > max_split) want = max_split;
   if (want < 1) want = 1;
   pl.nsplit = (int)want;
+  // the 9-load tile (final conv: 36 channels -> 3) needs ~190 registers = 8 warps per SM; three blocks of 3
+  // loads each run at 4x the occupancy and re-read only the 3-channel gradient (measured in profiles/r1_j)
+  static int ks = -1;
+  if (ks < 0) { const char* e = getenv("NLT_TPP_KSPLIT"); ks = e ? atoi(e) : 1; }
+  pl.ksplit = (ks == 1 && pl.vec == 4 && pl.n == 3 && nl == 9) ? 3 : 1;
   pl.ok = true;
   return pl;
 }
@@ -1069,15 +1078,15 @@ bool wgrad_tpp_applicable(const GConvK& k) { return tpp_plan(k).ok; }
 
 size_t wgrad_tpp_ws_floats(const GConvK& k) {
   TppPlan pl = tpp_plan(k);
-  return pl.ok ? (size_t)pl.nsplit * pl.k.rows * pl.k.ldw : 0;
+  return pl.ok ? (size_t)pl.nsplit * pl.ksplit * pl.k.rows * pl.k.ldw : 0;
 }
 
 int launch_wgrad_tpp(const GConvK& k, const float* G, float* ws, WgradK* w, size_t* KD_pad, cudaStream_t st) {
   TppPlan pl = tpp_plan(k);
   if (!pl.ok) return set_err(NLT_ERR_INVALID, "wgrad_tpp not applicable");
-  w->g = k; w->GS = pl.GS; w->KG = pl.KG; w->ld = pl.k.ldw; w->nsplit = pl.nsplit; w->pix_per_split = 0;
+  w->g = k; w->GS = pl.GS; w->KG = pl.KG; w->ld = pl.k.ldw; w->nsplit = pl.nsplit * pl.ksplit; w->pix_per_split = 0;
   *KD_pad = (size_t)pl.k.rows;
-  const unsigned grid = pl.nsplit;
+  const dim3 grid(pl.nsplit, pl.ksplit);
 #define NLT_TPP(NL_, V_, N_) wgrad_tpp_kernel<NL_, V_, N_><<<grid, TPP_THREADS, 0, st>>>(pl.k, G, ws)
   if (pl.vec == 1) {
     switch (pl.nl) {
@@ -1086,7 +1095,7 @@ int launch_wgrad_tpp(const GConvK& k, const float* G, float* ws, WgradK* w, size
       case 7: NLT_TPP(7, 1, 16); break; default: NLT_TPP(8, 1, 16); break;
     }
   } else if (pl.n == 3) {
-    switch (pl.nl) {
+    switch (pl.nl / pl.ksplit) {
       case 1: NLT_TPP(1, 4, 3); break; case 2: NLT_TPP(2, 4, 3); break; case 3: NLT_TPP(3, 4, 3); break;
       case 4: NLT_TPP(4, 4, 3); break; default: NLT_TPP(9, 4, 3); break;
     }
