@@ -86,6 +86,7 @@ struct GConvK {
   // the input lattice with N' = k*k*cout_true GEMM columns (n' = tap*cout_true + n),
   // each 4-channel group stored at output pixel (t*s + dy, t*s + dx).  Cout == N'.
   int d2s, d2s_s, cout_true;
+  FastDiv div_ct, div_s;   // by cout_true / by d2s_s (tap decode without integer division)
 };
 
 __device__ __forceinline__ void decode_pixel(const GConvK& g, uint32_t m, int& n, int& ty, int& tx) {

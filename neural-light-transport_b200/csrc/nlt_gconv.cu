@@ -89,6 +89,8 @@ int build_phases(const nlt_gconv_desc* d, GConvK* out, int* nphase, bool allow_d
     k.M = (uint32_t)((long long)k.N * k.ay.nt * k.ax.nt);
     k.div_x = make_fastdiv((uint32_t)k.ax.nt);
     k.div_yx = make_fastdiv((uint32_t)(k.ay.nt * k.ax.nt));
+    k.div_ct = make_fastdiv((uint32_t)(k.cout_true > 0 ? k.cout_true : 1));
+    k.div_s = make_fastdiv((uint32_t)(k.d2s ? k.d2s_s : 1));
   }
   *nphase = np;
   return NLT_OK;

@@ -79,7 +79,7 @@ pw_conv_kernel(const GConvK g, const float* __restrict__ bias, const int act, co
   for (int idx = tid; idx < K * NQ; idx += PW_THREADS) {
     const int k = idx / NQ, q = idx - k * NQ;
     int t = tap, nn0 = q * 4;
-    if (g.d2s) { t = (q * 4) / g.cout_true; nn0 = q * 4 - t * g.cout_true; }   // cout_true % 4 == 0: a quad stays in one tap
+    if (g.d2s) { t = (int)fdiv((uint32_t)(q * 4), g.div_ct); nn0 = q * 4 - t * g.cout_true; }   // cout_true % 4 == 0: a quad stays in one tap
     float v[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e)
@@ -107,14 +107,22 @@ pw_conv_kernel(const GConvK g, const float* __restrict__ bias, const int act, co
     ok[r] = p[r] < g.M;
   }
 #pragma unroll
-  for (int j = 0; j < QT; ++j) {
-    int cb = QD(j) * 4;
-    if (g.d2s) cb -= (cb / g.cout_true) * g.cout_true;
+  for (int r = 0; r < R; ++r)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float b = (bias != nullptr && QD(j) * 4 + e < g.Cout) ? __ldg(bias + cb + e) : 0.f;
+    for (int j = 0; j < QT; ++j)
 #pragma unroll
-      for (int r = 0; r < R; ++r) acc[r][j][e] = b;
+      for (int e = 0; e < 4; ++e) acc[r][j][e] = 0.f;
+  if (bias != nullptr) {      // (input-gradient launches carry no bias: keep their prologue free of the loads)
+#pragma unroll
+    for (int j = 0; j < QT; ++j) {
+      int cb = QD(j) * 4;
+      if (g.d2s) cb -= (int)fdiv((uint32_t)cb, g.div_ct) * g.cout_true;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float b = QD(j) * 4 + e < g.Cout ? __ldg(bias + cb + e) : 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r][j][e] = b;
+      }
     }
   }
 
@@ -134,8 +142,8 @@ pw_conv_kernel(const GConvK g, const float* __restrict__ bias, const int act, co
       if (ex_mode == 2) {
         int n, ty, tx;
         decode_pixel(g, p[r], n, ty, tx);
-        const int dy = qa / g.d2s_s, dx = qa - dy * g.d2s_s;     // tap index == lane index in the group
-        pix = ((size_t)n * g.Hout + ty * g.d2s_s + dy) * g.Wout + tx * g.d2s_s + dx;
+        const int dy = (int)fdiv((uint32_t)qa, g.div_s), dx = qa - dy * g.d2s_s;     // tap index == lane index in the group
+        pix = ((uint32_t)n * g.Hout + ty * g.d2s_s + dy) * g.Wout + tx * g.d2s_s + dx;
       }
 #pragma unroll
       for (int k2 = 0; k2 < PW_EX_KMAX; ++k2)
@@ -219,11 +227,12 @@ pw_conv_kernel(const GConvK g, const float* __restrict__ bias, const int act, co
     for (int j = 0; j < QT; ++j) {
       const int col = QD(j) * 4;
       if (g.d2s) {
-        const int t = col / g.cout_true, cb = col - t * g.cout_true;
-        const int dy = t / g.d2s_s, dx = t - dy * g.d2s_s;
-        const size_t pix = ((size_t)n * g.Hout + ty * g.d2s_s + dy) * g.Wout + tx * g.d2s_s + dx;
-        ob[j] = pix * g.cout_true + cb;
-        if (EX) { opx[j] = (uint32_t)pix; ocq[j] = cb >> 2; }
+        const int t = (int)fdiv((uint32_t)col, g.div_ct), cb = col - t * g.cout_true;
+        const int dy = (int)fdiv((uint32_t)t, g.div_s), dx = t - dy * g.d2s_s;
+        // 32-bit pixel index (build_phases checks N*H*W < 2^31), one widening multiply for the offset
+        const uint32_t pix = ((uint32_t)n * g.Hout + ty * g.d2s_s + dy) * g.Wout + tx * g.d2s_s + dx;
+        ob[j] = (size_t)pix * (uint32_t)g.cout_true + cb;
+        if (EX) { opx[j] = pix; ocq[j] = cb >> 2; }
       } else {
         ob[j] = (size_t)p[r] * g.Cout + col;
         if (EX) { opx[j] = p[r]; ocq[j] = col >> 2; }
