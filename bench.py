@@ -280,7 +280,7 @@ def run_b200(args):
         step_bytes = ALG_BYTES_PER_TEXEL.get(cq, 2210.0) * args.batch * args.uv * args.uv
         roof = {
             'bound': 'hbm', 'achieved': ach, 'peak': peak_gbs, 'unit': 'GB/s', 'frac': ach / peak_gbs,
-            'traffic': None, 'peak_source': how + ' copy bandwidth (MEASURED_PEAKS.json hbm_gbs)'
+            'traffic': ncu_traffic(top_label), 'peak_source': how + ' copy bandwidth (MEASURED_PEAKS.json hbm_gbs)'
             if how == 'measured' else 'fallback 6.65 TB/s (B200_PROFILING.md)',
             'kernel': top_label, 'kernel_launches_per_step': top['launches'] / 2,
             'kernel_ms_per_launch': top['ms'] / top['launches'],
@@ -329,6 +329,17 @@ def run_b200(args):
         emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def ncu_traffic(label):
+    """DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+    (profiles/ncu_traffic.json); None when that kernel has not been captured."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+            ent = json.load(f).get(label)
+        return float(ent['dram_bytes_per_launch']) if ent else None
+    except (OSError, ValueError, KeyError):
+        return None
 
 
 _JSON_OUT = None
