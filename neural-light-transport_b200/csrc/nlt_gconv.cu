@@ -572,6 +572,42 @@ gconv_wgrad_reduce_kernel(const WgradK w, const float* __restrict__ ws, size_t K
   }
 }
 
+// Few partials (the tcgen05 wgrad of the deep levels: 2-16 splits of a [K_d x N] matrix of up to 4096 x 256):
+// one thread per output, splits summed serially in fixed order.  The 32-lane form above keeps 2 of its 32 split
+// lanes busy there and took 45-160 us per launch (ncu launch list, profiles/r1_l) for 2 MB of partials.
+__global__ void __launch_bounds__(256)
+gconv_wgrad_reduce_flat_kernel(const WgradK w, const float* __restrict__ ws, size_t KD_pad,
+                               float* __restrict__ dW, float* __restrict__ db, int acc_w, int acc_b) {
+  const size_t total = (size_t)w.KG * 4 * w.g.Cout;
+  const size_t stride = KD_pad * w.ld;
+  const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int n = (int)(idx % w.g.Cout);
+  const int k = (int)(idx / w.g.Cout);
+  const int kg = k >> 2, e = k & 3;
+  int uy, ux, s, c;
+  decode_kgroup(w, kg, uy, ux, s, c);
+  float* dst = nullptr;
+  int accumulate = acc_w, ntaps_sum = 1;
+  if (s == -1) {
+    if (e == 0 && db != nullptr && (!w.g.d2s || n < w.g.cout_true)) {
+      dst = db + n; accumulate = acc_b;
+      if (w.g.d2s) ntaps_sum = w.g.d2s_s * w.g.d2s_s;
+    }
+  } else if (s >= 0 && c + e < w.g.seg[s].C) {
+    int tap = (w.g.ay.d0 + w.g.ay.ds * uy) * w.g.kw + (w.g.ax.d0 + w.g.ax.ds * ux), nn = n;
+    if (w.g.d2s) { tap = n / w.g.cout_true; nn = n - tap * w.g.cout_true; }
+    dst = dW + (long long)tap * w.g.wt + (long long)(w.g.seg[s].coff + c + e) * w.g.wc + (long long)nn * w.g.wn;
+  }
+  if (dst == nullptr) return;
+  float sum = 0.f;
+  for (int tp = 0; tp < ntaps_sum; ++tp) {
+    const float* src = ws + (size_t)k * w.ld + n + tp * w.g.cout_true;
+    for (int sp = 0; sp < w.nsplit; ++sp) sum += __ldg(src + (size_t)sp * stride);
+  }
+  *dst = accumulate ? (*dst + sum) : sum;
+}
+
 struct WgradPlan {
   int tkg, tn, nthr;
   int kd_tiles, n_tiles, nsplit;
@@ -787,10 +823,15 @@ int nlt_gconv_wgrad(const nlt_gconv_desc* d, const float* G, float* dW, float* d
     // every phase sees a disjoint subset of lattice pixels, so the bias gradient
     // accumulates across phases; taps are disjoint across phases.
     const size_t total = (size_t)w.KG * 4 * k.Cout;
-    int blocks = (int)((total + 7) / 8);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    gconv_wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(w, ws, KD_pad, dW, db, accumulate,
-                                                      bias_done ? 1 : accumulate);
+    if (w.nsplit <= 16) {
+      gconv_wgrad_reduce_flat_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, ws, KD_pad, dW, db, accumulate,
+                                                                                     bias_done ? 1 : accumulate);
+    } else {
+      int blocks = (int)((total + 7) / 8);
+      if (blocks > 148 * 16) blocks = 148 * 16;
+      gconv_wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(w, ws, KD_pad, dW, db, accumulate,
+                                                        bias_done ? 1 : accumulate);
+    }
     NLT_CUDA_LAUNCH_CHECK("gconv_wgrad_reduce_kernel");
     bias_done = true;
   }
