@@ -336,12 +336,6 @@ bool pw_extra_applicable(const GConvK& k, const PwExtra& ex, const float* out, c
          aligned16(out) && (mask_y == nullptr || aligned16(mask_y));
 }
 
-static bool pw_r1() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("NLT_PW_EX_R1"); v = e ? atoi(e) : 1; }
-  return v == 1;
-}
-
 int launch_pw_conv(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
                    float* out, cudaStream_t st, const PwExtra* ex) {
   const int nq = (k.Cout + 3) / 4;
@@ -351,7 +345,7 @@ int launch_pw_conv(const GConvK& k, const float* bias, int act, float beta, cons
   else if (nq <= 8) pw_launch<8, 4, 2>(k, bias, act, beta, mask_y, mask_act, out, ex, st);
   // fused term: one pixel per thread -- at 64 registers the two-pixel form spills ~130 bytes per thread and
   // the local-memory traffic exceeded the useful traffic (ncu: profiles/r1_k_ncu_full_pw_kernels.csv)
-  else if (ex != nullptr && pw_r1()) pw_launch<16, 4, 1>(k, bias, act, beta, mask_y, mask_act, out, ex, st);
+  else if (ex != nullptr) pw_launch<16, 4, 1>(k, bias, act, beta, mask_y, mask_act, out, ex, st);
   else pw_launch<16, 4, 2>(k, bias, act, beta, mask_y, mask_act, out, ex, st);
   NLT_CUDA_LAUNCH_CHECK("pw_conv_kernel");
   return NLT_OK;
@@ -1085,9 +1079,7 @@ static TppPlan tpp_plan(const GConvK& k) {
   pl.nsplit = (int)want;
   // the 9-load tile (final conv: 36 channels -> 3) needs ~190 registers = 8 warps per SM; three blocks of 3
   // loads each run at 4x the occupancy and re-read only the 3-channel gradient (measured in profiles/r1_j)
-  static int ks = -1;
-  if (ks < 0) { const char* e = getenv("NLT_TPP_KSPLIT"); ks = e ? atoi(e) : 1; }
-  pl.ksplit = (ks == 1 && pl.vec == 4 && pl.n == 3 && nl == 9) ? 3 : 1;
+  pl.ksplit = (pl.vec == 4 && pl.n == 3 && nl == 9) ? 3 : 1;
   pl.ok = true;
   return pl;
 }
