@@ -572,7 +572,7 @@ gconv_wgrad_reduce_kernel(const WgradK w, const float* __restrict__ ws, size_t K
   }
 }
 
-// Few partials (the tcgen05 wgrad of the deep levels: 2-16 splits of a [K_d x N] matrix of up to 4096 x 256):
+// Few partials (the tcgen05 wgrad of the deep levels: 2-32 splits of a [K_d x N] matrix of up to 4096 x 256):
 // one thread per output, splits summed serially in fixed order.  The 32-lane form above keeps 2 of its 32 split
 // lanes busy there and took 45-160 us per launch (ncu launch list, profiles/r1_l) for 2 MB of partials.
 __global__ void __launch_bounds__(256)
@@ -603,6 +603,7 @@ gconv_wgrad_reduce_flat_kernel(const WgradK w, const float* __restrict__ ws, siz
   float sum = 0.f;
   for (int tp = 0; tp < ntaps_sum; ++tp) {
     const float* src = ws + (size_t)k * w.ld + n + tp * w.g.cout_true;
+#pragma unroll 4
     for (int sp = 0; sp < w.nsplit; ++sp) sum += __ldg(src + (size_t)sp * stride);
   }
   *dst = accumulate ? (*dst + sum) : sum;
@@ -823,7 +824,7 @@ int nlt_gconv_wgrad(const nlt_gconv_desc* d, const float* G, float* dW, float* d
     // every phase sees a disjoint subset of lattice pixels, so the bias gradient
     // accumulates across phases; taps are disjoint across phases.
     const size_t total = (size_t)w.KG * 4 * k.Cout;
-    if (w.nsplit <= 16) {
+    if (w.nsplit <= 32) {
       gconv_wgrad_reduce_flat_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, ws, KD_pad, dW, db, accumulate,
                                                                                      bias_done ? 1 : accumulate);
     } else {
