@@ -142,3 +142,88 @@ def test_synth_batch_properties():
     frac_bg = float(((b[4] == 0).all(dim=3)).float().mean())
     assert 0.15 < frac_bg < 0.6
     assert torch.equal(b[4], b[4].half().float())
+
+
+# ---- gradient bookkeeping of the tape (engine.contribute): first writer beta = 0, later ones beta = 1, ----
+# ---- mask on the last; a small pointwise first contribution is parked and rides on the next launch     ----
+class _Rec:
+    """write_fn stand-in that records how it was called instead of launching a kernel."""
+
+    def __init__(self, log, name):
+        self.log, self.name = log, name
+
+    def __call__(self, out, beta, mask, mask_act, term):
+        self.log.append((self.name, beta, mask is not None, mask_act, term))
+
+
+def _act(n_cons, act='leakyrelu'):
+    import engine
+    a = engine.Act(torch.zeros(1, 2, 2, 4), act=act, needs_grad=True)
+    a.n_cons = n_cons
+    return a
+
+
+def test_contribute_plain_order_beta_and_mask():
+    import engine
+    log = []
+    a = _act(3)
+    for name in 'xyz':
+        engine.contribute(a, _Rec(log, name))
+    leaky = engine.nat.ACT_CODES['leakyrelu']
+    assert log == [('x', 0.0, False, 0, None), ('y', 1.0, False, 0, None), ('z', 1.0, True, leaky, None)]
+    assert a.grad is not None and a.n_contrib == 3
+
+
+def test_contribute_parks_pointwise_first_contribution_and_fuses_it():
+    import engine
+    assert engine.FUSE_POINTWISE_DGRAD
+    log = []
+    a = _act(2)
+    term = object()
+    engine.contribute(a, _Rec(log, 'final1x1'), offer=(term, ()))
+    assert log == [] and a.grad is None and a.pending is not None and a.n_contrib == 1
+    engine.contribute(a, _Rec(log, 'down'), can_fuse=lambda t, out, mask: t is term and mask is not None)
+    leaky = engine.nat.ACT_CODES['leakyrelu']
+    # ONE launch: beta 0 (nothing was written before), mask (it is the last contribution), term attached
+    assert log == [('down', 0.0, True, leaky, term)]
+    assert a.pending is None and a.n_contrib == 2
+    engine._PARKED.clear()
+
+
+def test_contribute_parked_contribution_is_issued_alone_when_next_cannot_fuse():
+    import engine
+    log = []
+    a = _act(3, act=None)
+    engine.contribute(a, _Rec(log, 'final1x1'), offer=(object(), ()))
+    engine.contribute(a, _Rec(log, 'tiled'), can_fuse=lambda t, out, mask: False)
+    engine.contribute(a, _Rec(log, 'last'))
+    assert log == [('final1x1', 0.0, False, 0, None), ('tiled', 1.0, False, 0, None), ('last', 1.0, False, 0, None)]
+    engine._PARKED.clear()
+
+
+def test_contribute_does_not_park_a_sole_or_late_contribution():
+    import engine
+    log = []
+    a = _act(1)
+    engine.contribute(a, _Rec(log, 'only'), offer=(object(), ()))
+    assert [e[0] for e in log] == ['only'] and a.pending is None      # sole consumer: launched, masked
+    b = _act(2)
+    engine.contribute(b, _Rec(log, 'first'))
+    engine.contribute(b, _Rec(log, 'second'), offer=(object(), ()))    # not first: plain accumulate
+    assert log[-1][:3] == ('second', 1.0, True) and b.pending is None
+
+
+def test_parked_contribution_without_follower_is_settled_by_the_tape():
+    import engine
+    log = []
+    a = _act(2)
+    tape = engine.Tape()
+    tape.record(lambda: engine.contribute(a, _Rec(log, 'final1x1'), offer=(object(), ())))
+    old = engine.USE_SIDE_STREAM
+    engine.USE_SIDE_STREAM = False
+    try:
+        tape.backward()
+    finally:
+        engine.USE_SIDE_STREAM = old
+    # the second consumer never contributed (its own gradient was None): the parked one must not be lost
+    assert log == [('final1x1', 0.0, False, 0, None)] and a.grad is not None and a.pending is None
