@@ -140,6 +140,12 @@ bool pw_conv_applicable(const GConvK& k);
 bool pw_extra_applicable(const GConvK& k, const PwExtra& ex, const float* out, const float* mask_y);
 int launch_pw_conv(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
                    float* out, cudaStream_t st, const PwExtra* ex = nullptr);
+// wide stencil kernel (pixel x 16 outputs per thread); option "dconv_wide" / NLT_DCONV_WIDE
+#define NLT_DCONV_WIDE_DEFAULT 1
+extern int g_opt_dconv_wide;
+bool dconv_wide_applicable(const GConvK& k, const float* out, const float* mask_y);
+int launch_dconv_wide(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
+                      float* out, cudaStream_t st);
 bool dconv_small_applicable(const GConvK& k);
 int launch_dconv_small(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
                        float* out, cudaStream_t st);

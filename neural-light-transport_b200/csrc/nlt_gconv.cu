@@ -681,6 +681,7 @@ int nlt_set_option(const char* name, int value) {
   if (strcmp(name, "tc") == 0) { g_opt_tc = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "tc_wgrad") == 0) { g_opt_tc_wgrad = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "wgrad_rows") == 0) { nlt::g_opt_wgrad_rows = value ? 1 : 0; return NLT_OK; }
+  if (strcmp(name, "dconv_wide") == 0) { nlt::g_opt_dconv_wide = value ? 1 : 0; return NLT_OK; }
   return set_err(NLT_ERR_INVALID, "unknown option '%s'", name);
 }
 
@@ -710,6 +711,7 @@ int nlt_gconv_fwd_ws(const nlt_gconv_desc* d, const float* bias, int act, float 
     if (k.M == 0) continue;
     if (pw_conv_applicable(k)) rc = launch_pw_conv(k, bias, act, beta, mask_y, mask_act, out, st);
     else if (dconv_small_applicable(k)) rc = launch_dconv_small(k, bias, act, beta, mask_y, mask_act, out, st);
+    else if (dconv_wide_applicable(k, out, mask_y)) rc = launch_dconv_wide(k, bias, act, beta, mask_y, mask_act, out, st);
     else if (k.Cout > 32) rc = launch_fwd<128, 64, 8, 8>(k, bias, act, beta, mask_y, mask_act, out, st);
     else if (k.Cout > 16) rc = launch_fwd<128, 32, 8, 4>(k, bias, act, beta, mask_y, mask_act, out, st);
     else if (k.Cout > 8) rc = launch_fwd<256, 16, 8, 4>(k, bias, act, beta, mask_y, mask_act, out, st);

@@ -530,6 +530,178 @@ dconv_small_kernel(const GConvK g, const float* __restrict__ bias, const int act
   }
 }
 
+// -----------------------------------------------------------------------------
+// Wide form of the small direct convolution: one thread = one lattice pixel x ALL 16 output channels (4
+// quads), R pixels per thread.  For the 16 -> 16 channel stencils (K = taps * C = 64) the tiled implicit-GEMM
+// kernel spends ~64 % of its instructions on address generation (ncu source view, profiles/r1_i); here every
+// input float4 is loaded once per 64 FMAs and every weight LDS.128 feeds 4*R FMAs.  Vector sources only, no
+// depth-to-space (those go to the pointwise kernel).
+// -----------------------------------------------------------------------------
+constexpr int DW_QT = 4;
+
+template <int R>
+__global__ void __launch_bounds__(PW_THREADS, 3)
+dconv_wide_kernel(const GConvK g, const float* __restrict__ bias, const int act, const float beta,
+                  const float* __restrict__ mask_y, const int mask_act, float* __restrict__ out) {
+  __shared__ float4 Ws[PW_KMAX * DW_QT];   // [k][quad]
+  const int tid = threadIdx.x;
+  int ctot = 0;
+  for (int s = 0; s < g.nseg; ++s) ctot += g.seg[s].C;
+  const int ntaps = g.ay.nu * g.ax.nu;
+  for (int idx = tid; idx < ntaps * ctot * DW_QT; idx += PW_THREADS) {
+    const int k = idx / DW_QT, q = idx - k * DW_QT;
+    const int tapi = k / ctot, c = k - tapi * ctot;
+    const int uy = tapi / g.ax.nu, ux = tapi - uy * g.ax.nu;
+    const int tap = (g.ay.d0 + g.ay.ds * uy) * g.kw + (g.ax.d0 + g.ax.ds * ux);
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int n = q * 4 + e;
+      v[e] = n < g.Cout ? __ldg(g.w + (long long)tap * g.wt + (long long)c * g.wc + (long long)n * g.wn) : 0.f;
+    }
+    Ws[idx] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  __syncthreads();
+
+  const uint32_t pbase = (uint32_t)blockIdx.x * (PW_THREADS * R) + tid;
+  int pn[R], pty[R], ptx[R];
+  bool ok[R];
+  float acc[R][DW_QT][4];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const uint32_t pp = pbase + r * PW_THREADS;
+    ok[r] = pp < g.M;
+    pn[r] = 0; pty[r] = 0; ptx[r] = 0;
+    if (ok[r]) decode_pixel(g, pp, pn[r], pty[r], ptx[r]);
+#pragma unroll
+    for (int j = 0; j < DW_QT; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[r][j][e] = 0.f;
+  }
+  if (bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < DW_QT; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float b = j * 4 + e < g.Cout ? __ldg(bias + j * 4 + e) : 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r][j][e] = b;
+      }
+  }
+
+  int k = 0;
+  for (int uy = 0; uy < g.ay.nu; ++uy)
+    for (int ux = 0; ux < g.ax.nu; ++ux) {
+      uint32_t pin[R];     // input pixel index (batch included; build_phases checks N*H*W < 2^31)
+      bool in[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int iy = pty[r] * g.ay.it + uy * g.ay.iu + g.ay.i0;
+        const int ix = ptx[r] * g.ax.it + ux * g.ax.iu + g.ax.i0;
+        in[r] = ok[r] && (unsigned)iy < (unsigned)g.Hin && (unsigned)ix < (unsigned)g.Win;
+        pin[r] = ((uint32_t)pn[r] * g.Hin + iy) * g.Win + ix;
+      }
+      for (int s = 0; s < g.nseg; ++s) {
+        const Seg sg = g.seg[s];
+        const float* pa[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          uint32_t pix = pin[r];
+          if (sg.bcast) pix -= (uint32_t)pn[r] * g.Hin * g.Win;
+          pa[r] = sg.ptr + (size_t)pix * sg.C;
+        }
+        for (int c = 0; c < sg.C; c += 4) {
+          float a[R][4];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in[r]) v = ld4(pa[r] + c);
+            a[r][0] = v.x; a[r][1] = v.y; a[r][2] = v.z; a[r][3] = v.w;
+          }
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+            for (int j = 0; j < DW_QT; ++j) {
+              const float4 w = Ws[(k + kk) * DW_QT + j];
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                acc[r][j][0] = fmaf(a[r][kk], w.x, acc[r][j][0]); acc[r][j][1] = fmaf(a[r][kk], w.y, acc[r][j][1]);
+                acc[r][j][2] = fmaf(a[r][kk], w.z, acc[r][j][2]); acc[r][j][3] = fmaf(a[r][kk], w.w, acc[r][j][3]);
+              }
+            }
+          }
+          k += 4;
+        }
+      }
+    }
+
+  // epilogue: Cout % 4 == 0 and 16-byte aligned out / mask (checked by the host): float4 path only
+  const int nqo = g.Cout >> 2;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (!ok[r]) continue;
+    const int oy = g.ay.o0 + g.ay.os * pty[r], ox = g.ax.o0 + g.ax.os * ptx[r];
+    const size_t ob = (size_t)(((uint32_t)pn[r] * g.Hout + oy) * g.Wout + ox) * (uint32_t)g.Cout;
+    constexpr int EB = 2;
+#pragma unroll
+    for (int j0 = 0; j0 < DW_QT; j0 += EB) {
+      float4 oldv[EB], yv[EB];
+#pragma unroll
+      for (int jj = 0; jj < EB; ++jj) {
+        oldv[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+        yv[jj] = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (j0 + jj < nqo) {
+          if (beta != 0.f) oldv[jj] = *reinterpret_cast<const float4*>(out + ob + (j0 + jj) * 4);
+          if (mask_y != nullptr) yv[jj] = ld4(mask_y + ob + (j0 + jj) * 4);
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < EB; ++jj) {
+        const int j = j0 + jj;
+        if (j >= nqo) continue;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = act_fwd(acc[r][j][e], act);
+        const float4 o = oldv[jj], y = yv[jj];
+        v[0] += beta * o.x; v[1] += beta * o.y; v[2] += beta * o.z; v[3] += beta * o.w;
+        if (mask_y != nullptr) {
+          v[0] *= act_bwd_from_y(y.x, mask_act); v[1] *= act_bwd_from_y(y.y, mask_act);
+          v[2] *= act_bwd_from_y(y.z, mask_act); v[3] *= act_bwd_from_y(y.w, mask_act);
+        }
+        *reinterpret_cast<float4*>(out + ob + j * 4) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    }
+  }
+}
+
+int g_opt_dconv_wide = -1;   // -1: environment default (NLT_DCONV_WIDE), 0 off, 1 on
+
+bool dconv_wide_applicable(const GConvK& k, const float* out, const float* mask_y) {
+  if (g_opt_dconv_wide < 0) {
+    const char* e = getenv("NLT_DCONV_WIDE");
+    g_opt_dconv_wide = e ? (atoi(e) != 0) : NLT_DCONV_WIDE_DEFAULT;
+  }
+  if (!g_opt_dconv_wide || k.d2s || k.M == 0) return false;
+  if (k.Cout <= 8 || k.Cout > 16 || k.Cout % 4 != 0 || k.cout_true != k.Cout) return false;
+  int ctot = 0;
+  for (int s = 0; s < k.nseg; ++s) {
+    if (!k.seg[s].vec || k.seg[s].sub != nullptr) return false;
+    ctot += k.seg[s].C;
+  }
+  const int ktot = k.ay.nu * k.ax.nu * ctot;
+  if (ktot < 1 || ktot > PW_KMAX) return false;
+  return aligned16(out) && (mask_y == nullptr || aligned16(mask_y));
+}
+
+int launch_dconv_wide(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
+                      float* out, cudaStream_t st) {
+  constexpr int R = 2;
+  const unsigned grid = (k.M + PW_THREADS * R - 1) / (PW_THREADS * R);
+  dconv_wide_kernel<R><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
+  NLT_CUDA_LAUNCH_CHECK("dconv_wide_kernel");
+  return NLT_OK;
+}
+
 template <int NQ, int R>
 static void dconv_launch(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
                       float* out, cudaStream_t st) {
