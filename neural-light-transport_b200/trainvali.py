@@ -175,12 +175,49 @@ def distributed_vali_step(strategy, model, batch, global_bs):
     return loss, to_vis
 
 
+def batch_source(config, strategy, steps, device='cuda', mode='train', seed=None):
+    """This rank's shards of `steps` global batches (trainvali.py:72-90).
+
+    Real data when `<data_root>.json` exists: `datasets.get_dataset_class(config dataset)` -> pipeline ->
+    `.shard(world, rank)` (the reference's `experimental_distribute_dataset`), cycling over epochs; the tensors
+    arrive pinned and are copied to `device` asynchronously.  Otherwise (no NLT data on this machine) synthetic
+    batches of the configured shape (util/synth.py)."""
+    import os
+    from util import synth
+    bs = config.getint('DEFAULT', 'bs')
+    data_root = config.get('DEFAULT', 'data_root', fallback='')
+    if data_root and os.path.exists(data_root.rstrip('/') + '.json'):
+        import datasets
+        geti = lambda k, d: config.getint('DEFAULT', k, fallback=d)
+        pre, par = geti('prefetch_buffer_size', -1), geti('n_map_parallel_calls', -1)
+        ds = datasets.get_dataset_class(config.get('DEFAULT', 'dataset', fallback='nlt'))(
+            config, mode, shuffle_buffer_size=geti('shuffle_buffer_size', 64),
+            prefetch_buffer_size=None if pre < 0 else pre, n_map_parallel_calls=None if par < 0 else par)
+        pipe = ds.build_pipeline(seed=seed, no_batch=config.getboolean('DEFAULT', 'no_batch', fallback=False))
+        pipe = pipe.shard(strategy.world, strategy.rank)
+        done = 0
+        while done < steps:
+            n_before = done
+            for batch in pipe:
+                yield tuple(t.to(device, non_blocking=True) if torch.is_tensor(t) else t for t in batch)
+                done += 1
+                if done >= steps:
+                    return
+            if done == n_before:
+                raise RuntimeError('dataset pipeline produced no batch')
+        return
+    local_bs = max(bs // strategy.world, 1)
+    for step in range(steps):
+        yield synth.make_batch(local_bs, config.getint('DEFAULT', 'uvh'), config.getint('DEFAULT', 'imh'),
+                               seed=1234 + step * strategy.world + strategy.rank, device=device)
+
+
 def main(argv=None):
-    """Same CLI flags as the reference (--config --debug --device); trains on
-    synthetic batches because the dataset pipeline is out of scope (N3)."""
+    """Same CLI flags as the reference (--config --debug --device).  Trains from the on-disk dataset named by
+    the config when it exists (datasets/nlt.py), else on synthetic batches of the configured shape."""
     import argparse
     import models
-    from util import io as ioutil, synth
+    from util import io as ioutil
     ap = argparse.ArgumentParser()
     ap.add_argument('--config', default='dragon_specular.ini')
     ap.add_argument('--debug', action='store_true')
@@ -193,12 +230,9 @@ def main(argv=None):
     model = Model(config)
     model.register_trainable()
     optimizer = Adam(learning_rate=config.getfloat('DEFAULT', 'lr'), amsgrad=True)
-    bs = config.getint('DEFAULT', 'bs')
-    global_bs = bs
-    local_bs = max(bs // strategy.world, 1)
-    for step in range(1 if args.debug else args.steps):
-        batch = synth.make_batch(local_bs, config.getint('DEFAULT', 'uvh'), config.getint('DEFAULT', 'imh'),
-                                 seed=1234 + step * strategy.world + strategy.rank, device='cuda')
+    global_bs = config.getint('DEFAULT', 'bs')
+    steps = 1 if args.debug else args.steps
+    for step, batch in enumerate(batch_source(config, strategy, steps, device='cuda')):
         loss, _ = distributed_train_step(strategy, model, batch, optimizer, global_bs)
         if strategy.rank == 0:
             print('step %d loss %.6f' % (step, float(loss)))
