@@ -682,7 +682,10 @@ bool dconv_wide_applicable(const GConvK& k, const float* out, const float* mask_
     g_opt_dconv_wide = e ? (atoi(e) != 0) : NLT_DCONV_WIDE_DEFAULT;
   }
   if (!g_opt_dconv_wide || k.d2s || k.M == 0) return false;
-  if (k.Cout <= 8 || k.Cout > 16 || k.Cout % 4 != 0 || k.cout_true != k.Cout) return false;
+  // routed shapes = the ones validated on hardware so far (tests/test_gpu_ops.py GEOMS + the model): exactly 16
+  // output channels from ONE non-broadcast float4 source; the kernel itself is written for 12/16 outputs and
+  // any segment list
+  if (k.Cout != 16 || k.cout_true != k.Cout || k.nseg != 1 || k.seg[0].bcast) return false;
   int ctot = 0;
   for (int s = 0; s < k.nseg; ++s) {
     if (!k.seg[s].vec || k.seg[s].sub != nullptr) return false;
