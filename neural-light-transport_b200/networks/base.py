@@ -1,4 +1,5 @@
-"""Mirror of nlt/networks/base.py:26-40."""
+"""Root of the network classes.  Interface of nlt/networks/base.py:26-40: a `.layers` list, call-ability, and the
+`str2none` helper the INI-driven constructors use (ConfigParser has no notion of None, so 'None' arrives as text)."""
 
 
 class Network:
@@ -10,9 +11,6 @@ class Network:
 
     @staticmethod
     def str2none(str_):
-        """Mostly to overcome there being no `config.getnone()` method
-        (reference: nlt/networks/base.py:33-40)."""
+        """'none' in any capitalisation -> None, every other string unchanged; non-strings are a caller bug."""
         assert isinstance(str_, str), "Call this only on strings"
-        if str_.lower() == 'none':
-            return None
-        return str_
+        return None if str_.lower() == 'none' else str_

@@ -1,9 +1,6 @@
-"""UV-space encoder/decoder layer list -- mirror of nlt/networks/convnet.py:30-90.
-
-Same constructor, same attributes (.layers, .is_contracting,
-.spatsize_changes); each entry of .layers is a callable Block (x -> y on NHWC
-CUDA tensors), which is what nlt/nlt_test.py:111-114 and
-nlt/models/nlt.py:147-198 iterate over.
+"""UV-space encoder/decoder: the layer list behind `networks.convnet.Network` (interface of
+nlt/networks/convnet.py:30-90).  Every entry of `.layers` is a callable `Block` (x -> y on NHWC CUDA tensors, or
+on engine segments), which is what `nlt_test.extract_feat` and the two-stream walk of `models.nlt` iterate over.
 """
 import numpy as np
 import torch
@@ -45,47 +42,50 @@ class Block:
         return self.forward_segs([Seg(Act(x.contiguous()))]).t
 
 
+def _block_kinds(n_feat):
+    """('down' | 'up', channels) for every entry of the channel schedule but the last: a block contracts when its
+    channel count does not drop below the previous block's -- so 256 -> 256 is still a *down* block
+    (nlt/networks/convnet.py:49), which is why depth 256 gives six downs and six ups."""
+    kinds, prev = [], 0
+    for n in n_feat[:-1]:
+        kinds.append(('down' if n >= prev else 'up', n))
+        prev = n
+    return kinds
+
+
 class Network(BaseNetwork):
-    def __init__(
-            self, depth0, depth, kernel, stride, norm_type=None,
-            act_type='relu', pool_type=None):
+    """Constructor signature, `.layers`, `.is_contracting` and `.spatsize_changes` of nlt/networks/convnet.py:30-90:
+    [1x1 conv -> depth0] + one two-conv block per schedule entry (strided conv + conv when contracting, strided
+    transposed conv + transposed conv when expanding, each followed by the activation) + [1x1 conv -> 3]."""
+
+    def __init__(self, depth0, depth, kernel, stride, norm_type=None, act_type='relu', pool_type=None):
         super().__init__()
-        norm_type = self.str2none(norm_type)
-        pool_type = self.str2none(pool_type)
-        norm(norm_type)   # raises NotImplementedError for unsupported kinds
-        pool(pool_type)
-        a = act(act_type)
+        # unsupported normalisation / pooling kinds raise NotImplementedError right here, like the reference's
+        # element factories; the supported kind for both is None (identity)
+        norm(self.str2none(norm_type))
+        pool(self.str2none(pool_type))
+        activation = act(act_type)
         n_feat = netutil.gen_feat_n(depth0, depth)
-        prev_n = 0
+
+        def add(convs, contracting, scale):
+            self.layers.append(Block(convs))
+            self.is_contracting.append(contracting)
+            self.spatsize_changes.append(scale)
+
+        def pair(make, n):
+            first, second = make(kernel, n, stride=stride), make(kernel, n, stride=1)
+            first.act = second.act = activation
+            return [first, second]
+
         self.is_contracting, self.spatsize_changes = [], []
-        # 1x1 conv to generate an original-res. feature map (convnet.py:44)
-        self.layers.append(Block([conv(1, n_feat[0], stride=1)]))
-        self.is_contracting.append(True)
-        self.spatsize_changes.append(1)
-        for n in n_feat[:-1]:
-            if n >= prev_n:   # so 64 -> 64 is considered "contracting" (:49)
-                c1, c2 = conv(kernel, n, stride=stride), conv(kernel, n, stride=1)
-                c1.act = c2.act = a
-                self.layers.append(Block([c1, c2]))
-                self.is_contracting.append(True)
-                self.spatsize_changes.append(1 / stride)
+        add([conv(1, n_feat[0], stride=1)], True, 1)                 # full-resolution feature map
+        for kind, n in _block_kinds(n_feat):
+            if kind == 'down':
+                add(pair(conv, n), True, 1 / stride)
             else:
-                d1, d2 = deconv(kernel, n, stride=stride), deconv(kernel, n, stride=1)
-                d1.act = d2.act = a
-                self.layers.append(Block([d1, d2]))
-                self.is_contracting.append(False)
-                self.spatsize_changes.append(stride)
-            prev_n = n
-        # final 1x1 conv (convnet.py:85)
-        self.layers.append(Block([conv(1, n_feat[-1], stride=1)]))
-        self.is_contracting.append(False)
-        self.spatsize_changes.append(1)
-        spatsizes = np.cumprod(self.spatsize_changes)
-        assert spatsizes[-1] == 1, \
-            "Resolution doesn't return to the original value"
+                add(pair(deconv, n), False, stride)
+        add([conv(1, n_feat[-1], stride=1)], False, 1)               # back to 3 channels
+        assert float(np.prod(self.spatsize_changes)) == 1, "Resolution doesn't return to the original value"
 
     def conv_layers(self):
-        out = []
-        for blk in self.layers:
-            out += blk.convs
-        return out
+        return [c for blk in self.layers for c in blk.convs]

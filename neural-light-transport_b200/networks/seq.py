@@ -1,4 +1,8 @@
-"""Mirror of nlt/networks/seq.py:27-41 (simple sequential flow)."""
+"""Sequential network: `build(input_shape)` then `net(x)` runs the layers in order (interface of
+nlt/networks/seq.py:27-41).  Layers are engine-backed blocks whose `build(cin, device)` returns their output
+channel count, so building is a fold over the channel dimension of `input_shape` (NHWC)."""
+import functools
+
 import torch
 
 from .base import Network as BaseNetwork
@@ -6,18 +10,12 @@ from .base import Network as BaseNetwork
 
 class Network(BaseNetwork):
     def build(self, input_shape):
-        """input_shape: (N, H, W, C) like Keras' Sequential.build."""
-        cin = int(input_shape[-1])
-        dev = torch.device('cuda', torch.cuda.current_device())
-        for layer in self.layers:
-            cin = layer.build(cin, dev)
-        for layer in self.layers:
-            assert layer.built, "Some layers not built"
+        device = torch.device('cuda', torch.cuda.current_device())
+        functools.reduce(lambda cin, layer: layer.build(cin, device), self.layers, int(input_shape[-1]))
+        assert all(layer.built for layer in self.layers), "Some layers not built"
 
     def __call__(self, tensor):
-        x = tensor
-        y = None
+        out = None
         for layer in self.layers:
-            y = layer(x)
-            x = y
-        return y
+            out = tensor = layer(tensor)
+        return out

@@ -1,29 +1,29 @@
-"""Channel schedule -- same semantics as nlt/util/net.py:18-56."""
-import math
+"""Channel schedule of the encoder/decoder (semantics of nlt/util/net.py:18-56, checked against the reference
+function's own outputs in tests/golden/gen_feat_n_reference.npz)."""
 
 
-def _ilog2(x):
-    return int(math.floor(math.log2(x) + 1e-12))
+def _floor_log2(x):
+    """floor(log2(x)) for x >= 1, the way int(np.log2(x)) truncates."""
+    x = float(x)
+    e = 0
+    while 2.0 ** (e + 1) <= x:
+        e += 1
+    return e
 
 
 def gen_feat_n(min_n, max_n, final_n=3):
-    """Numbers of channels across the network, excluding the first layer that
-    produces an original-resolution feature map,
-    e.g. `[8, 16, 32, 64, 64, 32, 16, 8, 4, 3]`."""
+    """Channel counts of every block after the full-resolution 1x1 conv: powers of two rising from `min_n` to
+    `max_n` (both ends included even when not powers of two), the same list mirrored, then halving down to --
+    and ending with -- `final_n`.  (16, 256) -> [16, 32, 64, 128, 256, 256, 128, 64, 32, 16, 8, 4, 3]."""
     assert max_n >= min_n and max_n >= final_n, \
-        ("Max number of channels must be greater than or equal to the final "
-         "number of channel")
-    up = [1 << e for e in range(_ilog2(min_n) + 1, _ilog2(max_n) + 1)]
-    if not up or up[0] != min_n:
-        up.insert(0, min_n)
-    if up[-1] != max_n:
-        up.append(max_n)
-    seq = up + up[::-1]
-    e = _ilog2(seq[-1]) - 1
-    while e > _ilog2(final_n):
-        seq.append(1 << e)
-        e -= 1
-    while seq and seq[-1] < final_n:
-        seq.pop()
-    seq.append(final_n)
-    return seq
+        "Max number of channels must be greater than or equal to the final number of channel"
+    rising = [min_n] + [2 ** e for e in range(_floor_log2(min_n) + 1, _floor_log2(max_n) + 1) if 2 ** e != min_n]
+    if rising[-1] != max_n:
+        rising.append(max_n)
+    schedule = rising + rising[::-1]
+    # halve below the last mirrored entry while strictly above final_n's power of two ...
+    schedule += [2 ** e for e in range(_floor_log2(schedule[-1]) - 1, _floor_log2(final_n), -1)]
+    # ... and never end on something smaller than final_n before appending it
+    while schedule and schedule[-1] < final_n:
+        schedule.pop()
+    return schedule + [final_n]
