@@ -325,7 +325,7 @@ class Model(BaseModel):
         self._d_pred = None
 
     # ------------------------------------------------------------------
-    # visualisation (numbers only; PNG/APNG/HTML writers are out of scope)
+    # visualisation (host side)
     # ------------------------------------------------------------------
     @staticmethod
     def psnr(im1, im2):
@@ -336,30 +336,86 @@ class Model(BaseModel):
         mse = np.mean((a - b) ** 2)
         return float(10 * np.log10(1.0 / mse)) if mse > 0 else float('inf')
 
+    @staticmethod
+    def _linear2srgb(im):
+        """IEC 61966-2-1 transfer curve on values in [0, 1] (xiuminglib img.linear2srgb)."""
+        im = np.asarray(im, dtype=np.float64)
+        return np.where(im <= 0.0031308, 12.92 * im, 1.055 * np.power(np.maximum(im, 0.0031308), 1 / 2.4) - 0.055)
+
+    @staticmethod
+    def _write_png(arr_0to1, path):
+        """float [0, 1] -> uint8 by truncation (xiuminglib io.img.write_arr: `(arr * 255).astype(uint8)`) -> PNG."""
+        from PIL import Image
+        img = (np.asarray(arr_0to1) * 255).astype(np.uint8)
+        Image.fromarray(img).save(path)
+        return img
+
     def vis_batch(self, data_dict, outdir, mode, dump_raw_to=None, **_):
-        """Writes `<i>_metadata.json` (id, nn_id, PSNRs as in nlt.py:258-269)
-        and raw `<i>_{pred,base,gt}.npy`; image/apng writers need xiuminglib
-        and are outside the hot path."""
+        """Per example i of the batch (nlt/models/nlt.py:207-271): `<i>_{base,pred,nn,gt}.png` (clipped to [0, 1],
+        linear -> sRGB when the config says `linear_space`), `<i>_base-vs-pred.apng` / `<i>_gt-vs-pred.apng` flip
+        books (unlabelled: the reference draws captions with xiuminglib), `<i>_metadata.json` with the ids and
+        the luma PSNRs of prediction and diffuse base against the ground truth; `dump_raw_to` pickles the raw
+        dictionary.  Everything here runs on the host after the tensors left the GPU."""
+        import pickle
+        from PIL import Image
         self._validate_mode(mode)
         os.makedirs(outdir, exist_ok=True)
+        to_np = lambda t: t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
         dec = lambda x: x.decode() if isinstance(x, bytes) else str(x)
         ids = [dec(x) for x in data_dict['id']]
         nn_ids = [dec(x) for x in data_dict['nn_id']]
-        preds = data_dict['pred_camspc'].detach().cpu().numpy()
-        bases = data_dict['base_camspc'].detach().cpu().numpy()
-        gts = None if mode == 'test' else data_dict['gt_camspc'].detach().cpu().numpy()
+        preds, bases = to_np(data_dict['pred_camspc']), to_np(data_dict['base_camspc'])
+        nns = to_np(data_dict['nn_camspc']) if 'nn_camspc' in data_dict else None
+        gts = None if mode == 'test' else to_np(data_dict['gt_camspc'])
+        is_linear = self.config.getboolean('DEFAULT', 'linear_space', fallback=False)
+        shown = (lambda x: self._linear2srgb(x)) if is_linear else (lambda x: x)
         for i, id_ in enumerate(ids):
-            meta = {'id': id_, 'nn_id': nn_ids[i]}
             pred, base = np.clip(preds[i], 0, 1), np.clip(bases[i], 0, 1)
-            np.save(os.path.join(outdir, '%d_pred.npy' % i), pred)
-            np.save(os.path.join(outdir, '%d_base.npy' % i), base)
-            if gts is not None:
-                gt = np.clip(gts[i], 0, 1)
-                np.save(os.path.join(outdir, '%d_gt.npy' % i), gt)
+            gt = None if gts is None else np.clip(gts[i], 0, 1)
+            frames = {'base': self._write_png(shown(base), os.path.join(outdir, '%d_base.png' % i)),
+                      'pred': self._write_png(shown(pred), os.path.join(outdir, '%d_pred.png' % i))}
+            if nns is not None:
+                self._write_png(shown(np.clip(nns[i], 0, 1)), os.path.join(outdir, '%d_nn.png' % i))
+            if gt is not None:
+                frames['gt'] = self._write_png(shown(gt), os.path.join(outdir, '%d_gt.png' % i))
+            for first, second in (('base', 'pred'), ('gt', 'pred')):
+                if first in frames:
+                    a, b = Image.fromarray(frames[first]), Image.fromarray(frames[second])
+                    a.save(os.path.join(outdir, '%d_%s-vs-%s.apng' % (i, first, second)), format='PNG',
+                           save_all=True, append_images=[b], duration=500, loop=0)
+            meta = {'id': id_, 'nn_id': nn_ids[i]}
+            if gt is not None:
                 meta['pred_psnr'] = self.psnr(gt, pred)
                 meta['base_psnr'] = self.psnr(gt, base)
             with open(os.path.join(outdir, '%d_metadata.json' % i), 'w') as h:
                 json.dump(meta, h)
+        if dump_raw_to is not None:
+            raw = {k: (to_np(v) if torch.is_tensor(v) else v) for k, v in data_dict.items()}
+            with open(dump_raw_to, 'wb') as h:
+                pickle.dump(raw, h)
 
     def compile_batch_vis(self, batch_vis_dirs, outpref, mode, fps=6, **_):
-        raise NotImplementedError('HTML/MP4 compilation needs xiuminglib (out of scope, SURVEY.md 8f N4)')
+        """train / vali: one HTML page with a row per visualised example (flip books + PSNRs); the reference also
+        renders test batches into an MP4, which needs an encoder that is not part of this repo."""
+        self._validate_mode(mode)
+        if mode == 'test':
+            raise NotImplementedError('MP4 compilation of test batches needs a video encoder (SURVEY.md 8f N4)')
+        rows = []
+        for d in batch_vis_dirs:
+            for name in sorted(f for f in os.listdir(d) if f.endswith('_metadata.json')):
+                i = name.split('_')[0]
+                with open(os.path.join(d, name)) as h:
+                    meta = json.load(h)
+                cells = ['<td>%s</td>' % meta['id']]
+                for pair in ('gt-vs-pred', 'base-vs-pred'):
+                    f = os.path.join(d, '%s_%s.apng' % (i, pair))
+                    cells.append('<td><img src="%s"></td>' % os.path.relpath(f, os.path.dirname(outpref) or '.')
+                                 if os.path.exists(f) else '<td></td>')
+                cells.append('<td>%s</td>' % ', '.join('%s %.2f dB' % (k, meta[k]) for k in ('pred_psnr', 'base_psnr')
+                                                         if k in meta))
+                rows.append('<tr>%s</tr>' % ''.join(cells))
+        outpath = outpref + '.html'
+        with open(outpath, 'w') as h:
+            h.write('<html><head><title>NLT (%s)</title></head><body><table>\n%s\n</table></body></html>\n'
+                    % (mode, '\n'.join(rows)))
+        return outpath

@@ -227,3 +227,58 @@ def test_parked_contribution_without_follower_is_settled_by_the_tape():
         engine.USE_SIDE_STREAM = old
     # the second consumer never contributed (its own gradient was None): the parked one must not be lost
     assert log == [('final1x1', 0.0, False, 0, None)] and a.grad is not None and a.pending is None
+
+
+def test_vis_batch_outputs_and_psnr(tmp_path):
+    """Host-side visualisation (nlt/models/nlt.py:207-286): PNGs by truncating uint8 conversion,
+    flip-book APNGs, metadata with luma PSNRs, optional raw pickle, HTML index."""
+    import json
+    import pickle
+    import numpy as np
+    from PIL import Image
+    import models
+    from util import io as ioutil
+    m = models.get_model_class('nlt')(ioutil.read_config('dragon_specular.ini'))
+    g = torch.Generator().manual_seed(3)
+    B, H, W = 2, 6, 5
+    gt = torch.rand(B, H, W, 3, generator=g)
+    pred = (gt + 0.05 * torch.randn(B, H, W, 3, generator=g))            # leaves [0, 1]: must be clipped
+    base = torch.rand(B, H, W, 3, generator=g)
+    d = {'id': [b'trainvali_000000000_c_l', b'trainvali_000000001_c_l'], 'nn_id': [b'n0', b'n1'],
+         'pred_camspc': pred, 'base_camspc': base, 'nn_camspc': base * 0.5, 'gt_camspc': gt}
+    out = str(tmp_path / 'vis' / 'batch0')
+    raw = str(tmp_path / 'raw.pkl')
+    m.vis_batch(d, out, 'vali', dump_raw_to=raw)
+    for i in range(B):
+        for name in ('base', 'pred', 'nn', 'gt'):
+            assert os.path.exists(os.path.join(out, '%d_%s.png' % (i, name)))
+        got = np.array(Image.open(os.path.join(out, '%d_pred.png' % i)))
+        want = (np.clip(pred[i].numpy(), 0, 1) * 255).astype(np.uint8)   # truncation, not rounding
+        np.testing.assert_array_equal(got, want)
+        ap = Image.open(os.path.join(out, '%d_gt-vs-pred.apng' % i))
+        assert getattr(ap, 'n_frames', 1) == 2
+        meta = json.load(open(os.path.join(out, '%d_metadata.json' % i)))
+        assert meta['id'] == d['id'][i].decode() and meta['nn_id'] == d['nn_id'][i].decode()
+        # luma PSNR, dynamic range 1, on the clipped images
+        w = np.array([0.2126, 0.7152, 0.0722])
+        a, b = np.clip(gt[i].numpy().astype(np.float64), 0, 1) @ w, np.clip(pred[i].numpy().astype(np.float64), 0, 1) @ w
+        assert abs(meta['pred_psnr'] - 10 * np.log10(1.0 / np.mean((a - b) ** 2))) <= 1e-9
+        assert meta['base_psnr'] < meta['pred_psnr']
+    dumped = pickle.load(open(raw, 'rb'))
+    np.testing.assert_array_equal(dumped['pred_camspc'], pred.numpy())
+    page = m.compile_batch_vis([out], str(tmp_path / 'vis' / 'index'), 'vali')
+    html = open(page).read()
+    assert page.endswith('.html') and html.count('<tr>') == B and 'batch0/0_gt-vs-pred.apng' in html
+    # test mode: no ground truth, no PSNRs; MP4 compilation is not offered
+    out_t = str(tmp_path / 'vis' / 'test0')
+    m.vis_batch({k: v for k, v in d.items() if k != 'gt_camspc'}, out_t, 'test')
+    meta = json.load(open(os.path.join(out_t, '0_metadata.json')))
+    assert 'pred_psnr' not in meta and not os.path.exists(os.path.join(out_t, '0_gt.png'))
+    with pytest.raises(NotImplementedError):
+        m.compile_batch_vis([out_t], str(tmp_path / 'vis' / 'video'), 'test')
+    with pytest.raises(ValueError):
+        m.vis_batch(d, out, 'predict')
+    # linear -> sRGB transfer curve
+    lin = np.array([0.0, 0.0031308, 0.5, 1.0])
+    np.testing.assert_allclose(m._linear2srgb(lin), [0.0, 12.92 * 0.0031308, 1.055 * 0.5 ** (1 / 2.4) - 0.055, 1.0],
+                               rtol=1e-12)
