@@ -72,7 +72,9 @@ const char* nlt_version(void);
 /* process-wide switches: "tc" (1: tcgen05 3xTF32 path where eligible [default], 0: fp32-FMA kernels only),
  * "tc_wgrad" (same for the weight-gradient kernel), "wgrad_rows" (1: row-run form of the warp-stream
  * weight-gradient kernel where float4 access allows it [default], 0: flat-pixel form), "dconv_wide" (1: the
- * pixel x 16-outputs stencil kernel for the 16-channel stencils, 0: the tiled implicit-GEMM kernel).
+ * pixel x 16-outputs stencil kernel for the 16-channel stencils, 0: the tiled implicit-GEMM kernel),
+ * "dconv_wide32" (EXPERIMENTAL, default 0 = off, not yet validated on hardware: the 32-output form of that kernel;
+ * 1 = one pixel per thread, 2 = two).
  * Environment defaults: NLT_DISABLE_TC=1, NLT_DISABLE_TC_WGRAD=1, NLT_DCONV_WIDE=0|1. */
 int nlt_set_option(const char* name, int value);
 const char* nlt_last_error(void);

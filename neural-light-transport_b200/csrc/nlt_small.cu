@@ -537,13 +537,13 @@ dconv_small_kernel(const GConvK g, const float* __restrict__ bias, const int act
 // input float4 is loaded once per 64 FMAs and every weight LDS.128 feeds 4*R FMAs.  Vector sources only, no
 // depth-to-space (those go to the pointwise kernel).
 // -----------------------------------------------------------------------------
-constexpr int DW_QT = 4;
+constexpr int DW_KMAX = 128;   // taps * channels of the widest routed stencil (32 -> 32 channels, 2x2)
 
-template <int R>
-__global__ void __launch_bounds__(PW_THREADS, 3)
+template <int DW_QT, int R, int MINB>
+__global__ void __launch_bounds__(PW_THREADS, MINB)
 dconv_wide_kernel(const GConvK g, const float* __restrict__ bias, const int act, const float beta,
                   const float* __restrict__ mask_y, const int mask_act, float* __restrict__ out) {
-  __shared__ float4 Ws[PW_KMAX * DW_QT];   // [k][quad]
+  __shared__ float4 Ws[(DW_QT == 4 ? PW_KMAX : DW_KMAX) * DW_QT];   // [k][quad]
   const int tid = threadIdx.x;
   int ctot = 0;
   for (int s = 0; s < g.nseg; ++s) ctot += g.seg[s].C;
@@ -676,31 +676,45 @@ dconv_wide_kernel(const GConvK g, const float* __restrict__ bias, const int act,
 
 int g_opt_dconv_wide = -1;   // -1: environment default (NLT_DCONV_WIDE), 0 off, 1 on
 
+int g_opt_dconv_wide32 = -1;   // EXPERIMENTAL (not validated on hardware yet): the 32-output form, default off
+
+static bool dconv_wide_common(const GConvK& k, const float* out, const float* mask_y, int cout, int kmax) {
+  if (k.d2s || k.M == 0) return false;
+  // routed shapes = the ones validated on hardware (tests/test_gpu_ops.py GEOMS + the model): ONE non-broadcast
+  // float4 source; the kernel itself is written for any segment list
+  if (k.Cout != cout || k.cout_true != k.Cout || k.nseg != 1 || k.seg[0].bcast) return false;
+  if (!k.seg[0].vec || k.seg[0].sub != nullptr) return false;
+  const int ktot = k.ay.nu * k.ax.nu * k.seg[0].C;
+  if (ktot < 1 || ktot > kmax) return false;
+  return aligned16(out) && (mask_y == nullptr || aligned16(mask_y));
+}
+
 bool dconv_wide_applicable(const GConvK& k, const float* out, const float* mask_y) {
   if (g_opt_dconv_wide < 0) {
     const char* e = getenv("NLT_DCONV_WIDE");
     g_opt_dconv_wide = e ? (atoi(e) != 0) : NLT_DCONV_WIDE_DEFAULT;
   }
-  if (!g_opt_dconv_wide || k.d2s || k.M == 0) return false;
-  // routed shapes = the ones validated on hardware so far (tests/test_gpu_ops.py GEOMS + the model): exactly 16
-  // output channels from ONE non-broadcast float4 source; the kernel itself is written for 12/16 outputs and
-  // any segment list
-  if (k.Cout != 16 || k.cout_true != k.Cout || k.nseg != 1 || k.seg[0].bcast) return false;
-  int ctot = 0;
-  for (int s = 0; s < k.nseg; ++s) {
-    if (!k.seg[s].vec || k.seg[s].sub != nullptr) return false;
-    ctot += k.seg[s].C;
+  if (g_opt_dconv_wide32 < 0) {
+    const char* e = getenv("NLT_DCONV_WIDE32");
+    g_opt_dconv_wide32 = e ? atoi(e) : 0;
   }
-  const int ktot = k.ay.nu * k.ax.nu * ctot;
-  if (ktot < 1 || ktot > PW_KMAX) return false;
-  return aligned16(out) && (mask_y == nullptr || aligned16(mask_y));
+  if (g_opt_dconv_wide && dconv_wide_common(k, out, mask_y, 16, PW_KMAX)) return true;
+  return g_opt_dconv_wide32 > 0 && dconv_wide_common(k, out, mask_y, 32, DW_KMAX);
 }
 
 int launch_dconv_wide(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
                       float* out, cudaStream_t st) {
-  constexpr int R = 2;
-  const unsigned grid = (k.M + PW_THREADS * R - 1) / (PW_THREADS * R);
-  dconv_wide_kernel<R><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
+  if (k.Cout == 16) {
+    constexpr int R = 2;
+    const unsigned grid = (k.M + PW_THREADS * R - 1) / (PW_THREADS * R);
+    dconv_wide_kernel<4, R, 3><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
+  } else if (g_opt_dconv_wide32 == 2) {      // two pixels per thread: 8 FMAs per weight LDS.128, ~2 CTAs per SM
+    const unsigned grid = (k.M + PW_THREADS * 2 - 1) / (PW_THREADS * 2);
+    dconv_wide_kernel<8, 2, 2><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
+  } else {                                   // one pixel per thread: 4 FMAs per weight LDS.128, 3 CTAs per SM
+    const unsigned grid = (k.M + PW_THREADS - 1) / PW_THREADS;
+    dconv_wide_kernel<8, 1, 3><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
+  }
   NLT_CUDA_LAUNCH_CHECK("dconv_wide_kernel");
   return NLT_OK;
 }

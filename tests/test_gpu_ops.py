@@ -3,6 +3,8 @@ oracle on seeded inputs.  Tolerances are fp32 round-off of sums of K terms
 (the SIMT path is plain fp32 FMA; no tensor-core truncation)."""
 import ctypes as C
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -258,6 +260,45 @@ def test_final_conv_input_gradient_rides_on_down_conv_dgrad(H, W, c_skip, c_othe
         assert torch.equal(a, b)
     if c_skip % 4 == 0:
         assert res[True]['launches'] == res[False]['launches'] - 1, (res[True]['launches'], res[False]['launches'])
+
+
+EXPERIMENTAL = os.environ.get('NLT_TEST_EXPERIMENTAL', '0') == '1'
+
+
+@pytest.mark.skipif(not EXPERIMENTAL, reason='experimental kernels are opt-in: NLT_TEST_EXPERIMENTAL=1')
+@pytest.mark.parametrize('mode', [1, 2])
+@pytest.mark.parametrize('kind,k,s,H,W,cin', [('conv', 2, 1, 16, 24, 32), ('conv', 2, 2, 32, 16, 16),
+                                              ('conv', 2, 2, 16, 16, 32), ('deconv', 2, 1, 12, 20, 32),
+                                              ('conv', 3, 1, 9, 11, 12)])
+def test_experimental_wide_stencil_32_outputs(kind, k, s, H, W, cin, mode):
+    """EXPERIMENTAL (not part of the validated build): the 32-output form of the wide stencil kernel (option
+    "dconv_wide32": 1 = one pixel per thread, 2 = two) against the default routing, fp32 kernels only."""
+    engine, nat = _mods()
+    dev = torch.device('cuda')
+    torch.manual_seed(31)
+    x = torch.randn(3, H, W, cin, device=dev)
+    res = {}
+    nat.set_option('tc', 0)
+    try:
+        for m in (mode, 0):
+            nat.set_option('dconv_wide32', m)
+            L = engine.ConvLayer(kind, k, s, 32, 'leakyrelu')
+            L.build(cin, dev, torch.Generator().manual_seed(1))
+            L.bias.copy_(torch.linspace(-0.1, 0.1, 32, device=dev))
+            a = engine.Act(x, act='leakyrelu', needs_grad=True)
+            tape = engine.Tape()
+            y = L.forward([engine.Seg(a)], tape)
+            torch.manual_seed(5)
+            y.grad = torch.randn_like(y.t)
+            tape.backward()
+            res[m] = (y.t.clone(), a.grad.clone(), L.gkernel.clone())
+    finally:
+        nat.set_option('dconv_wide32', 0)
+        nat.set_option('tc', 1)
+    rel = lambda p, q: float((p.double() - q.double()).norm() / q.double().norm())
+    assert rel(res[mode][0], res[0][0]) <= 1e-5
+    assert rel(res[mode][1], res[0][1]) <= 1e-5
+    assert torch.equal(res[mode][2], res[0][2])          # weight gradients do not go through this kernel
 
 
 def test_tensor_core_path_is_taken_and_matches_fp32_path():
