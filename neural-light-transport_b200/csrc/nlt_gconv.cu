@@ -658,6 +658,11 @@ uint64_t nlt_launch_count(void) { return __atomic_load_n(&nlt::g_launches, __ATO
 uint64_t nlt_tc_launch_count(void) { return __atomic_load_n(&nlt::g_tc_launches, __ATOMIC_RELAXED); }
 
 static int g_opt_tc = -1, g_opt_tc_wgrad = -1;   // -1: take the environment default
+static int g_opt_dconv_wide_first = -1;          // experimental routing switch (NLT_DCONV_WIDE_FIRST), see nlt_gconv_fwd_ws
+static bool dconv_wide_first() {
+  if (g_opt_dconv_wide_first < 0) { const char* e = getenv("NLT_DCONV_WIDE_FIRST"); g_opt_dconv_wide_first = (e && e[0] == '1') ? 1 : 0; }
+  return g_opt_dconv_wide_first == 1;
+}
 static bool tc_enabled() {
   if (g_opt_tc < 0) { const char* e = getenv("NLT_DISABLE_TC"); g_opt_tc = (e && e[0] == '1') ? 0 : 1; }
   return g_opt_tc == 1;
@@ -683,6 +688,7 @@ int nlt_set_option(const char* name, int value) {
   if (strcmp(name, "wgrad_rows") == 0) { nlt::g_opt_wgrad_rows = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "dconv_wide") == 0) { nlt::g_opt_dconv_wide = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "dconv_wide32") == 0) { nlt::g_opt_dconv_wide32 = value; return NLT_OK; }
+  if (strcmp(name, "dconv_wide_first") == 0) { g_opt_dconv_wide_first = value ? 1 : 0; return NLT_OK; }
   return set_err(NLT_ERR_INVALID, "unknown option '%s'", name);
 }
 
@@ -711,6 +717,10 @@ int nlt_gconv_fwd_ws(const nlt_gconv_desc* d, const float* bias, int act, float 
     const GConvK& k = ph[i];
     if (k.M == 0) continue;
     if (pw_conv_applicable(k)) rc = launch_pw_conv(k, bias, act, beta, mask_y, mask_act, out, st);
+    // EXPERIMENTAL routing (default off, option "dconv_wide_first"): prefer the wide stencil kernel over the
+    // quad-per-thread one where both apply (16 outputs, K <= 32: the up-conv input gradients of levels 11-12)
+    else if (dconv_wide_first() && dconv_small_applicable(k) && dconv_wide_applicable(k, out, mask_y))
+      rc = launch_dconv_wide(k, bias, act, beta, mask_y, mask_act, out, st);
     else if (dconv_small_applicable(k)) rc = launch_dconv_small(k, bias, act, beta, mask_y, mask_act, out, st);
     else if (dconv_wide_applicable(k, out, mask_y)) rc = launch_dconv_wide(k, bias, act, beta, mask_y, mask_act, out, st);
     else if (k.Cout > 32) rc = launch_fwd<128, 64, 8, 8>(k, bias, act, beta, mask_y, mask_act, out, st);

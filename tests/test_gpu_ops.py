@@ -301,6 +301,37 @@ def test_experimental_wide_stencil_32_outputs(kind, k, s, H, W, cin, mode):
     assert torch.equal(res[mode][2], res[0][2])          # weight gradients do not go through this kernel
 
 
+@pytest.mark.skipif(not EXPERIMENTAL, reason='experimental routing is opt-in: NLT_TEST_EXPERIMENTAL=1')
+@pytest.mark.parametrize('kind,k,s,H,W,cin', [('conv', 2, 2, 16, 24, 4), ('conv', 2, 2, 32, 16, 8), ('conv', 2, 1, 9, 16, 8),
+                                              ('deconv', 2, 1, 12, 8, 8)])
+def test_experimental_wide_stencil_preferred_over_quad_kernel(kind, k, s, H, W, cin):
+    """EXPERIMENTAL routing (option "dconv_wide_first"): 16 outputs from K <= 32 through the validated wide
+    stencil kernel instead of the quad-per-thread kernel -- same results."""
+    engine, nat = _mods()
+    dev = torch.device('cuda')
+    torch.manual_seed(33)
+    x = torch.randn(3, H, W, cin, device=dev)
+    res = {}
+    nat.set_option('tc', 0)
+    try:
+        for m in (1, 0):
+            nat.set_option('dconv_wide_first', m)
+            L = engine.ConvLayer(kind, k, s, 16, 'leakyrelu')
+            L.build(cin, dev, torch.Generator().manual_seed(1))
+            a = engine.Act(x, act='leakyrelu', needs_grad=True)
+            tape = engine.Tape()
+            y = L.forward([engine.Seg(a)], tape)
+            torch.manual_seed(5)
+            y.grad = torch.randn_like(y.t)
+            tape.backward()
+            res[m] = (y.t.clone(), a.grad.clone())
+    finally:
+        nat.set_option('dconv_wide_first', 0)
+        nat.set_option('tc', 1)
+    rel = lambda p, q: float((p.double() - q.double()).norm() / q.double().norm())
+    assert rel(res[1][0], res[0][0]) <= 1e-5 and rel(res[1][1], res[0][1]) <= 1e-5
+
+
 def test_tensor_core_path_is_taken_and_matches_fp32_path():
     """Eligible shapes must run on the tcgen05 kernel (launch counter moves) and agree with the
     fp32-FMA kernel of the same library to 3xTF32 accuracy (<= 4e-6 relative to the output scale)."""
