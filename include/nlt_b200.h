@@ -176,6 +176,18 @@ int nlt_l2_loss(const float* pred, const float* gt, int32_t B,
                 int64_t per_sample, float loss_scale, float* loss,
                 float* d_pred, void* workspace, void* stream);
 
+/* EXPERIMENTAL (arithmetic checked on the CPU against the pinned oracle, kernels not yet
+ * validated on hardware): losses.Barron with keep_batch (nlt/losses.py:90-121) fused with its gradient.
+ *   r = (gt - pred) [* alpha]  ->  volume-preserving YUV  ->  `levels`-level CDF 9/7 analysis (reflecting
+ *   boundaries)  ->  nll = sqrt((w/scale)^2 + 1) - 1 + log(scale) + log_z per coefficient
+ *   loss[b] = mean_{h,w,c} nll ;  d_pred = d(sum_b loss[b] * loss_scale) / d(pred)
+ * pred, gt: [B,H,W,3]; alpha: [B,H,W,1] or NULL; log_z = log Z(1) = log(2 e K_1(1)) = 1.18549523...;
+ * levels <= ceil(log2(min(H, W))) (the reference uses 5); d_pred may be NULL; workspace >= _workspace_bytes(). */
+int64_t nlt_barron_loss_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t levels);
+int nlt_barron_loss(const float* pred, const float* gt, const float* alpha, int32_t B, int32_t H, int32_t W,
+                    int32_t levels, float scale, float log_z, float loss_scale, float* loss, float* d_pred,
+                    void* workspace, void* stream);
+
 /* tf.keras.optimizers.Adam(lr, amsgrad=True) dense update over a flat bucket
  * (nlt/trainvali.py:122-127, 280); step is 1-based; grad_scale multiplies g. */
 int nlt_amsgrad_step(float* p, const float* g, float* m, float* v, float* vhat,

@@ -50,8 +50,49 @@ class SSIM():
 
 
 class Barron():
+    """nlt/losses.py:90-121 -- the adaptive robust loss with FIXED alpha = 1 (Charbonnier) and scale = 0.01 on a
+    5-level CDF 9/7 wavelet decomposition of the scaled-YUV residual; keep_batch -> (N,).  One fused CUDA call
+    produces the per-sample losses and d(sum_b loss_b * grad_scale)/d(pred) (nlt_barron_loss).
+
+    EXPERIMENTAL: the arithmetic is checked on the CPU against the reference-pinned oracle
+    (tests/test_barron_core.py), the CUDA kernels have not been validated on hardware yet, so the class only
+    constructs when NLT_EXPERIMENTAL_BARRON=1 (otherwise NotImplementedError, as before)."""
+    LOG_Z_ALPHA1 = 1.1854952323491930      # log Z(1) = log(2 e K_1(1)); the reference's spline agrees to 1e-10
+    SCALE = 0.01
+    LEVELS = 5
+
     def __init__(self, imw, imh):
-        raise NotImplementedError('barron: next row N1 (SURVEY.md 8f)')
+        import os
+        if os.environ.get('NLT_EXPERIMENTAL_BARRON', '0') != '1':
+            raise NotImplementedError('barron: next row N1 (SURVEY.md 8f); set NLT_EXPERIMENTAL_BARRON=1 for the '
+                                      'not-yet-validated CUDA implementation')
+        self.imw, self.imh = imw, imh
+        self._ws = None
+        self.d_pred = None
+        self.grad_scale = None
+
+    def __call__(self, gt, pred, keep_batch=False, weights=None):
+        lib = nat.lib()
+        B, H, W, C3 = pred.shape
+        if C3 != 3 or (H, W) != (self.imh, self.imw):
+            raise ValueError('expected [N, %d, %d, 3] images, got %s' % (self.imh, self.imw, tuple(pred.shape)))
+        need = lib.nlt_barron_loss_workspace_bytes(B, H, W, self.LEVELS)
+        if need < 0:
+            nat.check(-1)
+        if self._ws is None or self._ws.numel() * 4 < need or self._ws.device != pred.device:
+            self._ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=pred.device)
+        loss = torch.empty(B, dtype=torch.float32, device=pred.device)
+        want_grad = self.grad_scale is not None
+        self.d_pred = torch.empty_like(pred) if want_grad else None
+        scale = float(self.grad_scale) if want_grad else 0.0
+        if not keep_batch and want_grad:
+            scale = scale / B
+        if weights is not None:
+            weights = weights.to(pred.device, torch.float32).expand(B, H, W, 1).contiguous()
+        nat.check(lib.nlt_barron_loss(nat.ptr(pred), nat.ptr(gt), nat.ptr(weights), B, H, W, self.LEVELS, self.SCALE,
+                                      self.LOG_Z_ALPHA1, scale, nat.ptr(loss), nat.ptr(self.d_pred),
+                                      nat.ptr(self._ws), nat.stream()))
+        return loss if keep_batch else loss.mean()
 
 
 class LPIPS():

@@ -35,9 +35,13 @@ class Model:
         pairs = []
         for item in self.config.get('DEFAULT', 'loss').split(','):
             name, weight = self._parse_loss_and_weight(item)
-            if name not in _LOSS_TABLE:
+            if name == 'barron':     # needs the image size (nlt/models/nlt.py:78-79); experimental, see losses.Barron
+                loss = losses.Barron(self.config.getint('DEFAULT', 'imw'), self.config.getint('DEFAULT', 'imh'))
+            elif name in _LOSS_TABLE:
+                loss = _LOSS_TABLE[name]()
+            else:
                 raise NotImplementedError(name)
-            pairs.append((weight, _LOSS_TABLE[name]()))
+            pairs.append((weight, loss))
         return pairs
 
     @staticmethod

@@ -64,27 +64,6 @@ class Model(BaseModel):
         self._d_pred = None
         self._loss_grad_scale = None
 
-    def _init_loss(self):
-        """Overrides the base like the reference does (nlt.py:66-87)."""
-        wloss = []
-        loss_str = self.config.get('DEFAULT', 'loss')
-        for x in loss_str.split(','):
-            loss_name, weight = self._parse_loss_and_weight(x)
-            if loss_name == 'lpips':
-                loss = losses.LPIPS(per_ch=False)
-            elif loss_name == 'l1':
-                loss = losses.L1()
-            elif loss_name == 'l2':
-                loss = losses.L2()
-            elif loss_name == 'ssim':
-                loss = losses.SSIM(1 - 0)
-            elif loss_name == 'barron':
-                loss = losses.Barron(self.imw, self.imh)
-            else:
-                raise NotImplementedError(loss_name)
-            wloss.append((weight, loss))
-        return wloss
-
     # ------------------------------------------------------------------
     # parameters
     # ------------------------------------------------------------------

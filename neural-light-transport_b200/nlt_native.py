@@ -62,6 +62,9 @@ _SIGS = {
     'nlt_gconv_wgrad_workspace_bytes': (C.c_int64, [C.POINTER(GConvDesc)]),
     'nlt_gconv_wgrad': (C.c_int, [C.POINTER(GConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                   C.c_int64, C.c_void_p]),
+    'nlt_barron_loss_workspace_bytes': (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    'nlt_barron_loss': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'nlt_kmean_fwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     'nlt_kmean_bwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_float, C.c_void_p,
                                 C.c_int, C.c_void_p, C.c_void_p]),
