@@ -74,7 +74,8 @@ const char* nlt_version(void);
  * weight-gradient kernel where float4 access allows it [default], 0: flat-pixel form), "dconv_wide" (1: the
  * pixel x 16-outputs stencil kernel for the 16-channel stencils, 0: the tiled implicit-GEMM kernel),
  * "dconv_wide32" (EXPERIMENTAL, default 0 = off, not yet validated on hardware: the 32-output form of that kernel;
- * 1 = one pixel per thread, 2 = two), "dconv_wide_first" (EXPERIMENTAL routing, default 0: prefer the wide
+ * 1 = one pixel per thread, 2 = two), "dconv_wide8" (EXPERIMENTAL, default 0: the 8-output form, reached together
+ * with "dconv_wide_first"), "dconv_wide_first" (EXPERIMENTAL routing, default 0: prefer the wide
  * stencil kernel over the quad-per-thread one for 16 outputs with K <= 32).
  * Environment defaults: NLT_DISABLE_TC=1, NLT_DISABLE_TC_WGRAD=1, NLT_DCONV_WIDE=0|1. */
 int nlt_set_option(const char* name, int value);

@@ -678,16 +678,23 @@ int g_opt_dconv_wide = -1;   // -1: environment default (NLT_DCONV_WIDE), 0 off,
 
 int g_opt_dconv_wide32 = -1;   // EXPERIMENTAL (not validated on hardware yet): the 32-output form, default off
 
-static bool dconv_wide_common(const GConvK& k, const float* out, const float* mask_y, int cout, int kmax) {
+static bool dconv_wide_common(const GConvK& k, const float* out, const float* mask_y, int cout, int kmax, bool multi_seg) {
   if (k.d2s || k.M == 0) return false;
-  // routed shapes = the ones validated on hardware (tests/test_gpu_ops.py GEOMS + the model): ONE non-broadcast
-  // float4 source; the kernel itself is written for any segment list
-  if (k.Cout != cout || k.cout_true != k.Cout || k.nseg != 1 || k.seg[0].bcast) return false;
-  if (!k.seg[0].vec || k.seg[0].sub != nullptr) return false;
-  const int ktot = k.ay.nu * k.ax.nu * k.seg[0].C;
+  if (k.Cout != cout || k.cout_true != k.Cout) return false;
+  // the hardware-validated route (16 outputs) takes ONE non-broadcast float4 source; the experimental routes also
+  // take virtual concats (the kernel is written for any segment list)
+  if (!multi_seg && k.nseg != 1) return false;
+  int ctot = 0;
+  for (int s = 0; s < k.nseg; ++s) {
+    if (!k.seg[s].vec || k.seg[s].sub != nullptr || k.seg[s].bcast) return false;
+    ctot += k.seg[s].C;
+  }
+  const int ktot = k.ay.nu * k.ax.nu * ctot;
   if (ktot < 1 || ktot > kmax) return false;
   return aligned16(out) && (mask_y == nullptr || aligned16(mask_y));
 }
+
+int g_opt_dconv_wide8 = -1;    // EXPERIMENTAL: the 8-output form (up-conv levels 11-12), default off
 
 bool dconv_wide_applicable(const GConvK& k, const float* out, const float* mask_y) {
   if (g_opt_dconv_wide < 0) {
@@ -698,8 +705,13 @@ bool dconv_wide_applicable(const GConvK& k, const float* out, const float* mask_
     const char* e = getenv("NLT_DCONV_WIDE32");
     g_opt_dconv_wide32 = e ? atoi(e) : 0;
   }
-  if (g_opt_dconv_wide && dconv_wide_common(k, out, mask_y, 16, PW_KMAX)) return true;
-  return g_opt_dconv_wide32 > 0 && dconv_wide_common(k, out, mask_y, 32, DW_KMAX);
+  if (g_opt_dconv_wide8 < 0) {
+    const char* e = getenv("NLT_DCONV_WIDE8");
+    g_opt_dconv_wide8 = e ? atoi(e) : 0;
+  }
+  if (g_opt_dconv_wide && dconv_wide_common(k, out, mask_y, 16, PW_KMAX, false)) return true;
+  if (g_opt_dconv_wide32 > 0 && dconv_wide_common(k, out, mask_y, 32, DW_KMAX, true)) return true;
+  return g_opt_dconv_wide8 > 0 && dconv_wide_common(k, out, mask_y, 8, DW_KMAX, true);
 }
 
 int launch_dconv_wide(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
@@ -708,6 +720,9 @@ int launch_dconv_wide(const GConvK& k, const float* bias, int act, float beta, c
     constexpr int R = 2;
     const unsigned grid = (k.M + PW_THREADS * R - 1) / (PW_THREADS * R);
     dconv_wide_kernel<4, R, 3><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
+  } else if (k.Cout == 8) {                  // experimental: pixel x 8 outputs, four pixels per thread
+    const unsigned grid = (k.M + PW_THREADS * 4 - 1) / (PW_THREADS * 4);
+    dconv_wide_kernel<2, 4, 3><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
   } else if (g_opt_dconv_wide32 == 2) {      // two pixels per thread: 8 FMAs per weight LDS.128, ~2 CTAs per SM
     const unsigned grid = (k.M + PW_THREADS * 2 - 1) / (PW_THREADS * 2);
     dconv_wide_kernel<8, 2, 2><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);

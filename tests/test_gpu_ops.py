@@ -332,6 +332,41 @@ def test_experimental_wide_stencil_preferred_over_quad_kernel(kind, k, s, H, W, 
     assert rel(res[1][0], res[0][0]) <= 1e-5 and rel(res[1][1], res[0][1]) <= 1e-5
 
 
+@pytest.mark.skipif(not EXPERIMENTAL, reason='experimental kernels are opt-in: NLT_TEST_EXPERIMENTAL=1')
+@pytest.mark.parametrize('kind,k,s,H,W,segc,cout', [('conv', 2, 1, 16, 24, [8], 8), ('deconv', 2, 1, 12, 20, [8], 8),
+                                                    ('conv', 2, 2, 16, 16, [4], 8), ('conv', 2, 2, 16, 16, [16, 16], 32),
+                                                    ('conv', 2, 1, 9, 13, [8, 4], 8)])
+def test_experimental_wide_stencil_8_outputs_and_virtual_concats(kind, k, s, H, W, segc, cout):
+    """EXPERIMENTAL: the 8-output form (options "dconv_wide8" + "dconv_wide_first") and virtual-concat sources of
+    the experimental wide routes, against the default routing."""
+    engine, nat = _mods()
+    dev = torch.device('cuda')
+    torch.manual_seed(35)
+    xs = [torch.randn(3, H, W, c, device=dev) for c in segc]
+    res = {}
+    nat.set_option('tc', 0)
+    try:
+        for m in (1, 0):
+            for opt in ('dconv_wide8', 'dconv_wide32', 'dconv_wide_first'):
+                nat.set_option(opt, m)
+            L = engine.ConvLayer(kind, k, s, cout, 'leakyrelu')
+            L.build(sum(segc), dev, torch.Generator().manual_seed(1))
+            acts = [engine.Act(x, act='leakyrelu', needs_grad=True) for x in xs]
+            tape = engine.Tape()
+            y = L.forward([engine.Seg(a) for a in acts], tape)
+            torch.manual_seed(5)
+            y.grad = torch.randn_like(y.t)
+            tape.backward()
+            res[m] = [y.t.clone()] + [a.grad.clone() for a in acts]
+    finally:
+        for opt in ('dconv_wide8', 'dconv_wide32', 'dconv_wide_first'):
+            nat.set_option(opt, 0)
+        nat.set_option('tc', 1)
+    rel = lambda p, q: float((p.double() - q.double()).norm() / q.double().norm())
+    for p, q in zip(res[1], res[0]):
+        assert rel(p, q) <= 1e-5
+
+
 def test_tensor_core_path_is_taken_and_matches_fp32_path():
     """Eligible shapes must run on the tcgen05 kernel (launch counter moves) and agree with the
     fp32-FMA kernel of the same library to 3xTF32 accuracy (<= 4e-6 relative to the output scale)."""
