@@ -299,3 +299,17 @@ def test_barron_entry_point_host_side_and_gating(monkeypatch):
     monkeypatch.setenv('NLT_EXPERIMENTAL_BARRON', '1')
     b = losses.Barron(64, 48)
     assert (b.imw, b.imh) == (64, 48) and abs(b.LOG_Z_ALPHA1 - 1.185495232349193) < 1e-12
+
+
+def test_opbench_layer_table_matches_the_network_wiring():
+    """tools/opbench.py replays the two-stream wiring: 39 convs, concat widths 1024 / 640 / ... / 36."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('opbench', os.path.join(ROOT, 'tools', 'opbench.py'))
+    ob = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ob)
+    rows = {r[0]: r for r in ob.layer_table(uv=512, batch=1)}
+    assert len(rows) == 39
+    cin = {name: sum(r[5]) for name, r in rows.items()}
+    assert [cin['query.%d.0' % i] for i in range(7, 14)] == [1024, 640, 320, 160, 80, 40, 36]
+    assert cin['query.1.0'] == 32 and cin['obs.1.0'] == 16 and cin['query.6.0'] == 512
+    assert rows['query.7.0'][4] == 8 and rows['query.13.0'][4] == 512 and rows['query.13.0'][6] == 3
