@@ -73,10 +73,10 @@ const char* nlt_version(void);
  * "tc_wgrad" (same for the weight-gradient kernel), "wgrad_rows" (1: row-run form of the warp-stream
  * weight-gradient kernel where float4 access allows it [default], 0: flat-pixel form), "dconv_wide" (1: the
  * pixel x 16-outputs stencil kernel for the 16-channel stencils, 0: the tiled implicit-GEMM kernel),
- * "dconv_wide32" (EXPERIMENTAL, default 0 = off, not yet validated on hardware: the 32-output form of that kernel;
- * 1 = one pixel per thread, 2 = two), "dconv_wide8" (EXPERIMENTAL, default 0: the 8-output form, reached together
- * with "dconv_wide_first"), "dconv_wide_first" (EXPERIMENTAL routing, default 0: prefer the wide
- * stencil kernel over the quad-per-thread one for 16 outputs with K <= 32).
+ * "dconv_wide32" (default 0 = off: the 32-output form of that kernel, validated but not faster;
+ * 1 = one pixel per thread, 2 = two), "dconv_wide8" (default 1: the 8-output form, reached together
+ * with "dconv_wide_first"), "dconv_wide_first" (routing, default 1: prefer the wide
+ * stencil kernel over the quad-per-thread one for 16 / 8 outputs with K <= 32).
  * Environment defaults: NLT_DISABLE_TC=1, NLT_DISABLE_TC_WGRAD=1, NLT_DCONV_WIDE=0|1. */
 int nlt_set_option(const char* name, int value);
 const char* nlt_last_error(void);
@@ -177,8 +177,8 @@ int nlt_l2_loss(const float* pred, const float* gt, int32_t B,
                 int64_t per_sample, float loss_scale, float* loss,
                 float* d_pred, void* workspace, void* stream);
 
-/* EXPERIMENTAL (arithmetic checked on the CPU against the pinned oracle, kernels not yet
- * validated on hardware): losses.Barron with keep_batch (nlt/losses.py:90-121) fused with its gradient.
+/* SURVEY 8f row N1 (checked on the CPU and on hardware against the oracle pinned to the reference's wavelet
+ * fixtures): losses.Barron with keep_batch (nlt/losses.py:90-121) fused with its gradient.
  *   r = (gt - pred) [* alpha]  ->  volume-preserving YUV  ->  `levels`-level CDF 9/7 analysis (reflecting
  *   boundaries)  ->  nll = sqrt((w/scale)^2 + 1) - 1 + log(scale) + log_z per coefficient
  *   loss[b] = mean_{h,w,c} nll ;  d_pred = d(sum_b loss[b] * loss_scale) / d(pred)
@@ -194,6 +194,21 @@ int nlt_barron_loss(const float* pred, const float* gt, const float* alpha, int3
 int nlt_amsgrad_step(float* p, const float* g, float* m, float* v, float* vhat,
                      int64_t n, int32_t step, float lr, float beta1,
                      float beta2, float eps, float grad_scale, void* stream);
+
+/* acc[i] += sum_k in[k*per_sample + i]  -- running per-level sum of the observation features over the samples
+ * of a batch (the concat + tf.reduce_mean(axis=0) of nlt/nlt_test.py:114-124 without holding every sample). */
+int nlt_ksum_acc(const float* in, int32_t K, int64_t per_sample, float* acc, void* stream);
+/* x *= a   (the 1/count of that mean) */
+int nlt_scale(float* x, int64_t n, float a, void* stream);
+/* out = a * b elementwise (alpha_blend of the resized coverage, nlt/util/img.py:74-89, models/nlt.py:132-133) */
+int nlt_mul(const float* a, const float* b, int64_t n, float* out, void* stream);
+
+/* The same update with the 1-based step counter kept ON THE DEVICE (int32 *step_dev holds the number of updates
+ * already applied; the call advances it by one first), so the optimiser launch can be part of a captured CUDA
+ * graph of the whole train step (nlt/trainvali.py:267-290 runs as one tf.function). */
+int nlt_amsgrad_step_dev(float* p, const float* g, float* m, float* v, float* vhat,
+                         int64_t n, int32_t* step_dev, float lr, float beta1,
+                         float beta2, float eps, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -268,6 +268,49 @@ __global__ void amsgrad_kernel(float* __restrict__ p, const float* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------
+// small streaming helpers of the test-time feature cache (nlt/nlt_test.py:97-127) and the resize branch
+// ---------------------------------------------------------------------------
+__global__ void ksum_acc_kernel(const float* __restrict__ in, int K, size_t per, float* __restrict__ acc) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (size_t)gridDim.x * blockDim.x) {
+    float s = acc[i];
+    for (int k = 0; k < K; ++k) s += __ldg(in + (size_t)k * per + i);   // fixed order: deterministic
+    acc[i] = s;
+  }
+}
+__global__ void scale_kernel(float* __restrict__ x, size_t n, float a) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] *= a;
+}
+__global__ void mul_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n, float* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __ldg(a + i) * __ldg(b + i);
+}
+
+// Same update with the step counter ON THE DEVICE, so that the optimiser launch can live inside a captured CUDA
+// graph (a host-computed bias-corrected learning rate would be frozen into the graph at capture time).
+// `step` holds the number of updates applied so far; it is advanced by amsgrad_step_inc_kernel right before.
+__global__ void amsgrad_step_inc_kernel(int* __restrict__ step) { *step += 1; }
+
+__global__ void amsgrad_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                   float* __restrict__ v, float* __restrict__ vhat, size_t n,
+                                   const int* __restrict__ step, float lr, float b1, float b2, float eps, float gscale) {
+  __shared__ float lr_s;
+  if (threadIdx.x == 0) {
+    const int t = *step;
+    lr_s = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
+  }
+  __syncthreads();
+  const float lr_t = lr_s;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float mi = m[i] + (gi - m[i]) * (1.f - b1);
+    const float vi = v[i] + (gi * gi - v[i]) * (1.f - b2);
+    const float vh = fmaxf(vhat[i], vi);
+    m[i] = mi; v[i] = vi; vhat[i] = vh;
+    p[i] = p[i] - lr_t * mi / (sqrtf(vh) + eps);
+  }
+}
+
 }  // namespace nlt
 
 using namespace nlt;
@@ -373,6 +416,39 @@ int nlt_amsgrad_step(float* p, const float* g, float* m, float* v, float* vhat, 
   amsgrad_kernel<<<grid_for((size_t)n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, vhat, (size_t)n, (float)lr_t,
                                                                               beta1, beta2, eps, grad_scale);
   NLT_CUDA_LAUNCH_CHECK("amsgrad_kernel");
+  return NLT_OK;
+}
+
+int nlt_ksum_acc(const float* in, int32_t K, int64_t per_sample, float* acc, void* stream) {
+  NLT_CHECK_ARG(in && acc && K > 0 && per_sample > 0, "ksum_acc: bad argument");
+  ksum_acc_kernel<<<grid_for((size_t)per_sample, 256), 256, 0, (cudaStream_t)stream>>>(in, K, (size_t)per_sample, acc);
+  NLT_CUDA_LAUNCH_CHECK("ksum_acc_kernel");
+  return NLT_OK;
+}
+
+int nlt_scale(float* x, int64_t n, float a, void* stream) {
+  NLT_CHECK_ARG(x && n > 0, "scale: bad argument");
+  scale_kernel<<<grid_for((size_t)n, 256), 256, 0, (cudaStream_t)stream>>>(x, (size_t)n, a);
+  NLT_CUDA_LAUNCH_CHECK("scale_kernel");
+  return NLT_OK;
+}
+
+int nlt_mul(const float* a, const float* b, int64_t n, float* out, void* stream) {
+  NLT_CHECK_ARG(a && b && out && n > 0, "mul: bad argument");
+  mul_kernel<<<grid_for((size_t)n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, (size_t)n, out);
+  NLT_CUDA_LAUNCH_CHECK("mul_kernel");
+  return NLT_OK;
+}
+
+int nlt_amsgrad_step_dev(float* p, const float* g, float* m, float* v, float* vhat, int64_t n, int32_t* step_dev,
+                         float lr, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  NLT_CHECK_ARG(p && g && m && v && vhat && step_dev && n > 0, "amsgrad_dev: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  amsgrad_step_inc_kernel<<<1, 1, 0, st>>>(step_dev);
+  NLT_CUDA_LAUNCH_CHECK("amsgrad_step_inc_kernel");
+  amsgrad_dev_kernel<<<grid_for((size_t)n, 256), 256, 0, st>>>(p, g, m, v, vhat, (size_t)n, step_dev, lr, beta1, beta2,
+                                                               eps, grad_scale);
+  NLT_CUDA_LAUNCH_CHECK("amsgrad_dev_kernel");
   return NLT_OK;
 }
 

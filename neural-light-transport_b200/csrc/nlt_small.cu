@@ -694,7 +694,7 @@ static bool dconv_wide_common(const GConvK& k, const float* out, const float* ma
   return aligned16(out) && (mask_y == nullptr || aligned16(mask_y));
 }
 
-int g_opt_dconv_wide8 = -1;    // EXPERIMENTAL: the 8-output form (up-conv levels 11-12), default off
+int g_opt_dconv_wide8 = -1;    // the 8-output form (up-conv levels 11-12); default on (validated in round 2: profiles/r2_a_*)
 
 bool dconv_wide_applicable(const GConvK& k, const float* out, const float* mask_y) {
   if (g_opt_dconv_wide < 0) {
@@ -707,7 +707,7 @@ bool dconv_wide_applicable(const GConvK& k, const float* out, const float* mask_
   }
   if (g_opt_dconv_wide8 < 0) {
     const char* e = getenv("NLT_DCONV_WIDE8");
-    g_opt_dconv_wide8 = e ? atoi(e) : 0;
+    g_opt_dconv_wide8 = e ? atoi(e) : 1;
   }
   if (g_opt_dconv_wide && dconv_wide_common(k, out, mask_y, 16, PW_KMAX, false)) return true;
   if (g_opt_dconv_wide32 > 0 && dconv_wide_common(k, out, mask_y, 32, DW_KMAX, true)) return true;

@@ -96,11 +96,13 @@ class Tape:
     def backward(self):
         for fn in reversed(self.ops):
             fn()
+        if USE_SIDE_STREAM and torch.cuda.is_available():
+            # join the weight-gradient branch BEFORE the closures (and with them the activations the side stream
+            # may still be reading) are released
+            torch.cuda.current_stream().wait_stream(side_stream())
         self.ops = []
         while _PARKED:                      # leaves whose parked contribution nobody took along
             settle(_PARKED.pop())
-        if USE_SIDE_STREAM and torch.cuda.is_available():
-            torch.cuda.current_stream().wait_stream(side_stream())   # join the weight-gradient branch
 
 
 class Workspace:
@@ -117,6 +119,28 @@ class Workspace:
 
 _WS = Workspace()
 _WS_SIDE = Workspace()       # scratch of the weight-gradient stream
+
+
+class use_workspaces:
+    """Context manager: route the scratch requests of every op issued inside it to the given Workspace pair.
+    A captured CUDA graph bakes the raw scratch addresses into its kernel arguments (packed hi/lo weight planes,
+    TMA maps, wgrad partials), so a graph must own its scratch: trainvali.GraphedTrainStep warms up and captures
+    inside `use_workspaces(own_main, own_side)` and keeps both objects alive as long as the graph.  A later eager
+    call that needs a larger scratch grows the module-level pair only, never the graph's."""
+
+    def __init__(self, main, side):
+        self.pair = (main, side)
+
+    def __enter__(self):
+        global _WS, _WS_SIDE
+        self.saved = (_WS, _WS_SIDE)
+        _WS, _WS_SIDE = self.pair
+        return self
+
+    def __exit__(self, *exc):
+        global _WS, _WS_SIDE
+        _WS, _WS_SIDE = self.saved
+        return False
 _SIDE = {}                   # device index -> side stream
 
 
@@ -131,6 +155,9 @@ def side_stream():
 
 
 USE_SIDE_STREAM = True
+# called as WGRAD_HOOK(layer) right after a layer's weight-gradient launch has been issued (on the side stream when
+# USE_SIDE_STREAM): trainvali.GradReducer starts the early part of the gradient all-reduce from it
+WGRAD_HOOK = None
 
 
 def gconv_fwd(d, bias, act, beta, mask, mask_act, out):
@@ -350,6 +377,8 @@ class ConvLayer:
                 C.byref(d), nat.ptr(dz), nat.ptr(self.gkernel), nat.ptr(self.gbias), acc, nat.ptr(ws),
                 ws.numel() * 4, nat.stream())))
         self.grad_written = True
+        if WGRAD_HOOK is not None:
+            WGRAD_HOOK(self)
         # input gradients, one adjoint launch per differentiable segment
         pointwise = self.kind == 'conv' and self.k == 1 and self.s == 1 and self.cout <= 4
         coff = 0
@@ -413,30 +442,57 @@ def kmean(obs_y, K, tape=None, weights=None):
 
 class ParamBucket:
     """All trainable parameters of a model in ONE contiguous fp32 buffer (and
-    one gradient buffer), so that the data-parallel step is a single
-    all-reduce and a single fused AMSGrad launch (nlt/trainvali.py:279-280)."""
+    one gradient buffer), so that the data-parallel step is a single fused
+    AMSGrad launch and at most two all-reduce calls (nlt/trainvali.py:279-280).
 
-    def __init__(self, layers, device):
+    `layout`: order of the layers inside the flat buffers (default: as given).  models/nlt.py passes the order in
+    which the backward pass PRODUCES the weight gradients (decoder top-down, then encoder levels bottom-up), so the
+    gradient buffer fills front to back and its parameter-heavy head (the deep levels) can be all-reduced while the
+    full-resolution levels are still running.  `grad` carries LOSS_SLOTS extra floats behind the parameters: the
+    per-replica loss rides on the same collective (trainvali.py:317 is a second reduce in the reference)."""
+    LOSS_SLOTS = 4
+
+    def __init__(self, layers, device, layout=None):
         self.layers = list(layers)
+        order = list(range(len(self.layers))) if layout is None else list(layout)
+        assert sorted(order) == list(range(len(self.layers)))
         n = 0
-        self.slices = []
-        for L in self.layers:
+        slices = [None] * len(self.layers)
+        self.layout_ends = []                # (layer, end offset) in layout order
+        for li in order:
+            L = self.layers[li]
             assert L.built
             ks, bs = L.kernel.numel(), L.bias.numel()
             n_al = (n + 3) // 4 * 4          # keep every kernel 16B aligned
-            self.slices.append((n_al, ks, n_al + ks, bs))
+            slices[li] = (n_al, ks, n_al + ks, bs)
             n = n_al + ks + bs
+            self.layout_ends.append((L, (n + 3) // 4 * 4))
+        self.slices = slices
         self.n = (n + 3) // 4 * 4
         self.flat = torch.zeros(self.n, dtype=torch.float32, device=device)
-        self.grad = torch.zeros(self.n, dtype=torch.float32, device=device)
+        self._grad_all = torch.zeros(self.n + self.LOSS_SLOTS, dtype=torch.float32, device=device)
+        self.grad = self._grad_all[:self.n]
+        self.loss_slot = self._grad_all[self.n:self.n + 1]
         for L, (ko, ks, bo, bs) in zip(self.layers, self.slices):
             kshape, bshape = L.kernel.shape, L.bias.shape
             self.flat[ko:ko + ks].copy_(L.kernel.reshape(-1))
             self.flat[bo:bo + bs].copy_(L.bias.reshape(-1))
             L.kernel = self.flat[ko:ko + ks].view(kshape)
             L.bias = self.flat[bo:bo + bs].view(bshape)
-            L.gkernel = self.grad[ko:ko + ks].view(kshape)
-            L.gbias = self.grad[bo:bo + bs].view(bshape)
+            L.gkernel = self._grad_all[ko:ko + ks].view(kshape)
+            L.gbias = self._grad_all[bo:bo + bs].view(bshape)
+
+    def split_point(self, frac=0.9):
+        """(layer, offset): the first layer boundary of the layout at which `frac` of the parameters lie in front;
+        the collective of grad[:offset] may start as soon as that layer's weight gradient has been issued."""
+        for L, end in self.layout_ends[:-1]:
+            if end >= frac * self.n:
+                return L, end
+        return None, 0
+
+    def grad_with_loss(self):
+        """grad ++ loss slot: the buffer of the final collective."""
+        return self._grad_all[:self.n + 1]
 
     def variables(self):
         out = []

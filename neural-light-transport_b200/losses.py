@@ -1,8 +1,8 @@
 """Losses with the reference's class names (nlt/losses.py).
 
-Only L2 is on the accelerated hot path (it is the loss used
-when timing the path); it is fused with its own gradient in one CUDA pass.
-Barron / LPIPS are the "next" row N1 and raise NotImplementedError.
+L2 (the loss used when timing the path) and Barron (row N1: the
+first term of the shipped `loss = barron,1e+0lpips`) are each fused with their own
+gradient in CUDA.  LPIPS (the second term) raises NotImplementedError.
 """
 import torch
 
@@ -54,18 +54,13 @@ class Barron():
     5-level CDF 9/7 wavelet decomposition of the scaled-YUV residual; keep_batch -> (N,).  One fused CUDA call
     produces the per-sample losses and d(sum_b loss_b * grad_scale)/d(pred) (nlt_barron_loss).
 
-    EXPERIMENTAL: the arithmetic is checked on the CPU against the reference-pinned oracle
-    (tests/test_barron_core.py), the CUDA kernels have not been validated on hardware yet, so the class only
-    constructs when NLT_EXPERIMENTAL_BARRON=1 (otherwise NotImplementedError, as before)."""
+    The arithmetic is checked on the CPU (tests/test_barron_core.py) and the kernels on hardware
+    (tests/test_gpu_barron.py) against the oracle that is pinned to the reference's own wavelet fixtures."""
     LOG_Z_ALPHA1 = 1.1854952323491930      # log Z(1) = log(2 e K_1(1)); the reference's spline agrees to 1e-10
     SCALE = 0.01
     LEVELS = 5
 
     def __init__(self, imw, imh):
-        import os
-        if os.environ.get('NLT_EXPERIMENTAL_BARRON', '0') != '1':
-            raise NotImplementedError('barron: next row N1 (SURVEY.md 8f); set NLT_EXPERIMENTAL_BARRON=1 for the '
-                                      'not-yet-validated CUDA implementation')
         self.imw, self.imh = imw, imh
         self._ws = None
         self.d_pred = None

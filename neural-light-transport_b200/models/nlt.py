@@ -93,7 +93,16 @@ class Model(BaseModel):
         convs = q.conv_layers()
         for blk in o.layers:
             convs += blk.convs
-        self._bucket = ParamBucket(convs, self.device)
+        # flat layout = the order in which backward() produces the weight gradients: decoder blocks top-down, then
+        # per encoder level (bottom-up) the query block followed by the observation block, second conv first
+        index = {id(c): i for i, c in enumerate(convs)}
+        produced = []
+        n_q = len(q.layers)
+        for li in range(n_q - 1, -1, -1):
+            produced += [index[id(c)] for c in reversed(q.layers[li].convs)]
+            if q.is_contracting[li]:
+                produced += [index[id(c)] for c in reversed(o.layers[li].convs)]
+        self._bucket = ParamBucket(convs, self.device, layout=produced)
         for name, c in self.named_convs():   # profiler labels: 'query.1.0 conv2x2/s2 32->16'
             c.name = '%s %s%dx%d/s%d %d->%d' % (name, c.kind, c.k, c.k, c.s, c.cin, c.cout)
 
@@ -114,6 +123,10 @@ class Model(BaseModel):
     @property
     def flat_grads(self):
         return self._bucket.grad
+
+    @property
+    def bucket(self):
+        return self._bucket
 
     def named_convs(self):
         """('query.3.0', ConvLayer) in registration order."""
@@ -191,7 +204,9 @@ class Model(BaseModel):
                 return y
             pred_c, base_c = rs(pred_c), rs(base_c)
             if want_gt:
-                gt_c = rgb_camspc * rs(fg_c)     # alpha_blend (nlt.py:132-133)
+                fg_r = rs(fg_c)
+                gt_c = new(B, self.imh, self.imw, 3)     # alpha_blend (nlt.py:132-133)
+                nat.check(lib.nlt_mul(nat.ptr(rgb_camspc), nat.ptr(fg_r), gt_c.numel(), nat.ptr(gt_c), nat.stream()))
         if train:
             def tail_bwd():
                 d = self._d_pred

@@ -1,6 +1,5 @@
-"""EXPERIMENTAL (opt-in: NLT_TEST_EXPERIMENTAL=1): the CUDA Barron-loss entry point nlt_barron_loss against the
-reference-pinned oracle (oracle/barron_oracle.py).  The arithmetic shared with these kernels is already checked on
-the CPU (tests/test_barron_core.py); this is the hardware validation that is still pending."""
+"""The CUDA Barron-loss entry point nlt_barron_loss against the reference-pinned oracle (oracle/barron_oracle.py).
+The arithmetic shared with these kernels is also checked on the CPU (tests/test_barron_core.py)."""
 import math
 import os
 
@@ -10,9 +9,7 @@ import torch
 
 from oracle import barron_oracle as B
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('NLT_TEST_EXPERIMENTAL', '0') != '1',
-                                 reason='experimental kernels are opt-in: NLT_TEST_EXPERIMENTAL=1')]
+pytestmark = [pytest.mark.gpu]
 
 LOG_Z = 1.185495232349193
 

@@ -262,16 +262,12 @@ def test_final_conv_input_gradient_rides_on_down_conv_dgrad(H, W, c_skip, c_othe
         assert res[True]['launches'] == res[False]['launches'] - 1, (res[True]['launches'], res[False]['launches'])
 
 
-EXPERIMENTAL = os.environ.get('NLT_TEST_EXPERIMENTAL', '0') == '1'
-
-
-@pytest.mark.skipif(not EXPERIMENTAL, reason='experimental kernels are opt-in: NLT_TEST_EXPERIMENTAL=1')
 @pytest.mark.parametrize('mode', [1, 2])
 @pytest.mark.parametrize('kind,k,s,H,W,cin', [('conv', 2, 1, 16, 24, 32), ('conv', 2, 2, 32, 16, 16),
                                               ('conv', 2, 2, 16, 16, 32), ('deconv', 2, 1, 12, 20, 32),
                                               ('conv', 3, 1, 9, 11, 12)])
-def test_experimental_wide_stencil_32_outputs(kind, k, s, H, W, cin, mode):
-    """EXPERIMENTAL (not part of the validated build): the 32-output form of the wide stencil kernel (option
+def test_wide_stencil_32_outputs(kind, k, s, H, W, cin, mode):
+    """The 32-output form of the wide stencil kernel (option
     "dconv_wide32": 1 = one pixel per thread, 2 = two) against the default routing, fp32 kernels only."""
     engine, nat = _mods()
     dev = torch.device('cuda')
@@ -301,11 +297,10 @@ def test_experimental_wide_stencil_32_outputs(kind, k, s, H, W, cin, mode):
     assert torch.equal(res[mode][2], res[0][2])          # weight gradients do not go through this kernel
 
 
-@pytest.mark.skipif(not EXPERIMENTAL, reason='experimental routing is opt-in: NLT_TEST_EXPERIMENTAL=1')
 @pytest.mark.parametrize('kind,k,s,H,W,cin', [('conv', 2, 2, 16, 24, 4), ('conv', 2, 2, 32, 16, 8), ('conv', 2, 1, 9, 16, 8),
                                               ('deconv', 2, 1, 12, 8, 8)])
-def test_experimental_wide_stencil_preferred_over_quad_kernel(kind, k, s, H, W, cin):
-    """EXPERIMENTAL routing (option "dconv_wide_first"): 16 outputs from K <= 32 through the validated wide
+def test_wide_stencil_preferred_over_quad_kernel(kind, k, s, H, W, cin):
+    """Routing option "dconv_wide_first" (default on since round 2): 16 outputs from K <= 32 through the validated wide
     stencil kernel instead of the quad-per-thread kernel -- same results."""
     engine, nat = _mods()
     dev = torch.device('cuda')
@@ -326,19 +321,18 @@ def test_experimental_wide_stencil_preferred_over_quad_kernel(kind, k, s, H, W, 
             tape.backward()
             res[m] = (y.t.clone(), a.grad.clone())
     finally:
-        nat.set_option('dconv_wide_first', 0)
+        nat.set_option('dconv_wide_first', 1)      # library default
         nat.set_option('tc', 1)
     rel = lambda p, q: float((p.double() - q.double()).norm() / q.double().norm())
     assert rel(res[1][0], res[0][0]) <= 1e-5 and rel(res[1][1], res[0][1]) <= 1e-5
 
 
-@pytest.mark.skipif(not EXPERIMENTAL, reason='experimental kernels are opt-in: NLT_TEST_EXPERIMENTAL=1')
 @pytest.mark.parametrize('kind,k,s,H,W,segc,cout', [('conv', 2, 1, 16, 24, [8], 8), ('deconv', 2, 1, 12, 20, [8], 8),
                                                     ('conv', 2, 2, 16, 16, [4], 8), ('conv', 2, 2, 16, 16, [16, 16], 32),
                                                     ('conv', 2, 1, 9, 13, [8, 4], 8)])
-def test_experimental_wide_stencil_8_outputs_and_virtual_concats(kind, k, s, H, W, segc, cout):
-    """EXPERIMENTAL: the 8-output form (options "dconv_wide8" + "dconv_wide_first") and virtual-concat sources of
-    the experimental wide routes, against the default routing."""
+def test_wide_stencil_8_outputs_and_virtual_concats(kind, k, s, H, W, segc, cout):
+    """The 8-output form (options "dconv_wide8" + "dconv_wide_first") and virtual-concat sources of
+    the wide routes, against the tiled / quad-per-thread routing."""
     engine, nat = _mods()
     dev = torch.device('cuda')
     torch.manual_seed(35)
@@ -359,8 +353,8 @@ def test_experimental_wide_stencil_8_outputs_and_virtual_concats(kind, k, s, H, 
             tape.backward()
             res[m] = [y.t.clone()] + [a.grad.clone() for a in acts]
     finally:
-        for opt in ('dconv_wide8', 'dconv_wide32', 'dconv_wide_first'):
-            nat.set_option(opt, 0)
+        for opt, dflt in (('dconv_wide8', 1), ('dconv_wide32', 0), ('dconv_wide_first', 1)):
+            nat.set_option(opt, dflt)                 # library defaults
         nat.set_option('tc', 1)
     rel = lambda p, q: float((p.double() - q.double()).norm() / q.double().norm())
     for p, q in zip(res[1], res[0]):

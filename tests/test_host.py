@@ -285,18 +285,13 @@ def test_vis_batch_outputs_and_psnr(tmp_path):
 
 
 def test_barron_entry_point_host_side_and_gating(monkeypatch):
-    """nlt_barron_loss is experimental: the workspace query is pure host code, and losses.Barron only constructs
-    when NLT_EXPERIMENTAL_BARRON=1."""
+    """The workspace query of nlt_barron_loss is pure host code; losses.Barron constructs without a GPU."""
     import nlt_native as nat
     import losses
     lib = nat.lib()
     assert lib.nlt_barron_loss_workspace_bytes(1, 8, 8, 5) < 0           # 8 x 8 supports at most 3 levels
     assert lib.nlt_barron_loss_workspace_bytes(2, 64, 48, 5) > 4 * 2 * 3 * 64 * 48 * 2
     assert lib.nlt_barron_loss_workspace_bytes(0, 64, 64, 5) < 0
-    monkeypatch.delenv('NLT_EXPERIMENTAL_BARRON', raising=False)
-    with pytest.raises(NotImplementedError):
-        losses.Barron(64, 64)
-    monkeypatch.setenv('NLT_EXPERIMENTAL_BARRON', '1')
     b = losses.Barron(64, 48)
     assert (b.imw, b.imh) == (64, 48) and abs(b.LOG_Z_ALPHA1 - 1.185495232349193) < 1e-12
 
