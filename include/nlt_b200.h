@@ -160,6 +160,15 @@ int nlt_uv2cam_bwd(const float* d_pred_camspc, const float* warp, int32_t B,
                    int32_t H, int32_t W, int32_t ih, int32_t iw,
                    float* d_net_out, void* stream);
 
+/* The same gradient, bit-reproducible: contributions are accumulated as 64-bit fixed-point integers (order
+ * independent), scaled by the largest |d_pred_camspc| of the call, then converted to fp32 once.
+ * workspace: >= nlt_uv2cam_bwd_workspace_bytes(), 8-byte aligned, ZERO-FILLED by the caller before the first call;
+ * every call leaves it zero-filled again (the conversion pass clears what the scatter touched). */
+int64_t nlt_uv2cam_bwd_workspace_bytes(int32_t B, int32_t H, int32_t W);
+int nlt_uv2cam_bwd_det(const float* d_pred_camspc, const float* warp, int32_t B,
+                       int32_t H, int32_t W, int32_t ih, int32_t iw,
+                       float* d_net_out, void* workspace, void* stream);
+
 /* tf.image.resize bilinear, half-pixel centres (nlt/util/img.py:113-116) */
 int nlt_resize_bilinear_fwd(const float* in, int32_t B, int32_t H, int32_t W,
                             int32_t C, int32_t oh, int32_t ow, float* out,
@@ -194,6 +203,11 @@ int nlt_barron_loss(const float* pred, const float* gt, const float* alpha, int3
 int nlt_amsgrad_step(float* p, const float* g, float* m, float* v, float* vhat,
                      int64_t n, int32_t step, float lr, float beta1,
                      float beta2, float eps, float grad_scale, void* stream);
+
+/* Diagnostic (tests/test_gpu_tcts.py): out[128 x bn] = A[128 x 16] * B[bn x 16]^T through the TS form of
+ * tcgen05.mma (A operand written to tensor memory with tcgen05.st, B in shared memory); bn = 16 or 32.
+ * A is fed unrounded, so the result shows how the tensor core treats the low 13 mantissa bits of fp32 inputs. */
+int nlt_debug_tcts_probe(const float* A, const float* B, int32_t bn, float* out, void* stream);
 
 /* acc[i] += sum_k in[k*per_sample + i]  -- running per-level sum of the observation features over the samples
  * of a batch (the concat + tf.reduce_mean(axis=0) of nlt/nlt_test.py:114-124 without holding every sample). */

@@ -162,6 +162,14 @@ bool wgrad_tpp_applicable(const GConvK& k);
 size_t wgrad_tpp_ws_floats(const GConvK& k);
 int launch_wgrad_tpp(const GConvK& k, const float* G, float* ws, WgradK* w, size_t* KD_pad, cudaStream_t st);
 
+// wide pointwise conv into 16 channels (nlt_pwx.cu): level 0 of the 64-channel query stack
+extern int g_opt_pwx;
+bool pwx_fwd_applicable(const GConvK& k, float beta, const float* mask_y, const float* out);
+int launch_pwx_fwd(const GConvK& k, const float* bias, int act, float* out, cudaStream_t st);
+bool pwx_wgrad_applicable(const GConvK& k, const float* G);
+size_t pwx_wgrad_ws_floats(const GConvK& k);
+int launch_pwx_wgrad(const GConvK& k, const float* G, float* ws, WgradK* w, size_t* KD_pad, cudaStream_t st);
+
 // tcgen05 tensor-core path (nlt_tc.cu)
 extern unsigned long long g_tc_launches;
 bool tc_applicable(const GConvK& k);

@@ -686,6 +686,7 @@ int nlt_set_option(const char* name, int value) {
   if (strcmp(name, "tc") == 0) { g_opt_tc = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "tc_wgrad") == 0) { g_opt_tc_wgrad = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "wgrad_rows") == 0) { nlt::g_opt_wgrad_rows = value ? 1 : 0; return NLT_OK; }
+  if (strcmp(name, "pwx") == 0) { nlt::g_opt_pwx = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "dconv_wide") == 0) { nlt::g_opt_dconv_wide = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "dconv_wide32") == 0) { nlt::g_opt_dconv_wide32 = value; return NLT_OK; }
   if (strcmp(name, "dconv_wide8") == 0) { nlt::g_opt_dconv_wide8 = value; return NLT_OK; }
@@ -717,7 +718,8 @@ int nlt_gconv_fwd_ws(const nlt_gconv_desc* d, const float* bias, int act, float 
   for (int i = 0; i < np; ++i) {
     const GConvK& k = ph[i];
     if (k.M == 0) continue;
-    if (pw_conv_applicable(k)) rc = launch_pw_conv(k, bias, act, beta, mask_y, mask_act, out, st);
+    if (pwx_fwd_applicable(k, beta, mask_y, out)) rc = launch_pwx_fwd(k, bias, act, out, st);
+    else if (pw_conv_applicable(k)) rc = launch_pw_conv(k, bias, act, beta, mask_y, mask_act, out, st);
     // option "dconv_wide_first" (default on; measured -0.4 ms per cfg2 step together with the 8-output form,
     // profiles/r2_a_*): prefer the wide stencil kernel over the quad-per-thread one where both apply
     // (16 / 8 outputs, K <= 32: the up-conv input gradients of levels 11-12)
@@ -783,7 +785,8 @@ int64_t nlt_gconv_wgrad_workspace_bytes(const nlt_gconv_desc* d) {
   size_t mx = 0;
   for (int i = 0; i < np; ++i) {
     if (ph[i].M == 0) continue;
-    size_t need = use_tc_wgrad(ph[i]) ? tc_wgrad_ws_floats(ph[i])
+    size_t need = pwx_wgrad_applicable(ph[i], nullptr) ? pwx_wgrad_ws_floats(ph[i])
+                  : use_tc_wgrad(ph[i]) ? tc_wgrad_ws_floats(ph[i])
                   : wgrad_tpp_applicable(ph[i]) ? wgrad_tpp_ws_floats(ph[i])
                   : wgrad_small_applicable(ph[i]) ? wgrad_small_ws_floats(ph[i]) : plan_wgrad(ph[i]).ws_floats;
     if (need > mx) mx = need;
@@ -808,7 +811,10 @@ int nlt_gconv_wgrad(const nlt_gconv_desc* d, const float* G, float* dW, float* d
     float* ws = (float*)workspace;
     WgradK w;
     size_t KD_pad = 0;
-    if (use_tc_wgrad(k)) {
+    if (pwx_wgrad_applicable(k, G) && (int64_t)(pwx_wgrad_ws_floats(k) * sizeof(float)) <= workspace_bytes) {
+      rc = launch_pwx_wgrad(k, G, ws, &w, &KD_pad, st);
+      if (rc != NLT_OK) return rc;
+    } else if (use_tc_wgrad(k)) {
       NLT_CHECK_ARG((int64_t)(tc_wgrad_ws_floats(k) * sizeof(float)) <= workspace_bytes, "workspace too small");
       rc = launch_tc_wgrad(k, G, ws, &w, &KD_pad, st);
       if (rc != NLT_OK) return rc;

@@ -160,6 +160,67 @@ __global__ void uv2cam_bwd_kernel(const float* __restrict__ d_pred_c, const floa
   }
 }
 
+// Deterministic form of the scatter: the four tap contributions are accumulated as 64-bit FIXED-POINT integers
+// (integer addition is associative, so the result does not depend on the order in which the atomics land), then
+// converted to fp32 in one pass that also re-zeroes the accumulator for the next call (no memset pass).
+// Scale: 2^(37 - floor(log2(gmax))) with gmax = max |d_pred_camspc| of THIS call (a max-reduction, itself order
+// independent): every contribution is below 2^38 in magnitude, a texel can collect all ih*iw <= 2^24 camera pixels of
+// its image without overflowing 63 bits, and the quantum gmax * 2^-38 is 2^14 times finer than fp32's own
+// resolution at gmax.
+__global__ void absmax_kernel(const float* __restrict__ x, size_t n, unsigned int* __restrict__ out_bits) {
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(__ldg(x + i)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_uint(m));   // non-negative floats order as uints
+}
+
+__device__ __forceinline__ double fixed_scale(unsigned int gmax_bits) {
+  const int e = (int)((gmax_bits >> 23) & 0xffu) - 127;          // floor(log2(gmax)) for normal numbers
+  return ldexp(1.0, 37 - e);
+}
+
+__global__ void uv2cam_bwd_fixed_kernel(const float* __restrict__ d_pred_c, const float* __restrict__ warp, int B, int H,
+                                        int W, int ih, int iw, const unsigned int* __restrict__ gmax_bits,
+                                        unsigned long long* __restrict__ acc) {
+  const size_t npix = (size_t)B * ih * iw;
+  const size_t per_cam = (size_t)ih * iw;
+  const double scale = fixed_scale(*gmax_bits);
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(p / per_cam);
+    const float2 wv = __ldg(reinterpret_cast<const float2*>(warp) + p);
+    const float x = wv.x * (float)W, y = wv.y * (float)H;
+    Taps t;
+    if (!resampler_taps(x, y, H, W, t)) continue;
+    float g[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) g[c] = __ldg(d_pred_c + p * 3 + c);
+    if (g[0] == 0.f && g[1] == 0.f && g[2] == 0.f) continue;
+    unsigned long long* du = acc + (size_t)b * H * W * 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int id = t.idx[k];
+      if (id <= 0) continue;   // out of range, or texel (0,0) whose mask multiply kills the gradient
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const long long q = __double2ll_rn((double)(t.w[k] * g[c]) * scale);
+        if (q != 0) atomicAdd(du + (size_t)id * 3 + c, (unsigned long long)q);   // two's complement: signed sum
+      }
+    }
+  }
+}
+
+__global__ void fixed_to_float_kernel(unsigned long long* __restrict__ acc, size_t n,
+                                      const unsigned int* __restrict__ gmax_bits, float* __restrict__ out) {
+  const double inv = 1.0 / fixed_scale(*gmax_bits);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const long long v = (long long)acc[i];
+    out[i] = (float)((double)v * inv);
+    if (v != 0) acc[i] = 0ull;                 // leave the accumulator zeroed for the next call
+  }
+}
+
 // ---------------------------------------------------------------------------
 // tf.image.resize bilinear, half-pixel centres -- nlt/util/img.py:113-116
 // ---------------------------------------------------------------------------
@@ -366,6 +427,33 @@ int nlt_uv2cam_bwd(const float* d_pred_camspc, const float* warp, int32_t B, int
   const size_t npix = (size_t)B * ih * iw;
   uv2cam_bwd_kernel<<<grid_for(npix, 256), 256, 0, st>>>(d_pred_camspc, warp, B, H, W, ih, iw, d_net_out);
   NLT_CUDA_LAUNCH_CHECK("uv2cam_bwd_kernel");
+  return NLT_OK;
+}
+
+int64_t nlt_uv2cam_bwd_workspace_bytes(int32_t B, int32_t H, int32_t W) {
+  if (B <= 0 || H <= 0 || W <= 0) return -1;
+  return (int64_t)B * H * W * 3 * 8 + 256;
+}
+
+int nlt_uv2cam_bwd_det(const float* d_pred_camspc, const float* warp, int32_t B, int32_t H, int32_t W, int32_t ih,
+                       int32_t iw, float* d_net_out, void* workspace, void* stream) {
+  NLT_CHECK_ARG(d_pred_camspc && warp && d_net_out && workspace, "uv2cam_bwd_det: null pointer");
+  NLT_CHECK_ARG(B > 0 && H > 0 && W > 0 && ih > 0 && iw > 0, "uv2cam_bwd_det: bad geometry");
+  NLT_CHECK_ARG((long long)ih * iw <= (1ll << 24), "uv2cam_bwd_det: camera image too large for the fixed-point range");
+  NLT_CHECK_ARG((((uintptr_t)workspace) & 7) == 0, "uv2cam_bwd_det: workspace must be 8-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned int* gmax = reinterpret_cast<unsigned int*>(workspace);            // first 256 bytes: the max scalar
+  unsigned long long* acc = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + 256);
+  cudaError_t e = cudaMemsetAsync(gmax, 0, 4, st);
+  if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+  const size_t npix = (size_t)B * ih * iw;
+  absmax_kernel<<<grid_for(npix * 3, 256, 4), 256, 0, st>>>(d_pred_camspc, npix * 3, gmax);
+  NLT_CUDA_LAUNCH_CHECK("absmax_kernel");
+  uv2cam_bwd_fixed_kernel<<<grid_for(npix, 256), 256, 0, st>>>(d_pred_camspc, warp, B, H, W, ih, iw, gmax, acc);
+  NLT_CUDA_LAUNCH_CHECK("uv2cam_bwd_fixed_kernel");
+  const size_t n = (size_t)B * H * W * 3;
+  fixed_to_float_kernel<<<grid_for(n, 256), 256, 0, st>>>(acc, n, gmax, d_net_out);
+  NLT_CUDA_LAUNCH_CHECK("fixed_to_float_kernel");
   return NLT_OK;
 }
 

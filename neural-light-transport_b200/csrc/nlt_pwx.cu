@@ -1,0 +1,454 @@
+// Wide pointwise (1x1, stride 1) convolution into 16 channels over a virtual channel concat of 17..128 inputs:
+// the level-0 layer of the 64-channel query stack (BASELINE.json "1024^2 x 64ch": base 3 + cvis 60 + lvis 1 -> 16,
+// nlt/models/nlt.py:95 + nlt/networks/convnet.py:44) -- forward and weight gradient.
+//
+// Both are streams of [pixels x K] rows against a tiny [K x 16] matrix (AI ~ 6 FLOP/B), so the design goal is:
+// every input byte crosses HBM once, arrives in shared memory by cp.async (16-byte pieces for float4-able
+// sources, 4-byte pieces for the 3- and 1-channel ones -- no register staging, two tiles in flight), and the math
+// runs as packed FFMA2 (two fp32 FMAs per issued instruction, sm_100) so that the CUDA-core issue rate stays
+// below the HBM time per tile:
+//
+//   tile = 256 consecutive pixels (1x1 conv: each source's tile is one contiguous run of bytes)
+//   smem row of a pixel = [float4-able sources ...][scalar sources ...][zero pad], stride KROW = K4*4 + 4 floats
+//   (an odd number of 16-byte chunks: thread-per-pixel LDS.128 over consecutive rows is bank-conflict free)
+//
+//   forward : thread = pixel, 16 outputs as 16 float2 accumulators over (even, odd) channel pairs; the weight
+//             pairs (W[c][n], W[c+1][n]) sit in shared memory so one broadcast LDS.128 feeds two FFMA2
+//   wgrad   : warp = pixel, lane = (channel quad group cg, output quad ng); dz is staged duplicated
+//             (d, d) so that x pairs (c, c+1) times a broadcast pair accumulate dW[c..c+1][n] in one FFMA2;
+//             one fp32 partial per CTA goes to the workspace in the k-group layout of WgradK, the fixed-order
+//             reduce kernel of nlt_gconv.cu finishes (deterministic).
+#include "nlt_common.cuh"
+
+namespace nlt {
+
+constexpr int PWX_T = 256;          // pixels per tile
+constexpr int PWX_THREADS = 256;
+constexpr int PWX_N = 16;           // output channels
+constexpr int PWX_KMAX = 128;
+
+struct PwxSeg {
+  const float* ptr;
+  int C;         // channels
+  int off;       // first smem column
+  int vec;       // 1: 16-byte pieces
+  FastDiv div;   // division of the float4 index by C/4 (vec) or of the element index by C (scalar)
+};
+
+struct PwxParams {
+  PwxSeg seg[NLT_MAX_SEG];
+  int nseg;
+  int K, K4;           // channels, float4 groups per smem row (incl. zero padding up to a multiple of 8 groups for wgrad)
+  int krow;            // smem row stride in floats
+  uint32_t M;          // pixels
+  uint32_t ntiles;
+  int16_t col_c[PWX_KMAX];    // smem column -> concat channel (weight row), -1 pad
+  int16_t col_row[PWX_KMAX];  // smem column -> workspace row of the wgrad partial (k-group layout), -1 pad
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+__device__ __forceinline__ uint32_t pwx_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// stage the x rows of tile `t` into xs (row stride p.krow floats); rows beyond M are zero-filled by the caller once
+__device__ __forceinline__ void pwx_stage_x(const PwxParams& p, uint32_t t, float* xs) {
+  const uint32_t pix0 = t * PWX_T;
+  const uint32_t npx = min((uint32_t)PWX_T, p.M - pix0);
+  const uint32_t xs_u = pwx_smem_u32(xs);
+#pragma unroll 1
+  for (int s = 0; s < p.nseg; ++s) {
+    const PwxSeg sg = p.seg[s];
+    if (sg.vec) {
+      const uint32_t c4 = (uint32_t)sg.C >> 2;
+      const uint32_t n4 = npx * c4;
+      const float4* src = reinterpret_cast<const float4*>(sg.ptr + (size_t)pix0 * sg.C);
+      for (uint32_t i = threadIdx.x; i < n4; i += PWX_THREADS) {
+        const uint32_t px = fdiv(i, sg.div);
+        const uint32_t j = i - px * c4;
+        cp_async16(xs_u + (px * p.krow + sg.off + 4 * j) * 4, src + i);
+      }
+    } else {
+      const uint32_t n = npx * (uint32_t)sg.C;
+      const float* src = sg.ptr + (size_t)pix0 * sg.C;
+      for (uint32_t i = threadIdx.x; i < n; i += PWX_THREADS) {
+        const uint32_t px = fdiv(i, sg.div);
+        const uint32_t c = i - px * (uint32_t)sg.C;
+        cp_async4(xs_u + (px * p.krow + sg.off + c) * 4, src + i);
+      }
+    }
+  }
+}
+
+// zero the rows [from, PWX_T) of an x stage
+__device__ __forceinline__ void pwx_zero_rows(const PwxParams& p, float* xs, uint32_t from) {
+  for (uint32_t i = from * p.krow + threadIdx.x; i < (uint32_t)PWX_T * p.krow; i += PWX_THREADS) xs[i] = 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+constexpr int PWX_OROW = 20;        // floats per staged output row (16 + 4: conflict-free STS.128 per pixel)
+
+__global__ void __launch_bounds__(PWX_THREADS, 1)
+pwx_fwd_kernel(const PwxParams p, const float* __restrict__ w, long long wc, long long wn,
+               const float* __restrict__ bias, const int act, float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  const int npair = p.K4 * 2;                                  // channel pairs
+  float* wp = smem;                                            // [npair][16][2]
+  float* xs0 = wp + npair * 32;
+  float* xs1 = xs0 + PWX_T * p.krow;
+  float* so = xs1 + PWX_T * p.krow;                            // [PWX_T][PWX_OROW]
+  const int tid = threadIdx.x;
+
+  // weights as (even, odd) channel pairs in smem column order; pad columns contribute zero
+  for (int i = tid; i < npair * 16; i += PWX_THREADS) {
+    const int cp = i >> 4, n = i & 15;
+    const int c0 = p.col_c[2 * cp], c1 = p.col_c[2 * cp + 1];
+    wp[i * 2 + 0] = c0 >= 0 ? __ldg(w + (long long)c0 * wc + (long long)n * wn) : 0.f;
+    wp[i * 2 + 1] = c1 >= 0 ? __ldg(w + (long long)c1 * wc + (long long)n * wn) : 0.f;
+  }
+  pwx_zero_rows(p, xs0, 0);
+  pwx_zero_rows(p, xs1, 0);
+  float bv[16];
+#pragma unroll
+  for (int n = 0; n < 16; ++n) bv[n] = bias ? __ldg(bias + n) : 0.f;
+  __syncthreads();
+
+  uint32_t t = blockIdx.x;
+  if (t < p.ntiles) pwx_stage_x(p, t, xs0);
+  cp_async_commit();
+  int buf = 0;
+  for (; t < p.ntiles; t += gridDim.x, buf ^= 1) {
+    float* xs = buf ? xs1 : xs0;
+    float* xn = buf ? xs0 : xs1;
+    const uint32_t tn = t + gridDim.x;
+    if (tn < p.ntiles) {
+      if (p.M - tn * PWX_T < (uint32_t)PWX_T) pwx_zero_rows(p, xn, p.M - tn * PWX_T);   // partial last tile
+      pwx_stage_x(p, tn, xn);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();                                           // tile t has landed for every thread
+
+    float2 acc[16];
+#pragma unroll
+    for (int n = 0; n < 16; ++n) acc[n] = make_float2(bv[n], 0.f);
+    const float4* xrow = reinterpret_cast<const float4*>(xs + tid * p.krow);
+    const float4* wq = reinterpret_cast<const float4*>(wp);
+#pragma unroll 2
+    for (int q = 0; q < p.K4; ++q) {
+      const float4 xv = xrow[q];
+      const float2 xa = make_float2(xv.x, xv.y), xb = make_float2(xv.z, xv.w);
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        const float4 wa = wq[(2 * q) * 8 + h];                 // pair 2q:   (n = 2h), (n = 2h+1)
+        const float4 wb = wq[(2 * q + 1) * 8 + h];             // pair 2q+1
+        acc[2 * h] = __ffma2_rn(xa, make_float2(wa.x, wa.y), acc[2 * h]);
+        acc[2 * h + 1] = __ffma2_rn(xa, make_float2(wa.z, wa.w), acc[2 * h + 1]);
+        acc[2 * h] = __ffma2_rn(xb, make_float2(wb.x, wb.y), acc[2 * h]);
+        acc[2 * h + 1] = __ffma2_rn(xb, make_float2(wb.z, wb.w), acc[2 * h + 1]);
+      }
+    }
+    float o[16];
+#pragma unroll
+    for (int n = 0; n < 16; ++n) o[n] = act_fwd(acc[n].x + acc[n].y, act);
+    float4* srow = reinterpret_cast<float4*>(so + tid * PWX_OROW);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) srow[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    __syncthreads();                                           // outputs staged; every thread is done with xs
+    // coalesced 16-byte stores: the tile's outputs are one contiguous run of PWX_T*16 floats
+    const uint32_t pix0 = t * PWX_T;
+    const uint32_t npx = min((uint32_t)PWX_T, p.M - pix0);
+    float4* dst = reinterpret_cast<float4*>(out + (size_t)pix0 * 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t qi = tid + i * PWX_THREADS;               // float4 index inside the tile
+      const uint32_t px = qi >> 2, j = qi & 3;
+      if (px < npx) dst[qi] = *reinterpret_cast<const float4*>(so + px * PWX_OROW + 4 * j);
+    }
+    // so is rewritten only after the next tile's first barrier, xs[buf] after this loop's top-of-iteration staging of
+    // tile t + 2*grid, which follows that barrier too: one more barrier is not needed
+  }
+  cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight gradient
+// ---------------------------------------------------------------------------------------------
+template <int NG>                  // float4 channel groups per lane (K4 <= 8*NG)
+__global__ void __launch_bounds__(PWX_THREADS, 1)
+pwx_wgrad_kernel(const PwxParams p, const float* __restrict__ G, float* __restrict__ ws, const int kd_pad,
+                 const int bias_row) {
+  extern __shared__ __align__(16) float smem[];
+  float* xs0 = smem;
+  float* xs1 = xs0 + PWX_T * p.krow;
+  float* gs0 = xs1 + PWX_T * p.krow;                           // [PWX_T][32]: dz duplicated (d, d)
+  float* gs1 = gs0 + PWX_T * 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cg = lane & 7, ng = lane >> 3;
+
+  pwx_zero_rows(p, xs0, 0);
+  pwx_zero_rows(p, xs1, 0);
+  __syncthreads();
+
+  float2 acc[NG][2][4];
+  float bs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int g = 0; g < NG; ++g)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int n = 0; n < 4; ++n) acc[g][h][n] = make_float2(0.f, 0.f);
+
+  // dz of a tile: PWX_T*16 floats = 1024 float4, 4 per thread; loaded one tile ahead into registers
+  auto load_g = [&](uint32_t t, float4 (&r)[4]) {
+    const uint32_t pix0 = t * PWX_T;
+    const uint32_t nq = min((uint32_t)PWX_T, p.M - pix0) * 4;
+    const float4* src = reinterpret_cast<const float4*>(G + (size_t)pix0 * 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t qi = tid + i * PWX_THREADS;
+      r[i] = qi < nq ? __ldg(src + qi) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto store_g = [&](float* gs, const float4 (&r)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t qi = tid + i * PWX_THREADS;               // pixel = qi / 4, output quad = qi % 4
+      float4* d = reinterpret_cast<float4*>(gs + (qi >> 2) * 32 + (qi & 3) * 8);
+      d[0] = make_float4(r[i].x, r[i].x, r[i].y, r[i].y);
+      d[1] = make_float4(r[i].z, r[i].z, r[i].w, r[i].w);
+    }
+  };
+
+  uint32_t t = blockIdx.x;
+  float4 gr[4];
+  if (t < p.ntiles) {
+    if (p.M - t * PWX_T < (uint32_t)PWX_T) pwx_zero_rows(p, xs0, p.M - t * PWX_T);
+    pwx_stage_x(p, t, xs0);
+    load_g(t, gr);
+    store_g(gs0, gr);
+  }
+  cp_async_commit();
+  int buf = 0;
+  for (; t < p.ntiles; t += gridDim.x, buf ^= 1) {
+    float* xs = buf ? xs1 : xs0;
+    float* xn = buf ? xs0 : xs1;
+    float* gs = buf ? gs1 : gs0;
+    float* gn = buf ? gs0 : gs1;
+    const uint32_t tn = t + gridDim.x;
+    const bool more = tn < p.ntiles;
+    if (more) {
+      if (p.M - tn * PWX_T < (uint32_t)PWX_T) pwx_zero_rows(p, xn, p.M - tn * PWX_T);
+      pwx_stage_x(p, tn, xn);
+      load_g(tn, gr);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();                                           // x and dz of tile t are visible
+
+#pragma unroll 2
+    for (int i = 0; i < PWX_T / 8; ++i) {
+      const int px = warp + 8 * i;
+      const float4* xr = reinterpret_cast<const float4*>(xs + px * p.krow);
+      const float4* gq = reinterpret_cast<const float4*>(gs + px * 32 + ng * 8);
+      const float4 g0 = gq[0], g1 = gq[1];                     // (d0,d0,d1,d1), (d2,d2,d3,d3)
+      const float2 gd[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y),
+                            make_float2(g1.z, g1.w)};
+      bs[0] += g0.x; bs[1] += g0.z; bs[2] += g1.x; bs[3] += g1.z;
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const float4 xv = xr[cg + 8 * g];
+        const float2 xa = make_float2(xv.x, xv.y), xb = make_float2(xv.z, xv.w);
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          acc[g][0][n] = __ffma2_rn(xa, gd[n], acc[g][0][n]);
+          acc[g][1][n] = __ffma2_rn(xb, gd[n], acc[g][1][n]);
+        }
+      }
+    }
+    if (more) store_g(gn, gr);                                 // gn was last read in the previous iteration
+    __syncthreads();                                           // everyone is done with xs / gs of tile t
+  }
+  cp_async_wait<0>();
+
+  // ---- cross-warp reduction in fixed order, one partial per CTA ----
+  float* red = smem;                                           // [8 warps][8*NG*4 columns][16]
+  const int ncol = 8 * NG * 4;
+#pragma unroll
+  for (int g = 0; g < NG; ++g)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int col = (cg + 8 * g) * 4 + 2 * h;
+      float* r0 = red + ((size_t)warp * ncol + col) * 16 + ng * 4;
+      *reinterpret_cast<float4*>(r0) = make_float4(acc[g][h][0].x, acc[g][h][1].x, acc[g][h][2].x, acc[g][h][3].x);
+      *reinterpret_cast<float4*>(r0 + 16) = make_float4(acc[g][h][0].y, acc[g][h][1].y, acc[g][h][2].y, acc[g][h][3].y);
+    }
+  float* redb = red + (size_t)8 * ncol * 16;                   // [8 warps][16] bias partials
+  if (cg == 0) *reinterpret_cast<float4*>(redb + warp * 16 + ng * 4) = make_float4(bs[0], bs[1], bs[2], bs[3]);
+  __syncthreads();
+  float* dst = ws + (size_t)blockIdx.x * kd_pad * 16;
+  for (int i = tid; i < ncol * 16; i += PWX_THREADS) {
+    const int col = i >> 4, n = i & 15;
+    float s = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) s += red[((size_t)wv * ncol + col) * 16 + n];
+    const int row = col < PWX_KMAX ? p.col_row[col] : -1;
+    if (row >= 0) dst[(size_t)row * 16 + n] = s;
+  }
+  if (tid < 16) {
+    float s = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) s += redb[wv * 16 + tid];
+    dst[(size_t)bias_row * 16 + tid] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static bool pwx_shape_ok(const GConvK& k) {
+  if (k.d2s || k.M == 0 || k.Cout != PWX_N || k.cout_true != PWX_N) return false;
+  if (k.ay.nu != 1 || k.ax.nu != 1 || k.ay.it != 1 || k.ax.it != 1 || k.ay.i0 != 0 || k.ax.i0 != 0) return false;
+  if (k.ay.os != 1 || k.ax.os != 1 || k.ay.o0 != 0 || k.ax.o0 != 0) return false;
+  if (k.Hin != k.Hout || k.Win != k.Wout || k.ay.nt != k.Hout || k.ax.nt != k.Wout) return false;
+  int K = 0;
+  for (int s = 0; s < k.nseg; ++s) {
+    if (k.seg[s].sub != nullptr || k.seg[s].bcast) return false;
+    K += k.seg[s].C;
+  }
+  return K > 16 && K <= PWX_KMAX - 8 && k.M >= 4 * PWX_T;
+}
+
+static bool pwx_build(const GConvK& k, bool for_wgrad, PwxParams* p, int* kd_pad, int* bias_row, int* GS_out) {
+  memset(p, 0, sizeof(*p));
+  for (int i = 0; i < PWX_KMAX; ++i) { p->col_c[i] = -1; p->col_row[i] = -1; }
+  int gbase[NLT_MAX_SEG], GS = 0;
+  for (int s = 0; s < k.nseg; ++s) { gbase[s] = GS; GS += (k.seg[s].C + 3) / 4; }
+  int off = 0, K = 0;
+  p->nseg = k.nseg;
+  // float4-able sources first (their rows start on 16-byte columns), scalar ones behind
+  for (int pass = 0; pass < 2; ++pass)
+    for (int s = 0; s < k.nseg; ++s) {
+      const Seg& sg = k.seg[s];
+      if ((sg.vec ? 0 : 1) != pass) continue;
+      PwxSeg& d = p->seg[s];
+      d.ptr = sg.ptr; d.C = sg.C; d.off = off; d.vec = sg.vec;
+      d.div = make_fastdiv(sg.vec ? (uint32_t)sg.C / 4 : (uint32_t)sg.C);
+      for (int c = 0; c < sg.C; ++c) {
+        if (off + c >= PWX_KMAX) return false;
+        p->col_c[off + c] = (int16_t)(sg.coff + c);
+        p->col_row[off + c] = (int16_t)((gbase[s] + c / 4) * 4 + (c & 3));
+      }
+      off += sg.C;
+      K += sg.C;
+    }
+  p->K = K;
+  int K4 = (off + 3) / 4;
+  if (for_wgrad) K4 = (K4 + 7) / 8 * 8;           // lanes cover 8 groups per step
+  else K4 = (K4 + 0);
+  if (K4 * 4 > PWX_KMAX) return false;
+  p->K4 = K4;
+  p->krow = K4 * 4 + 4;
+  p->M = k.M;
+  p->ntiles = (k.M + PWX_T - 1) / PWX_T;
+  if (kd_pad) *kd_pad = (GS + 1) * 4;
+  if (bias_row) *bias_row = GS * 4;
+  if (GS_out) *GS_out = GS;
+  return true;
+}
+
+static size_t pwx_fwd_smem(const PwxParams& p) {
+  return ((size_t)p.K4 * 2 * 32 + 2 * (size_t)PWX_T * p.krow + (size_t)PWX_T * PWX_OROW) * sizeof(float);
+}
+static size_t pwx_wgrad_smem(const PwxParams& p) {
+  const size_t stage = (2 * (size_t)PWX_T * p.krow + 2 * (size_t)PWX_T * 32) * sizeof(float);
+  const size_t red = ((size_t)8 * p.K4 * 4 * 16 + 8 * 16) * sizeof(float);
+  return stage > red ? stage : red;
+}
+constexpr size_t PWX_SMEM_MAX = 227 * 1024;
+
+int g_opt_pwx = -1;     // option "pwx" / NLT_PWX: 1 (default) the kernels of this file, 0 the general routes
+static bool pwx_enabled() {
+  if (g_opt_pwx < 0) { const char* e = getenv("NLT_PWX"); g_opt_pwx = (e && e[0] == '0') ? 0 : 1; }
+  return g_opt_pwx == 1;
+}
+
+bool pwx_fwd_applicable(const GConvK& k, float beta, const float* mask_y, const float* out) {
+  if (!pwx_enabled() || !pwx_shape_ok(k) || beta != 0.f || mask_y != nullptr || !aligned16(out)) return false;
+  PwxParams p;
+  return pwx_build(k, false, &p, nullptr, nullptr, nullptr) && pwx_fwd_smem(p) <= PWX_SMEM_MAX;
+}
+
+int launch_pwx_fwd(const GConvK& k, const float* bias, int act, float* out, cudaStream_t st) {
+  PwxParams p;
+  if (!pwx_build(k, false, &p, nullptr, nullptr, nullptr)) return set_err(NLT_ERR_INVALID, "pwx_fwd not applicable");
+  const size_t smem = pwx_fwd_smem(p);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static bool attr_set[64] = {false};
+  if (dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(pwx_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PWX_SMEM_MAX);
+    if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set[dev] = true;
+  }
+  const unsigned grid = p.ntiles < 148u ? p.ntiles : 148u;
+  pwx_fwd_kernel<<<grid, PWX_THREADS, smem, st>>>(p, k.w, k.wc, k.wn, bias, act, out);
+  NLT_CUDA_LAUNCH_CHECK("pwx_fwd_kernel");
+  return NLT_OK;
+}
+
+bool pwx_wgrad_applicable(const GConvK& k, const float* G) {
+  if (!pwx_enabled() || !pwx_shape_ok(k) || (G != nullptr && !aligned16(G))) return false;
+  PwxParams p;
+  return pwx_build(k, true, &p, nullptr, nullptr, nullptr) && pwx_wgrad_smem(p) <= PWX_SMEM_MAX;
+}
+
+static unsigned pwx_wgrad_grid(const PwxParams& p) { return p.ntiles < 148u ? p.ntiles : 148u; }
+
+size_t pwx_wgrad_ws_floats(const GConvK& k) {
+  PwxParams p;
+  int kd_pad = 0;
+  if (!pwx_build(k, true, &p, &kd_pad, nullptr, nullptr)) return 0;
+  return (size_t)pwx_wgrad_grid(p) * kd_pad * 16;
+}
+
+template <int NG>
+static int pwx_wgrad_launch(const PwxParams& p, const float* G, float* ws, int kd_pad, int bias_row, cudaStream_t st) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static bool attr_set[64] = {false};
+  if (dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(pwx_wgrad_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PWX_SMEM_MAX);
+    if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set[dev] = true;
+  }
+  pwx_wgrad_kernel<NG><<<pwx_wgrad_grid(p), PWX_THREADS, pwx_wgrad_smem(p), st>>>(p, G, ws, kd_pad, bias_row);
+  NLT_CUDA_LAUNCH_CHECK("pwx_wgrad_kernel");
+  return NLT_OK;
+}
+
+int launch_pwx_wgrad(const GConvK& k, const float* G, float* ws, WgradK* w, size_t* KD_pad, cudaStream_t st) {
+  PwxParams p;
+  int kd_pad = 0, bias_row = 0, GS = 0;
+  if (!pwx_build(k, true, &p, &kd_pad, &bias_row, &GS)) return set_err(NLT_ERR_INVALID, "pwx_wgrad not applicable");
+  // rows of pad channels inside a k-group are never read by the reduce stage, but the workspace may hold NaN
+  // bit patterns from an earlier use: the reduce stage only touches (c + e < C) rows, so nothing to clear
+  w->g = k; w->GS = GS; w->KG = GS + 1; w->ld = 16; w->nsplit = (int)pwx_wgrad_grid(p); w->pix_per_split = 0;
+  *KD_pad = (size_t)kd_pad;
+  switch (p.K4 / 8) {
+    case 1: return pwx_wgrad_launch<1>(p, G, ws, kd_pad, bias_row, st);
+    case 2: return pwx_wgrad_launch<2>(p, G, ws, kd_pad, bias_row, st);
+    case 3: return pwx_wgrad_launch<3>(p, G, ws, kd_pad, bias_row, st);
+    default: return pwx_wgrad_launch<4>(p, G, ws, kd_pad, bias_row, st);
+  }
+}
+
+}  // namespace nlt

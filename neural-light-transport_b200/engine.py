@@ -158,6 +158,9 @@ USE_SIDE_STREAM = True
 # called as WGRAD_HOOK(layer) right after a layer's weight-gradient launch has been issued (on the side stream when
 # USE_SIDE_STREAM): trainvali.GradReducer starts the early part of the gradient all-reduce from it
 WGRAD_HOOK = None
+# debugging / parity tap: FWD_TAP(layer, output tensor) after every conv launch (tests/test_gpu_parity.py collects the
+# activation-derivative masks of the product with it)
+FWD_TAP = None
 
 
 def gconv_fwd(d, bias, act, beta, mask, mask_act, out):
@@ -341,6 +344,8 @@ class ConvLayer:
         out = torch.empty((N, d.Hout, d.Wout, self.cout), dtype=torch.float32, device=ref.device)
         nb = 4 * (sum(sg.a.t.numel() * (2 if sg.sub is not None else 1) for sg in segs) + out.numel())
         PROF.run('fwd ' + self.name, nb, lambda: gconv_fwd(d, self.bias, nat.ACT_CODES[self.act], 0.0, None, 0, out))
+        if FWD_TAP is not None:
+            FWD_TAP(self, out)
         y = Act(out, act=self.act, needs_grad=tape is not None)
         if tape is not None:
             for sg in segs:
@@ -421,7 +426,8 @@ def kmean(obs_y, K, tape=None, weights=None):
     B = t.shape[0] // K
     per = t.shape[1] * t.shape[2] * t.shape[3]
     out = torch.empty((B,) + tuple(t.shape[1:]), dtype=torch.float32, device=t.device)
-    nat.check(lib.nlt_kmean_fwd(nat.ptr(t), nat.ptr(weights), K, B, per, nat.ptr(out), nat.stream()))
+    PROF.run('fwd kmean', 4 * (t.numel() + out.numel()), lambda: nat.check(
+        lib.nlt_kmean_fwd(nat.ptr(t), nat.ptr(weights), K, B, per, nat.ptr(out), nat.stream())))
     agg = Act(out, act=None, needs_grad=tape is not None and obs_y.needs_grad)
     if tape is not None and obs_y.needs_grad:
         obs_y.n_cons += 1
@@ -432,8 +438,10 @@ def kmean(obs_y, K, tape=None, weights=None):
                 return
 
             def write(o, beta, mask, mask_act, term=None):
-                nat.check(lib.nlt_kmean_bwd(nat.ptr(agg.grad), nat.ptr(weights), K, B, per, beta, nat.ptr(mask),
-                                            mask_act, nat.ptr(o), nat.stream()))
+                nb = 4 * (agg.grad.numel() + o.numel() * (1 + (beta != 0) + (mask is not None)))
+                PROF.run('dgrad kmean', nb, lambda: nat.check(lib.nlt_kmean_bwd(
+                    nat.ptr(agg.grad), nat.ptr(weights), K, B, per, beta, nat.ptr(mask), mask_act, nat.ptr(o),
+                    nat.stream())))
             contribute(obs_y, write)
             agg.grad = None
         tape.record(bwd)

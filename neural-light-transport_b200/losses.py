@@ -32,8 +32,10 @@ class L2():
         scale = float(self.grad_scale) if want_grad else 0.0
         if not keep_batch and want_grad:
             scale = scale / B   # mean over the batch as well
-        nat.check(lib.nlt_l2_loss(nat.ptr(pred), nat.ptr(gt), B, per, scale, nat.ptr(loss),
-                                  nat.ptr(self.d_pred), nat.ptr(self._ws), nat.stream()))
+        from engine import PROF
+        PROF.run('fwd loss l2', 4 * pred.numel() * (3 if want_grad else 2), lambda: nat.check(lib.nlt_l2_loss(
+            nat.ptr(pred), nat.ptr(gt), B, per, scale, nat.ptr(loss), nat.ptr(self.d_pred), nat.ptr(self._ws),
+            nat.stream())))
         if keep_batch:
             return loss
         return loss.mean()
@@ -84,9 +86,10 @@ class Barron():
             scale = scale / B
         if weights is not None:
             weights = weights.to(pred.device, torch.float32).expand(B, H, W, 1).contiguous()
-        nat.check(lib.nlt_barron_loss(nat.ptr(pred), nat.ptr(gt), nat.ptr(weights), B, H, W, self.LEVELS, self.SCALE,
-                                      self.LOG_Z_ALPHA1, scale, nat.ptr(loss), nat.ptr(self.d_pred),
-                                      nat.ptr(self._ws), nat.stream()))
+        from engine import PROF
+        PROF.run('fwd loss barron', 4 * pred.numel() * (3 if want_grad else 2), lambda: nat.check(lib.nlt_barron_loss(
+            nat.ptr(pred), nat.ptr(gt), nat.ptr(weights), B, H, W, self.LEVELS, self.SCALE, self.LOG_Z_ALPHA1, scale,
+            nat.ptr(loss), nat.ptr(self.d_pred), nat.ptr(self._ws), nat.stream())))
         return loss if keep_batch else loss.mean()
 
 

@@ -18,7 +18,7 @@ import torch
 
 import losses
 import nlt_native as nat
-from engine import Act, Seg, Tape, ParamBucket, kmean
+from engine import Act, Seg, Tape, ParamBucket, kmean, PROF
 from networks import convnet
 from .base import Model as BaseModel
 
@@ -63,6 +63,7 @@ class Model(BaseModel):
         self._tape = None
         self._d_pred = None
         self._loss_grad_scale = None
+        self._scatter_ws = None
 
     # ------------------------------------------------------------------
     # parameters
@@ -168,7 +169,21 @@ class Model(BaseModel):
             raise nat.NativeError('no CUDA device: the NLT hot path has no CPU fallback')
         dev = self.device
         base, cvis, lvis, warp = (_dev_tensor(t, dev) for t in (base, cvis, lvis, warp))
+        # The reference passes exactly one neighbour (nlt.py:96, "only one neighbor") while `_call` takes a list of
+        # K; here K observations may ride in the same two slots of the tuple, either as lists of K [B,H,W,3]
+        # tensors or as one k-major [K,B,H,W,3] tensor each (K = 6)
+        if isinstance(nn_rgb, (list, tuple)):
+            nn_rgb = torch.stack([_dev_tensor(t, dev) for t in nn_rgb], dim=0)
+            nn_base = torch.stack([_dev_tensor(t, dev) for t in nn_base], dim=0)
         nn_base, nn_rgb = _dev_tensor(nn_base, dev), _dev_tensor(nn_rgb, dev)
+        K = 1
+        if nn_rgb.dim() == 5:
+            K = nn_rgb.shape[0]
+            if nn_base.shape != nn_rgb.shape or nn_rgb.shape[1] != base.shape[0]:
+                raise ValueError('K-observation inputs must be [K,B,H,W,3], got %s / %s' % (
+                    tuple(nn_rgb.shape), tuple(nn_base.shape)))
+            nn_rgb = nn_rgb.reshape((-1,) + tuple(nn_rgb.shape[2:]))      # k-major stack: a view, no copy
+            nn_base = nn_base.reshape((-1,) + tuple(nn_base.shape[2:]))
         train = mode == 'train'
         tape = Tape() if train else None
         if train:
@@ -176,7 +191,7 @@ class Model(BaseModel):
         # x = concat(base, cvis, lvis); y_obs = [nn_rgb - nn_base]  (nlt.py:95-96)
         q_segs = [Seg(Act(base)), Seg(Act(cvis)), Seg(Act(lvis))]
         o_segs = [Seg(Act(nn_rgb), sub=nn_base)]
-        net_out = self._call_segs(q_segs, o_segs, 1, None, obs_override, tape)
+        net_out = self._call_segs(q_segs, o_segs, K, None, obs_override, tape)
         skip_connect_base = self.config.getboolean(
             'DEFAULT', 'skip_connect_base')
         # ---- UV -> camera tail (nlt.py:99-120) in one fused pass ----
@@ -192,10 +207,14 @@ class Model(BaseModel):
         pred_c, base_c = new(B, ih, iw, 3), new(B, ih, iw, 3)
         fg_c = new(B, ih, iw, 3) if (resize and want_gt) else None
         gt_c = new(B, ih, iw, 3) if (want_gt and not resize) else None
-        nat.check(lib.nlt_uv2cam_fwd(
+        # algorithmic bytes of the tail: net_out + base in, pred out (UV); warp + rgb in, 4 gathers of 3 channels from
+        # the two UV maps, pred/base/gt out (camera)
+        tail_bytes = 4 * (9 * B * H * W + (2 + 6 + 3 * (1 if gt_c is not None else 0)
+                                             + 3 * (2 + (gt_c is not None) + (fg_c is not None))) * B * ih * iw)
+        PROF.run('fwd tail uv2cam', tail_bytes, lambda: nat.check(lib.nlt_uv2cam_fwd(
             nat.ptr(net_out.t), nat.ptr(base), nat.ptr(warp), nat.ptr(rgb_camspc) if gt_c is not None else None,
             B, H, W, ih, iw, 1 if skip_connect_base else 0, nat.ptr(pred), nat.ptr(pred_c), nat.ptr(base_c),
-            nat.ptr(fg_c), nat.ptr(gt_c), nat.stream()))
+            nat.ptr(fg_c), nat.ptr(gt_c), nat.stream())))
         if resize:   # tf.image.resize to (imh, imw)  (nlt.py:116-120)
             def rs(x):
                 y = new(B, self.imh, self.imw, 3)
@@ -218,7 +237,15 @@ class Model(BaseModel):
                                                           nat.ptr(d_full), nat.stream()))
                     d = d_full
                 g = new(B, H, W, 3)
-                nat.check(lib.nlt_uv2cam_bwd(nat.ptr(d), nat.ptr(warp), B, H, W, ih, iw, nat.ptr(g), nat.stream()))
+                # bit-reproducible scatter (64-bit fixed-point accumulation); its accumulator is zero-filled once
+                # and handed back zero-filled by every call
+                need = lib.nlt_uv2cam_bwd_workspace_bytes(B, H, W)
+                if self._scatter_ws is None or self._scatter_ws.numel() * 8 < need or self._scatter_ws.device != dev:
+                    self._scatter_ws = torch.zeros((need + 7) // 8, dtype=torch.int64, device=dev)
+                ws = self._scatter_ws
+                PROF.run('dgrad tail uv2cam', 4 * (5 * B * ih * iw + 3 * B * H * W), lambda: nat.check(
+                    lib.nlt_uv2cam_bwd_det(nat.ptr(d), nat.ptr(warp), B, H, W, ih, iw, nat.ptr(g), ws.data_ptr(),
+                                           nat.stream())))
                 net_out.grad = g
             tape.record(tail_bwd)
         self._tape = tape

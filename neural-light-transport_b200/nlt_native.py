@@ -70,6 +70,8 @@ _SIGS = {
                                 C.c_int, C.c_void_p, C.c_void_p]),
     'nlt_uv2cam_fwd': (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 6 + [C.c_void_p] * 6),
     'nlt_uv2cam_bwd': (C.c_int, [C.c_void_p] * 2 + [C.c_int32] * 5 + [C.c_void_p] * 2),
+    'nlt_uv2cam_bwd_workspace_bytes': (C.c_int64, [C.c_int32] * 3),
+    'nlt_uv2cam_bwd_det': (C.c_int, [C.c_void_p] * 2 + [C.c_int32] * 5 + [C.c_void_p] * 3),
     'nlt_resize_bilinear_fwd': (C.c_int, [C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p] * 2),
     'nlt_resize_bilinear_bwd': (C.c_int, [C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p] * 2),
     'nlt_l2_loss_workspace_bytes': (C.c_int64, [C.c_int32, C.c_int64]),
@@ -77,6 +79,7 @@ _SIGS = {
                               C.c_void_p, C.c_void_p]),
     'nlt_amsgrad_step': (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_int32] + [C.c_float] * 5 + [C.c_void_p]),
     'nlt_amsgrad_step_dev': (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_void_p] + [C.c_float] * 5 + [C.c_void_p]),
+    'nlt_debug_tcts_probe': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     'nlt_ksum_acc': (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     'nlt_scale': (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
     'nlt_mul': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

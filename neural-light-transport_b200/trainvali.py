@@ -97,6 +97,13 @@ class Adam:
         flat_g, flat_p = self._flat(list(grads_and_vars))
         self._state(flat_p)
         self.iterations += 1
+        from engine import PROF
+        if PROF.enabled:       # 4 state reads + 1 gradient read + 4 writes per parameter
+            return PROF.run('opt amsgrad', 4 * 9 * flat_p.numel(), lambda: self._launch(flat_p, flat_g, grad_scale,
+                                                                                      device_step))
+        self._launch(flat_p, flat_g, grad_scale, device_step)
+
+    def _launch(self, flat_p, flat_g, grad_scale, device_step):
         if device_step:
             nat.check(nat.lib().nlt_amsgrad_step_dev(
                 nat.ptr(flat_p), nat.ptr(flat_g), nat.ptr(self.m), nat.ptr(self.v), nat.ptr(self.vhat),

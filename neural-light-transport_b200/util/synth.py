@@ -14,7 +14,7 @@ def _q255(x):
     return torch.round(x * 255.0) / 255.0
 
 
-def make_batch(B, uv, im, seed=1234, device='cpu', c_extra=0, pin=False):
+def make_batch(B, uv, im, seed=1234, device='cpu', c_extra=0, pin=False, k_obs=1):
     """Returns the 11-tuple (id, base, cvis, lvis, warp, rgb, rgb_camspc,
     nn_id, nn_base, nn_rgb, nn_rgb_camspc).  c_extra > 0 widens cvis with
     extra U[0,1) maps (cfg4's 64-channel query stack: tf.concat is
@@ -22,7 +22,10 @@ def make_batch(B, uv, im, seed=1234, device='cpu', c_extra=0, pin=False):
     g = torch.Generator().manual_seed(seed)
     r = lambda *s: torch.rand(*s, generator=g, dtype=torch.float32)
     base, rgb = _q255(r(B, uv, uv, 3)), _q255(r(B, uv, uv, 3))
-    nn_base, nn_rgb = _q255(r(B, uv, uv, 3)), _q255(r(B, uv, uv, 3))
+    if k_obs > 1:   # K neighbours, k-major [K,B,H,W,3] (cfg3's 6-neighbour observed-light stack)
+        nn_base, nn_rgb = _q255(r(k_obs, B, uv, uv, 3)), _q255(r(k_obs, B, uv, uv, 3))
+    else:
+        nn_base, nn_rgb = _q255(r(B, uv, uv, 3)), _q255(r(B, uv, uv, 3))
     cos = lambda: _q255((r(B, uv, uv, 1) * 1.3 - 0.3).clamp(0, 1))
     cvis, lvis = cos(), cos()
     if c_extra:

@@ -307,7 +307,10 @@ def model_call(params, cfg, batch, mode, obs_override=None):
     id_, base, cvis, lvis, warp, rgb, rgb_camspc, nn_id, nn_base, nn_rgb, \
         nn_rgb_camspc = batch
     x = torch.cat((base, cvis, lvis), dim=3)                      # :95
-    y_obs = [nn_rgb - nn_base]                                    # :96
+    if nn_rgb.dim() == 5:       # K observations, k-major [K,B,H,W,3] (`_call` takes a list, :153-164)
+        y_obs = [nn_rgb[k] - nn_base[k] for k in range(nn_rgb.shape[0])]
+    else:
+        y_obs = [nn_rgb - nn_base]                                # :96
     pred = net_call(params, cfg, x, y_obs, obs_override=obs_override)
     if cfg.get('skip_connect_base', True):
         pred = pred + base                                        # :101-102

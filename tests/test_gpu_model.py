@@ -193,7 +193,7 @@ def test_obs_override_equals_live_path_and_extract_feat():
     m.build(5, 3)
     m.load_params(params)
     train_batches = [synth.make_batch(2, 64, 64, seed=s) for s in (21, 22)]
-    feat = nlt_test.extract_feat(m, train_batches)
+    feat = nlt_test.extract_feat(m, train_batches, n_obs_batches=-1)
     want = O.extract_feat(params, oc, [(b[1].double(), b[5].double()) for b in train_batches])
     assert len(feat) == 7
     for f, w in zip(feat, want):

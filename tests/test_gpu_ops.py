@@ -82,6 +82,12 @@ GEOMS = [
     ('conv', 2, 2, 6, 200, [16, 16], 16),
     ('deconv', 2, 1, 32, 16, [16], 16),
     ('conv', 2, 2, 64, 64, [32, 16], 32),       # mixed 32/16 sources -> 16-wide blocks
+    # wide pointwise conv into 16 channels (nlt_pwx.cu: level 0 of the 64-channel query stack): cp.async-staged
+    # 256-pixel tiles, ragged last tile, float4-able and scalar sources mixed, K not a multiple of 32
+    ('conv', 1, 1, 33, 37, [3, 60, 1], 16),
+    ('conv', 1, 1, 32, 32, [64], 16),
+    ('conv', 1, 1, 24, 24, [20, 4], 16),
+    ('conv', 1, 1, 40, 40, [3, 40, 1, 2], 16),
 ]
 
 

@@ -27,7 +27,7 @@ def layer_table(uv=1024, batch=8, depth0=16, depth=256, k=2, s=2, c_query=5, c_o
     rows = []
     h = uv
     rows.append(('obs.0.0', 'conv', 1, 1, h, [c_obs], n_feat[0]))
-    rows.append(('query.0.0', 'conv', 1, 1, h, [c_query], n_feat[0]))
+    rows.append(('query.0.0', 'conv', 1, 1, h, list(c_query) if isinstance(c_query, (list, tuple)) else [c_query], n_feat[0]))
     x = [n_feat[0], n_feat[0]]              # query stream input of the next layer: query_y (+) observation aggregate
     obs_c = n_feat[0]
     skips = [list(x)]                       # pushed after every contracting layer (models/nlt.py:171-177)
@@ -62,8 +62,10 @@ def main():
     ap.add_argument('--iters', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--opt', nargs='*', default=[], help='nlt_set_option pairs, e.g. dconv_wide32=1 tc=0')
+    ap.add_argument('--cq-segs', dest='cq_segs', type=int, nargs='*', default=[3, 1, 1],
+                    help='channel counts of the query input sources (cfg4: 3 60 1)')
     args = ap.parse_args()
-    table = layer_table(args.uv, args.batch)
+    table = layer_table(args.uv, args.batch, c_query=args.cq_segs)
     if args.list:
         for r in table:
             print('%-12s %-6s k%d s%d  H_in %4d  segments %-14s -> %d' % (r[0], r[1], r[2], r[3], r[4], r[5], r[6]))
