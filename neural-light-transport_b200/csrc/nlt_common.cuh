@@ -171,6 +171,8 @@ size_t pwx_wgrad_ws_floats(const GConvK& k);
 int launch_pwx_wgrad(const GConvK& k, const float* G, float* ws, WgradK* w, size_t* KD_pad, cudaStream_t st);
 
 // tcgen05 tensor-core path (nlt_tc.cu)
+#define NLT_TCS_DEFAULT 0
+extern int g_opt_tcs;            // TS form of the forward kernel (A operand through tensor memory)
 extern unsigned long long g_tc_launches;
 bool tc_applicable(const GConvK& k);
 size_t tc_workspace_bytes(const GConvK& k);

@@ -128,6 +128,27 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// TS form: A operand in tensor memory (see nlt_tcts.cu for the probe of the layout this relies on)
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -442,6 +463,292 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   }
 }
 
+template <int BN, int KBW>
+__global__ void __launch_bounds__(TCF_THREADS, 1)
+tcs_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+  constexpr int ROWB = KBW * 4;                   // bytes per operand row
+  constexpr int TC_KB = KBW;
+  constexpr int TC_A_BYTES = TC_BM * ROWB;
+  constexpr int B_BYTES = BN * ROWB;
+  constexpr int STAGE_BYTES = TC_A_BYTES + 2 * B_BYTES;          // raw A tile + Bhi + Blo (no A-lo plane: A goes to TMEM)
+  constexpr int NTA = (512 - 2 * BN) / (2 * KBW) < 8 ? (512 - 2 * BN) / (2 * KBW) : 8;   // TMEM stages of the A operand
+  constexpr uint32_t ACOL0 = 2 * BN;                             // first A column (behind the two accumulators)
+  constexpr uint32_t TMEM_NEED = ACOL0 + NTA * 2 * KBW;
+  constexpr uint32_t TMEM_COLS = TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
+  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B swizzle
+  // offset arithmetic on the __shared__ array keeps the address space (LDS/STS instead of generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ __align__(8) uint64_t bars[4 * TC_MAX_STAGES + 4];
+  const int TC_STAGES = p.stages;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };                              // TMA -> converters / MMA (smem stage)
+  auto bar_empty = [&](int s) { return bar0 + 8u * (TC_MAX_STAGES + s); };           // converters (256) + MMA commit (1) -> TMA
+  auto bar_aready = [&](int t) { return bar0 + 8u * (2 * TC_MAX_STAGES + t); };      // converters -> MMA (TMEM stage)
+  auto bar_afree = [&](int t) { return bar0 + 8u * (3 * TC_MAX_STAGES + t); };       // MMA commit -> converters
+  auto bar_accf = [&](int b) { return bar0 + 8u * (4 * TC_MAX_STAGES + b); };
+  auto bar_acce = [&](int b) { return bar0 + 8u * (4 * TC_MAX_STAGES + 2 + b); };
+  const uint32_t smem_base = smem_u32(smem);
+  auto a_hi = [&](int s) { return smem_base + (uint32_t)s * STAGE_BYTES; };          // the raw fp32 A tile
+  auto b_hi = [&](int s) { return smem_base + (uint32_t)s * STAGE_BYTES + TC_A_BYTES; };
+  auto b_lo = [&](int s) { return smem_base + (uint32_t)s * STAGE_BYTES + TC_A_BYTES + B_BYTES; };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 257);
+    }
+    for (int t = 0; t < NTA; ++t) {
+      mbar_init(bar_aready(t), 256);
+      mbar_init(bar_afree(t), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_accf(b), 1);
+      mbar_init(bar_acce(b), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                 "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int kb_total = p.kb_total;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles_n;
+        const int mt = tile / p.n_tiles_n;
+        const int n = mt / tiles_per_img;
+        const int r = mt - n * tiles_per_img;
+        const int ty0 = (r / p.tiles_x) * p.TH, tx0 = (r % p.tiles_x) * p.TW;
+        int kb = 0;
+        for (int uy = 0; uy < p.ntap_y; ++uy)
+          for (int ux = 0; ux < p.ntap_x; ++ux)
+            for (int s = 0; s < p.nseg; ++s)
+              for (int ch = 0; ch < p.seg_chunks[s]; ++ch, ++kb) {
+                mbar_wait(bar_empty(stage), phase ^ 1);
+                mbar_expect_tx(bar_full(stage), TC_A_BYTES + 2 * B_BYTES);   // raw A + Bhi + Blo
+                if (p.mode_patch)
+                  tma_load_5d(a_hi(stage), &maps.a[s], bar_full(stage), ch * TC_KB, ux, tx0, uy, n * p.Hs + ty0);
+                else
+                  tma_load_4d(a_hi(stage), &maps.a[s], bar_full(stage), ch * TC_KB, tx0 + ux * p.ux_step + p.x_off,
+                              ty0 + uy * p.uy_step + p.y_off, n);
+                tma_load_3d(b_hi(stage), &maps.bhi, bar_full(stage), 0, nt * BN, kb);
+                tma_load_3d(b_lo(stage), &maps.blo, bar_full(stage), 0, nt * BN, kb);
+                if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+              }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int stage = 0, ts = 0;
+      uint32_t phase = 0, tphase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1;
+        mbar_wait(bar_acce(buf), acc_phase ^ 1);     // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(bar_full(stage), phase);         // B planes of this stage have landed
+          mbar_wait(bar_aready(ts), tphase);         // A (hi, lo) of this k-block is in tensor memory
+          tc_fence_after();
+          const uint32_t a_col = tmem_base + ACOL0 + (uint32_t)(ts * 2 * KBW);
+#pragma unroll
+          for (int k = 0; k < TC_KB / 8; ++k) {
+            const uint64_t bh = umma_desc_kmajor<ROWB>(b_hi(stage) + k * 32), bl = umma_desc_kmajor<ROWB>(b_lo(stage) + k * 32);
+            tc_mma_tf32_ts(d_tmem, a_col + KBW + 8 * k, bh, IDESC, (kb | k) != 0);   // Alo * Bhi   (small terms first)
+            tc_mma_tf32_ts(d_tmem, a_col + 8 * k, bl, IDESC, 1);                     // Ahi * Blo
+            tc_mma_tf32_ts(d_tmem, a_col + 8 * k, bh, IDESC, 1);                     // Ahi * Bhi
+          }
+          tc_commit(bar_empty(stage));               // B planes of the smem stage are free once these MMAs have read them
+          tc_commit(bar_afree(ts));                  // ... and so is the TMEM stage
+          if (kb == kb_total - 1) tc_commit(bar_accf(buf));
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (++ts == NTA) { ts = 0; tphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 6 || warp >= 10) {
+    // ================= operand conversion: raw fp32 rows in shared memory -> (hi, lo) TF32 columns in TMEM =================
+    // thread = pixel row = TMEM lane (a warp may only touch the lane quarter warp % 4); two warps per quarter share
+    // the KBW channels of a k-block.  One conflict-free LDS.128 per four channels (the TMA swizzle is undone in the
+    // address), the split in registers, tcgen05.st -- no smem -> smem pass, no A-lo plane, no proxy fence.
+    const int quarter = warp & 3, half = warp >= 10 ? 1 : 0;
+    const int r = quarter * 32 + lane;
+    constexpr int CH = KBW / 2;                      // channels per thread and k-block
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    int stage = 0, ts = 0;
+    uint32_t phase = 0, tphase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < kb_total; ++kb) {
+        mbar_wait(bar_full(stage), phase);
+        const uint8_t* row = smem + (size_t)stage * STAGE_BYTES + (size_t)r * ROWB;
+        float4 v[CH / 4];
+#pragma unroll
+        for (int i = 0; i < CH / 4; ++i) {
+          const int c = half * (CH / 4) + i;        // logical 16-byte chunk of the row
+          const int pc = ROWB == 128 ? (c ^ (r & 7)) : (c ^ ((r >> 1) & 3));
+          v[i] = *reinterpret_cast<const float4*>(row + pc * 16);
+        }
+        uint32_t hi[CH], lo[CH];
+#pragma unroll
+        for (int i = 0; i < CH / 4; ++i) {
+          const float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            // the tensor core TRUNCATES a 32-bit TF32 operand to its upper 19 bits (measured: tests/test_gpu_tcts.py,
+            // profiles/r2_c_tcts_probe.json), so the raw fp32 word IS the hi part; lo = x - trunc(x) is exact in
+            // fp32 and is rounded to TF32 so that the dominant residual stays unbiased
+            const uint32_t xb = __float_as_uint(x[e]);
+            hi[4 * i + e] = xb;
+            lo[4 * i + e] = __float_as_uint(tf32_round(x[e] - __uint_as_float(xb & 0xFFFFE000u)));
+          }
+        }
+        mbar_wait(bar_afree(ts), tphase ^ 1);        // the MMAs that read this TMEM stage last time are done
+        tc_fence_after();
+        const uint32_t a_col = lane_base + ACOL0 + (uint32_t)(ts * 2 * KBW) + (uint32_t)(half * CH);
+        if constexpr (CH == 16) { tc_st16(a_col, hi); tc_st16(a_col + KBW, lo); }
+        else { tc_st8(a_col, hi); tc_st8(a_col + KBW, lo); }
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar_aready(ts));
+        mbar_arrive(bar_empty(stage));               // this thread is done reading the raw tile
+        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        if (++ts == NTA) { ts = 0; tphase ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue =================
+    // TMEM -> registers (lane = pixel) -> bias/activation -> per-warp smem staging -> transposed read
+    // (8 lanes = 128 contiguous bytes of one pixel) -> beta / derivative-mask -> coalesced global store.
+    // The read-modify-write operands of the NEXT 32-column chunk are loaded before the current one is
+    // processed, so their DRAM latency overlaps the TMEM drain.
+    const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32)
+    float* stg = reinterpret_cast<float*>(smem + (size_t)TC_STAGES * STAGE_BYTES) + quarter * 32 * TC_EPI_PAD;
+    const bool rmw = (p.beta != 0.f) || (p.mask_y != nullptr);
+    constexpr int NCH = (BN + 31) / 32;           // 32-column chunks per tile (BN == 16: one half-used chunk)
+    constexpr int CW = BN < 32 ? BN : 32;         // columns per chunk
+    constexpr int QPR = CW / 4;                   // float4 quads per pixel row of a chunk
+    constexpr int RPI = 32 / QPR;                 // pixel rows covered per pass of the warp
+    constexpr int NPASS = 32 / RPI;               // passes per chunk (== QPR)
+    const int lq = lane % QPR, lr = lane / QPR;
+
+    struct Coord { int n, ty0, tx0, nt; };
+    auto tile_coord = [&](int tile) {
+      Coord c;
+      c.nt = tile % p.n_tiles_n;
+      const int mt = tile / p.n_tiles_n;
+      c.n = mt / tiles_per_img;
+      const int r = mt - c.n * tiles_per_img;
+      c.ty0 = (r / p.tiles_x) * p.TH; c.tx0 = (r % p.tiles_x) * p.TW;
+      return c;
+    };
+    // element offset of (tile row, GEMM column) in the output tensor
+    auto out_off = [&](const Coord& c, int row, int nb) -> size_t {
+      const int ty = c.ty0 + row / p.TW, tx = c.tx0 + row % p.TW;
+      int cb = nb, oy, ox;
+      if (p.d2s) {
+        const int tap = nb / p.cout_true;
+        cb = nb - tap * p.cout_true;
+        const int dy = tap / p.d2s_s;
+        oy = ty * p.d2s_s + dy; ox = tx * p.d2s_s + (tap - dy * p.d2s_s);
+      } else {
+        oy = p.o0y + p.osy * ty; ox = p.o0x + p.osx * tx;
+      }
+      return (((size_t)c.n * p.Hout + oy) * p.Wout + ox) * p.cout_true + cb;
+    };
+    float4 rm_old[NPASS], rm_y[NPASS];
+    auto prefetch = [&](const Coord& c, int ch) {
+#pragma unroll
+      for (int i = 0; i < NPASS; ++i) {
+        const size_t ob = out_off(c, quarter * 32 + i * RPI + lr, c.nt * BN + ch * 32 + lq * 4);
+        rm_old[i] = (p.beta != 0.f) ? *reinterpret_cast<const float4*>(p.out + ob) : make_float4(0.f, 0.f, 0.f, 0.f);
+        rm_y[i] = (p.mask_y != nullptr) ? ld4(p.mask_y + ob) : make_float4(1.f, 1.f, 1.f, 1.f);
+      }
+    };
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1;
+      const Coord tc = tile_coord(tile);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN);
+#pragma unroll 1
+      for (int ch = 0; ch < NCH; ++ch) {
+        // read-modify-write operands first: their latency overlaps the accumulator wait / TMEM drain
+        if (rmw) prefetch(tc, ch);
+        if (ch == 0) {
+          mbar_wait(bar_accf(buf), acc_phase);
+          tc_fence_after();
+        }
+        const int col0 = tc.nt * BN + ch * 32;    // GEMM column of this chunk
+#pragma unroll
+        for (int h = 0; h < CW / 16; ++h) {
+          uint32_t v[16];
+          tc_ld16(taddr + ch * 32 + h * 16, v);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            int cb = col0 + h * 16 + q4 * 4;
+            if (p.d2s) cb -= (cb / p.cout_true) * p.cout_true;
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float x = __uint_as_float(v[q4 * 4 + e]);
+              if (p.bias != nullptr) x += __ldg(p.bias + cb + e);
+              o[e] = act_fwd(x, p.act);
+            }
+            *reinterpret_cast<float4*>(stg + lane * TC_EPI_PAD + h * 16 + q4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < NPASS; ++i) {
+          const int row = i * RPI + lr;
+          float4 o = *reinterpret_cast<const float4*>(stg + row * TC_EPI_PAD + lq * 4);
+          if (rmw) {
+            o.x += p.beta * rm_old[i].x; o.y += p.beta * rm_old[i].y; o.z += p.beta * rm_old[i].z; o.w += p.beta * rm_old[i].w;
+            if (p.mask_y != nullptr) {
+              o.x *= act_bwd_from_y(rm_y[i].x, p.mask_act); o.y *= act_bwd_from_y(rm_y[i].y, p.mask_act);
+              o.z *= act_bwd_from_y(rm_y[i].z, p.mask_act); o.w *= act_bwd_from_y(rm_y[i].w, p.mask_act);
+            }
+          }
+          const size_t ob = out_off(tc, quarter * 32 + row, col0 + lq * 4);
+          *reinterpret_cast<float4*>(p.out + ob) = o;
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      mbar_arrive(bar_acce(buf));
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -465,6 +772,7 @@ static EncodeTiledFn get_encode() {
 
 struct TcPlan {
   bool ok;
+  bool ts;      // TS form (tcs_gconv_kernel)
   int bn;
   int kbw;
   TcParams p;
@@ -482,11 +790,23 @@ static int pick_bn(int cout) {
   return 0;
 }
 
+// "tcs" (TS form: A operand converted on the way into tensor memory, tcs_gconv_kernel): option / NLT_TCS,
+// 1 = use it wherever the tensor path applies (and from NLT_TCS_KMIN contraction terms on), 0 = SS form only
+int g_opt_tcs = -1;
+static int g_tcs_kmin = -1;
+static bool tcs_enabled() {
+  if (g_opt_tcs < 0) { const char* e = getenv("NLT_TCS"); g_opt_tcs = e ? (atoi(e) != 0) : NLT_TCS_DEFAULT; }
+  if (g_tcs_kmin < 0) { const char* e = getenv("NLT_TCS_KMIN"); g_tcs_kmin = e ? atoi(e) : 64; }
+  return g_opt_tcs == 1;
+}
+
 // Which single-phase GConvK shapes the tensor path takes (everything else stays on the SIMT kernels).
 static TcPlan tc_plan(const GConvK& k) {
   TcPlan pl;
   memset(&pl, 0, sizeof(pl));
   pl.ok = false;
+  const bool ts = tcs_enabled();
+  pl.ts = ts;
   if (k.cout_true % 4 != 0) return pl;
   pl.bn = pick_bn(k.Cout);
   if (pl.bn == 0) return pl;
@@ -500,10 +820,14 @@ static TcPlan tc_plan(const GConvK& k) {
   }
   const int TC_KB = pl.kbw;
   if (!aligned16(k.w)) { /* weights are only read by the pack kernel: no alignment needed */ }
-  // with less than 64 contraction terms the op is a pure stream: the pointwise / fp32 kernels are faster there
-  if (k.ay.nu * k.ax.nu * ctot < 64) return pl;
-  // measured: 16-channel (64-byte-row) K-blocks only pay off from K = 128 up
-  if (pl.kbw == 16 && k.ay.nu * k.ax.nu * ctot < 128) return pl;
+  if (ts) {
+    if (k.ay.nu * k.ax.nu * ctot < g_tcs_kmin) return pl;
+  } else {
+    // with less than 64 contraction terms the op is a pure stream: the pointwise / fp32 kernels are faster there
+    if (k.ay.nu * k.ax.nu * ctot < 64) return pl;
+    // measured: 16-channel (64-byte-row) K-blocks only pay off from K = 128 up
+    if (pl.kbw == 16 && k.ay.nu * k.ax.nu * ctot < 128) return pl;
+  }
   if (k.ay.nu < 1 || k.ax.nu < 1) return pl;
   TcParams& p = pl.p;
   p.N = k.N; p.Hl = k.ay.nt; p.Wl = k.ax.nt;
@@ -544,7 +868,7 @@ static TcPlan tc_plan(const GConvK& k) {
   pl.cout_pad = k.Cout;
   pl.pack_floats = (size_t)p.kb_total * pl.cout_pad * TC_KB;
   {
-    const size_t stage_bytes = 2 * (size_t)TC_BM * TC_KB * 4 + 2 * (size_t)pl.bn * TC_KB * 4;
+    const size_t stage_bytes = (ts ? 1 : 2) * (size_t)TC_BM * TC_KB * 4 + 2 * (size_t)pl.bn * TC_KB * 4;
     int st = (int)((227 * 1024 - TC_EPI_BYTES - 2048) / stage_bytes);
     if (st > TC_MAX_STAGES) st = TC_MAX_STAGES;
     if (st < 2) return pl;
@@ -1010,11 +1334,13 @@ size_t tc_wgrad_ws_floats(const GConvK& k) {
 
 template <int BN>
 static int wg_launch(const WgMaps& maps, const WgPlan& pl, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};     // per device: the attribute is not process-wide
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096);
     if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   dim3 grid(pl.nsplit, pl.p.n_mtiles, pl.p.n_ntiles);
   tc_wgrad_kernel<BN><<<grid, TC_THREADS, pl.smem_bytes, st>>>(maps, pl.p);
@@ -1089,15 +1415,21 @@ size_t tc_workspace_bytes(const GConvK& k) {
 
 template <int BN, int KBW>
 static int tc_launch_bn(const TcMaps& maps, const TcPlan& pl, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gconv_kernel<BN, KBW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024 - 1024);
+  // the opt-in to > 48 KB of dynamic shared memory is a per-device attribute
+  static bool attr_set[2][64] = {{false}};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[pl.ts ? 1 : 0][dev]) {
+    cudaError_t e = pl.ts ? cudaFuncSetAttribute(tcs_gconv_kernel<BN, KBW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 227 * 1024 - 1024)
+                          : cudaFuncSetAttribute(tc_gconv_kernel<BN, KBW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 227 * 1024 - 1024);
     if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[pl.ts ? 1 : 0][dev] = true;
   }
   const int grid = pl.p.total_tiles < 148 ? pl.p.total_tiles : 148;
-  tc_gconv_kernel<BN, KBW><<<grid, TCF_THREADS, pl.smem_bytes, st>>>(maps, pl.p);
+  if (pl.ts) tcs_gconv_kernel<BN, KBW><<<grid, TCF_THREADS, pl.smem_bytes, st>>>(maps, pl.p);
+  else tc_gconv_kernel<BN, KBW><<<grid, TCF_THREADS, pl.smem_bytes, st>>>(maps, pl.p);
   NLT_CUDA_LAUNCH_CHECK("tc_gconv_kernel");
   __atomic_add_fetch(&g_tc_launches, 1ull, __ATOMIC_RELAXED);
   return NLT_OK;

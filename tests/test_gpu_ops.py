@@ -133,8 +133,21 @@ def test_gconv_forward_backward(kind, k, s, H, W, segc, cout, act):
 TC_SHAPES = [g for g in GEOMS if all(c % 16 == 0 for c in g[5]) and g[6] % 16 == 0 and g[3] * g[4] >= 256]
 
 
+@pytest.fixture(params=['ss', 'ts'])
+def tc_form(request):
+    """Both forms of the tcgen05 forward / input-gradient kernel: 'ss' = operands in shared memory after an smem -> smem
+    split (round 1), 'ts' = the activation operand converted on its way into tensor memory (round 2)."""
+    import nlt_native as nat
+    nat.set_option('tcs', 1 if request.param == 'ts' else 0)
+    yield request.param
+    nat.set_option('tcs', int(os.environ.get('NLT_TCS', '%d' % TCS_DEFAULT)))
+
+
+TCS_DEFAULT = 0
+
+
 @pytest.mark.parametrize('kind,k,s,H,W,segc,cout', TC_SHAPES)
-def test_tensor_core_vs_fp32_kernels(kind, k, s, H, W, segc, cout):
+def test_tensor_core_vs_fp32_kernels(kind, k, s, H, W, segc, cout, tc_form):
     """A/B on identical inputs: tcgen05 3xTF32 kernels (forward, input gradients with beta + mask, weight /
     bias gradients) against the fp32-FMA kernels of the same library: relative Frobenius error <= 5e-6."""
     engine, nat = _mods()

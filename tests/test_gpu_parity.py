@@ -66,28 +66,39 @@ def _product_and_masks(over, B, seed, c_extra=0, k_obs=1):
 
 
 def _oracle_grads(params, oc, bt, B, masks=None):
-    """fp64 oracle gradients; with `masks` (product order) the activation derivative follows the product's branch."""
+    """fp64 oracle gradients; with `masks` ([(layer name, bool tensor)] of the product, observation tensors k-major
+    [K*B, ...]) the activation derivative follows the product's branch."""
     ps = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
     bt64 = tuple(t.double() if torch.is_tensor(t) else t for t in bt)
     flips = {'flipped': 0, 'total': 0}
     if masks is not None:
-        it = iter(masks)
-        orig = O.act
+        by_name = {name.split(' ')[0]: mk for name, mk in masks}
+        ctx = {'net': None, 'li': None, 'conv': 0, 'calls': {}}
+        orig_act, orig_layer = O.act, O.apply_layer
+
+        def apply_layer(params_, cfg_, net, li, x):
+            k = ctx['calls'].get((net, li), 0)           # k-th observation through this layer (query: always 0)
+            ctx['calls'][(net, li)] = k + 1
+            ctx.update(net=net, li=li, conv=0, k=k)
+            return orig_layer(params_, cfg_, net, li, x)
 
         def act(x, type_):
             assert type_ == 'leakyrelu'
-            name, mk = next(it)
-            assert mk.shape == x.shape, (name, tuple(mk.shape), tuple(x.shape))
+            mk = by_name['%s.%d.%d' % (ctx['net'], ctx['li'], ctx['conv'])]
+            ctx['conv'] += 1
+            n = x.shape[0]
+            mk = mk[ctx['k'] * n:(ctx['k'] + 1) * n]
+            assert mk.shape == x.shape, (ctx, tuple(mk.shape), tuple(x.shape))
             flips['flipped'] += int(((x.detach() > 0) != mk).sum())
             flips['total'] += mk.numel()
             return _MaskedAct.apply(x, mk)
-        O.act = act
+        O.act, O.apply_layer = act, apply_layer
     try:
         pred, gt, _, _ = O.model_call(ps, oc, bt64, 'train')
         (O.l2_loss(gt, pred, keep_batch=True).sum() / B).backward()
     finally:
         if masks is not None:
-            O.act = orig
+            O.act, O.apply_layer = orig_act, orig_layer
     return pred.detach(), {k: v.grad for k, v in ps.items()}, flips
 
 
@@ -167,18 +178,19 @@ def test_three_amsgrad_steps_on_the_default_path():
                                           (dict(uvh=256, uvw=256, imh=256, imw=256, depth=1024), 2, 1)])
 def test_model_backward_k_observations_and_depth_1024(over, k_obs, B):
     """Model-level forward + backward for the cfg3 ingredients: K > 1 observations through Model.call (mean over K
-    and its adjoint) and the 18-layer depth-1024 network.  fp32-FMA kernels, strict bars."""
+    and its adjoint) and the 18-layer depth-1024 network, on the DEFAULT path.  Strict bar (1e-4) against the oracle
+    that differentiates through the product's LeakyReLU branches: at the 1x1 .. 4x4 bottleneck levels of the
+    depth-1024 network one flipped derivative bit moves a bias gradient by a percent, which says nothing about the
+    kernels."""
     import nlt_native as nat
-    nat.set_option('tc', 0)
-    try:
-        m, oc, bt, params, _, pred, per = _product_and_masks(over, B, seed=77, k_obs=k_obs)
-        p64, g64, _ = _oracle_grads(params, oc, bt, B)
-    finally:
-        nat.set_option('tc', 1)
+    nat.set_option('tc', 1)
+    m, oc, bt, params, masks, pred, per = _product_and_masks(over, B, seed=77, k_obs=k_obs)
+    p64, g64, flips = _oracle_grads(params, oc, bt, B, masks)
     assert float((pred.double().cpu() - p64).abs().max()) <= 2e-5
     grads = m.export_grads()
     worst = max((rel_fro(grads[k], g64[k]), k) for k in params)
-    assert worst[0] <= 1e-4, worst
+    assert worst[0] <= 1e-4, (worst, flips)
+    assert flips['flipped'] <= 1e-4 * flips['total'] + 2, flips
 
 
 def test_full_size_sample_1024_forward_backward():
