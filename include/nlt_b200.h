@@ -204,6 +204,25 @@ int nlt_amsgrad_step(float* p, const float* g, float* m, float* v, float* vhat,
                      int64_t n, int32_t step, float lr, float beta1,
                      float beta2, float eps, float grad_scale, void* stream);
 
+/* Normalisation layers of the conv blocks (conv -> norm -> act, nlt/networks/convnet.py:50-59, 67-76), each fused
+ * with the activation that follows it.  x, y, dz, dx: [pixels or N*HW][C] NHWC rows, C % 4 == 0.
+ *   pixel    (nlt/networks/elements.py:103-121): y = act(x * rsqrt(mean_c(x^2) + 1e-8)); no parameters.
+ *            _bwd: dx from dz = d(loss)/d(norm output) (the activation's derivative is applied by the consumer
+ *            from the saved output, as for every other op).
+ *   instance (elements.py:97-100, tf.contrib.layers.instance_norm(center=True, scale=True, epsilon=1e-6)):
+ *            y = act(gamma * (x - mean_hw) * rsqrt(var_hw + eps) + beta), statistics per sample and channel
+ *            (biased variance); _fwd also returns mean / rstd [N*C] for the backward pass; _bwd writes dx and
+ *            (accumulate ? adds to : overwrites) dgamma / dbeta [C].  Deterministic (fixed-order reductions).
+ *            workspace >= nlt_instnorm_workspace_bytes(). */
+int nlt_pixelnorm_fwd(const float* x, int64_t pixels, int32_t C, int act, float* y, void* stream);
+int nlt_pixelnorm_bwd(const float* x, const float* dz, int64_t pixels, int32_t C, float* dx, void* stream);
+int64_t nlt_instnorm_workspace_bytes(int32_t N, int32_t HW, int32_t C);
+int nlt_instnorm_fwd(const float* x, const float* gamma, const float* beta, int32_t N, int32_t HW, int32_t C, int act,
+                     float eps, float* y, float* mean, float* rstd, void* workspace, void* stream);
+int nlt_instnorm_bwd(const float* x, const float* dz, const float* gamma, const float* mean, const float* rstd,
+                     int32_t N, int32_t HW, int32_t C, float* dx, float* dgamma, float* dbeta, int accumulate,
+                     void* workspace, void* stream);
+
 /* Diagnostic (tests/test_gpu_tcts.py): out[128 x bn] = A[128 x 16] * B[bn x 16]^T through the TS form of
  * tcgen05.mma (A operand written to tensor memory with tcgen05.st, B in shared memory); bn = 16 or 32.
  * A is fed unrounded, so the result shows how the tensor core treats the low 13 mantissa bits of fp32 inputs. */

@@ -416,6 +416,100 @@ class ConvLayer:
         y.grad = None   # dz is dead: release it
 
 
+class NormLayer:
+    """`norm(type)` + the activation that follows it in a block (nlt/networks/convnet.py:50-59, 67-76):
+    'pixel' (elements.py:103-121, no parameters) or 'instance' (elements.py:97-100: per-sample, per-channel
+    statistics over H x W, eps 1e-6, learnable scale `kernel` (gamma, ones) and centre `bias` (beta, zeros)).
+    The conv in front of it runs without activation; this op applies norm and activation in one pass and its
+    backward turns d(norm output) into d(conv output)."""
+    EPS_INSTANCE = 1.0e-6
+
+    def __init__(self, kind, act=None):
+        assert kind in ('pixel', 'instance')
+        self.kind, self.act = kind, act
+        self.has_params = kind == 'instance'
+        self.cout = None
+        self.name = kind + 'norm'
+        self.kernel = self.bias = self.gkernel = self.gbias = None
+        self.grad_written = False
+        self._ws = None
+
+    @property
+    def built(self):
+        return self.cout is not None
+
+    def build(self, C, device, generator=None):
+        self.cout = C
+        if self.has_params:
+            self.kernel = torch.ones(C, dtype=torch.float32, device=device)
+            self.bias = torch.zeros(C, dtype=torch.float32, device=device)
+            self.gkernel, self.gbias = torch.zeros_like(self.kernel), torch.zeros_like(self.bias)
+        return C
+
+    def _workspace(self, N, HW, C, device):
+        need = nat.lib().nlt_instnorm_workspace_bytes(N, HW, C)
+        if need < 0:
+            nat.check(-1)
+        if self._ws is None or self._ws.numel() * 4 < need or self._ws.device != device:
+            self._ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=device)
+        return self._ws
+
+    def forward(self, x, tape=None):
+        lib = nat.lib()
+        t = x.t
+        N, H, W, C = t.shape
+        if not self.built:
+            self.build(C, t.device)
+        if C != self.cout:
+            raise ValueError('norm built for %d channels, got %d' % (self.cout, C))
+        y = torch.empty_like(t)
+        act = nat.ACT_CODES[self.act]
+        saved = None
+        if self.kind == 'pixel':
+            PROF.run('fwd ' + self.name, 8 * t.numel(), lambda: nat.check(
+                lib.nlt_pixelnorm_fwd(nat.ptr(t), N * H * W, C, act, nat.ptr(y), nat.stream())))
+        else:
+            mean = torch.empty(N * C, dtype=torch.float32, device=t.device)
+            rstd = torch.empty_like(mean)
+            ws = self._workspace(N, H * W, C, t.device)
+            PROF.run('fwd ' + self.name, 12 * t.numel(), lambda: nat.check(lib.nlt_instnorm_fwd(
+                nat.ptr(t), nat.ptr(self.kernel), nat.ptr(self.bias), N, H * W, C, act, self.EPS_INSTANCE, nat.ptr(y),
+                nat.ptr(mean), nat.ptr(rstd), nat.ptr(ws), nat.stream())))
+            saved = (mean, rstd)
+        out = Act(y, act=self.act, needs_grad=tape is not None)
+        if tape is not None:
+            if x.needs_grad:
+                x.n_cons += 1
+            tape.record(lambda: self._backward(x, out, saved))
+        return out
+
+    def _backward(self, x, out, saved):
+        lib = nat.lib()
+        settle(out)
+        dz = out.grad
+        if dz is None or not x.needs_grad:
+            return
+        t = x.t
+        N, H, W, C = t.shape
+
+        def write(o, beta, mask, mask_act, term):
+            # the conv in front has no activation of its own and this op is its only consumer
+            assert beta == 0.0 and mask is None and term is None
+            if self.kind == 'pixel':
+                PROF.run('dgrad ' + self.name, 12 * t.numel(), lambda: nat.check(
+                    lib.nlt_pixelnorm_bwd(nat.ptr(t), nat.ptr(dz), N * H * W, C, nat.ptr(o), nat.stream())))
+            else:
+                mean, rstd = saved
+                ws = self._workspace(N, H * W, C, t.device)
+                acc = 1 if self.grad_written else 0
+                PROF.run('dgrad ' + self.name, 20 * t.numel(), lambda: nat.check(lib.nlt_instnorm_bwd(
+                    nat.ptr(t), nat.ptr(dz), nat.ptr(self.kernel), nat.ptr(mean), nat.ptr(rstd), N, H * W, C, nat.ptr(o),
+                    nat.ptr(self.gkernel), nat.ptr(self.gbias), acc, nat.ptr(ws), nat.stream())))
+                self.grad_written = True
+        contribute(x, write)
+        out.grad = None
+
+
 def kmean(obs_y, K, tape=None, weights=None):
     """mean over the K stacked observations (nlt/models/nlt.py:161-164).
     obs_y: Act [K*B,H,W,C] (k-major).  K == 1 aliases (no kernel, no copy)."""

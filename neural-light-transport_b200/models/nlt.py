@@ -91,21 +91,28 @@ class Model(BaseModel):
                 if skips:
                     q_in += skips.pop()
                 q_in = blk.build(q_in, self.device, gen)
-        convs = q.conv_layers()
-        for blk in o.layers:
-            convs += blk.convs
+        # everything that owns parameters (convs, and the norm layers of `norm = instance`), in registration order
+        layers = q.param_layers() + o.param_layers()
         # flat layout = the order in which backward() produces the weight gradients: decoder blocks top-down, then
-        # per encoder level (bottom-up) the query block followed by the observation block, second conv first
-        index = {id(c): i for i, c in enumerate(convs)}
+        # per encoder level (bottom-up) the query block followed by the observation block, last layer first
+        index = {id(c): i for i, c in enumerate(layers)}
         produced = []
         n_q = len(q.layers)
         for li in range(n_q - 1, -1, -1):
-            produced += [index[id(c)] for c in reversed(q.layers[li].convs)]
+            produced += [index[id(c)] for _, c in reversed(q.layers[li].param_layers())]
             if q.is_contracting[li]:
-                produced += [index[id(c)] for c in reversed(o.layers[li].convs)]
-        self._bucket = ParamBucket(convs, self.device, layout=produced)
+                produced += [index[id(c)] for _, c in reversed(o.layers[li].param_layers())]
+        self._bucket = ParamBucket(layers, self.device, layout=produced)
         for name, c in self.named_convs():   # profiler labels: 'query.1.0 conv2x2/s2 32->16'
-            c.name = '%s %s%dx%d/s%d %d->%d' % (name, c.kind, c.k, c.k, c.s, c.cin, c.cout)
+            if hasattr(c, 'kind') and c.kind in ('conv', 'deconv'):
+                c.name = '%s %s%dx%d/s%d %d->%d' % (name, c.kind, c.k, c.k, c.s, c.cin, c.cout)
+            else:
+                c.name = '%s %snorm %d' % (name, c.kind, c.cout)
+        for net in ('query', 'obs'):         # parameter-free norm layers get labels too
+            for li, blk in enumerate(self.net[net].layers):
+                for ci, nm in enumerate(blk.norms):
+                    if nm is not None and not nm.has_params:
+                        nm.name = '%s.%d.%d.norm %snorm %d' % (net, li, ci, nm.kind, nm.cout)
 
     @property
     def trainable_variables(self):
@@ -130,12 +137,13 @@ class Model(BaseModel):
         return self._bucket
 
     def named_convs(self):
-        """('query.3.0', ConvLayer) in registration order."""
+        """('query.3.0', ConvLayer) -- and ('query.3.0.norm', NormLayer) for `norm = instance`, whose scale / centre
+        vectors ride in the `kernel` / `bias` slots -- in registration order."""
         out = []
         for net in ('query', 'obs'):
             for li, blk in enumerate(self.net[net].layers):
-                for ci, c in enumerate(blk.convs):
-                    out.append(('%s.%d.%d' % (net, li, ci), c))
+                for suffix, c in blk.param_layers():
+                    out.append(('%s.%d.%s' % (net, li, suffix), c))
         return out
 
     def load_params(self, params):

@@ -5,7 +5,7 @@ conv + norm + act triple of the reference is executed as ONE fused CUDA op
 (bias and activation live in the conv epilogue), so `norm`/`act`/`iden`
 return markers rather than callable layers.
 """
-from engine import ConvLayer
+from engine import ConvLayer, NormLayer  # noqa: F401
 
 
 def conv(kernel_size, n_ch_out, stride=1):
@@ -23,11 +23,14 @@ def upconv(n_ch_out):
 
 
 def norm(type_):
+    """None -> identity; 'pixel' / 'instance' -> the kind of engine.NormLayer a block inserts between each conv and
+    its activation.  'batch' couples the samples of a batch (the data-parallel split would change its statistics) and
+    'layer' is unshipped: both stay NotImplementedError."""
     if type_ is None or type_.lower() == 'none':
         return None
-    if type_ in ('batch', 'layer', 'instance', 'pixel'):
-        # 'instance' raises in the reference too (tf.contrib is gone in TF2,
-        # elements.py:97-100); batch/layer/pixel are unshipped options.
+    if type_ in ('pixel', 'instance'):
+        return type_
+    if type_ in ('batch', 'layer'):
         raise NotImplementedError('norm=%s is not on the accelerated path' % type_)
     raise NotImplementedError(type_)
 

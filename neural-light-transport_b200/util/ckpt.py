@@ -26,8 +26,9 @@ def _named(model):
     out = []
     for net_name, net in model.net.items():
         for li, blk in enumerate(net.layers):
-            for ci, c in enumerate(blk.convs):
-                out.append(('net/net_%s_layer%d/conv%d' % (net_name, li, ci), c))
+            for suffix, c in blk.param_layers():          # '0', '1', and '0.norm' / '1.norm' for norm = instance
+                ci, _, nm = suffix.partition('.')
+                out.append(('net/net_%s_layer%d/%s%s' % (net_name, li, 'norm' if nm else 'conv', ci), c))
     return out
 
 

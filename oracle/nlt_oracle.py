@@ -120,13 +120,22 @@ def act(x, type_):
     raise NotImplementedError(type_)
 
 
-def norm(x, type_):
-    """elements.py:51-66 (None and 'pixel' only; the others are outside the
-    oracle: 'instance' is broken upstream (D2), batch/layer unshipped)."""
+def norm(x, type_, gamma=None, beta=None):
+    """elements.py:51-66: None, 'pixel' (:103-121) and 'instance' (:97-100).  The instance branch restates
+    tf.contrib.layers.instance_norm(center=True, scale=True, epsilon=1e-6) -- per sample and channel over H x W, biased
+    variance; upstream that call does not exist in TF 2.2, so this branch pins only this repo's own
+    kernels.  'batch' / 'layer' are unshipped and outside the oracle."""
     if type_ is None or str(type_).lower() == 'none':
         return x
     if type_ == 'pixel':         # elements.py:103-121
         return x * torch.rsqrt((x * x).mean(dim=3, keepdim=True) + 1.0e-8)
+    if type_ == 'instance':
+        mean = x.mean(dim=(1, 2), keepdim=True)
+        var = ((x - mean) ** 2).mean(dim=(1, 2), keepdim=True)
+        y = (x - mean) * torch.rsqrt(var + 1.0e-6)
+        if gamma is not None:
+            y = y * gamma + beta
+        return y
     raise NotImplementedError(type_)
 
 
@@ -244,6 +253,12 @@ def init_params(cfg, c_query=5, c_obs=3, seed=0, dtype=torch.float32,
                 b = (torch.rand((cout,), generator=g, dtype=torch.float64) * 2 - 1) * bias_range
                 params['%s.%d.%d.kernel' % (net, li, ci)] = w.to(dtype)
                 params['%s.%d.%d.bias' % (net, li, ci)] = b.to(dtype)
+                if str(cfg.get('norm', 'None')) == 'instance' and len(convs) == 2:
+                    # scale ~ 1, centre ~ 0 (tf.contrib defaults are exactly 1 / 0; perturbed so both are exercised)
+                    params['%s.%d.%d.norm.kernel' % (net, li, ci)] = \
+                        (1.0 + 0.2 * (torch.rand((cout,), generator=g, dtype=torch.float64) - 0.5)).to(dtype)
+                    params['%s.%d.%d.norm.bias' % (net, li, ci)] = \
+                        (0.2 * (torch.rand((cout,), generator=g, dtype=torch.float64) - 0.5)).to(dtype)
     return params
 
 
@@ -261,11 +276,13 @@ def apply_layer(params, cfg, net, li, x):
     b = lambda ci: params['%s.%d.%d.bias' % (net, li, ci)]
     if kind == 'conv1x1':
         return conv2d_same(x, w(0), b(0), 1)
+    g = lambda ci: params.get('%s.%d.%d.norm.kernel' % (net, li, ci))     # instance norm: scale / centre
+    bt = lambda ci: params.get('%s.%d.%d.norm.bias' % (net, li, ci))
     if kind == 'down':
-        x = act(norm(conv2d_same(x, w(0), b(0), s), nm), a)
-        return act(norm(conv2d_same(x, w(1), b(1), 1), nm), a)
-    x = act(norm(conv2d_transpose_same(x, w(0), b(0), s), nm), a)
-    return act(norm(conv2d_transpose_same(x, w(1), b(1), 1), nm), a)
+        x = act(norm(conv2d_same(x, w(0), b(0), s), nm, g(0), bt(0)), a)
+        return act(norm(conv2d_same(x, w(1), b(1), 1), nm, g(1), bt(1)), a)
+    x = act(norm(conv2d_transpose_same(x, w(0), b(0), s), nm, g(0), bt(0)), a)
+    return act(norm(conv2d_transpose_same(x, w(1), b(1), 1), nm, g(1), bt(1)), a)
 
 
 def net_call(params, cfg, query_x, obs_xs, obs_weights=None, obs_override=None):

@@ -38,7 +38,14 @@ def test_network_structure_matches_reference_wiring():
     assert len(sss.layers) == 18
     with pytest.raises(AssertionError):
         convnet.Network(16, 256, 2, 2, norm_type=None)          # str2none asserts on non-strings
-    for bad in (dict(norm_type='instance'), dict(pool_type='max'), dict(act_type='gelu')):
+    # norm = pixel / instance: conv -> norm -> act, the activation moves into the norm op (convnet.py:50-59)
+    for kind in ('pixel', 'instance'):
+        nn_ = convnet.Network(16, 256, 2, 2, norm_type=kind, act_type='leakyrelu', pool_type='None')
+        blk = nn_.layers[3]
+        assert [c.act for c in blk.convs] == [None, None]
+        assert [(n.kind, n.act, n.has_params) for n in blk.norms] == [(kind, 'leakyrelu', kind == 'instance')] * 2
+        assert nn_.layers[0].norms == [None] and nn_.layers[13].norms == [None]     # bare 1x1 convs (:44, :85)
+    for bad in (dict(norm_type='batch'), dict(norm_type='layer'), dict(pool_type='max'), dict(act_type='gelu')):
         kw = dict(norm_type='None', act_type='relu', pool_type='None')
         kw.update(bad)
         with pytest.raises(NotImplementedError):
