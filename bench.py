@@ -263,11 +263,13 @@ class TrainRun:
             tc += steps * self.graphed.captured_tc_launches
         return ms, launches, tc
 
-    def measure_e2e(self, steps):
-        """pinned host inputs -> H2D each step (copy stream, overlapped with the previous step) -> loss read back"""
+    def measure_e2e(self, steps, uint8=False):
+        """pinned host inputs -> H2D each step (copy stream, overlapped with the previous step) -> loss read back.
+        uint8: the image tensors of the batch travel as bytes (datasets `uint8_inputs`), normalised on the device."""
+        from util import synth
         copy_stream = torch.cuda.Stream()
         state = {}
-        host, dev = self.host, self.dev
+        host, dev = ([synth.as_uint8(b) for b in self.host] if uint8 else self.host), self.dev
 
         def prefetch(i):
             with torch.cuda.stream(copy_stream):
@@ -493,6 +495,7 @@ def run_b200(args):
 
     # ---- end-to-end arm ----
     ms_e2e, h2d_bytes = run.measure_e2e(args.steps)
+    ms_e2e_u8, h2d_bytes_u8 = run.measure_e2e(args.steps, uint8=True)
 
     # ---- roofline leg ----
     summ = run.per_op(rank)       # every rank runs these steps (they contain the gradient all-reduce)
@@ -575,7 +578,12 @@ def run_b200(args):
             'e2e': {'value': texels_step / (ms_e2e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e,
                     'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
                     'note': 'float32 host buffers (the reference tuple\'s dtypes) copied H2D every step on a copy '
-                            'stream; the loss (4 bytes) is the result read back -- a train step returns nothing else'},
+                            'stream; the loss (4 bytes) is the result read back -- a train step returns nothing else',
+                    'uint8_inputs': {'value': texels_step / (ms_e2e_u8 * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e_u8,
+                                     'h2d_bytes_per_step': h2d_bytes_u8,
+                                     'note': 'same call with the image tensors as uint8 PNG samples (datasets '
+                                             'uint8_inputs = True; v / 255 on the device, bit-identical results); the '
+                                             'float32 number above is bounded by PCIe (h2d bytes / step time)'}},
             'gpu_launches': launches, 'tcgen05_launches': tc_launches, 'clocks': clocks, 'parity': parity,
             'roofline': roof, 'cpu_baseline': cpu,
         }

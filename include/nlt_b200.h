@@ -228,6 +228,10 @@ int nlt_instnorm_bwd(const float* x, const float* dz, const float* gamma, const 
  * A is fed unrounded, so the result shows how the tensor core treats the low 13 mantissa bits of fp32 inputs. */
 int nlt_debug_tcts_probe(const float* A, const float* B, int32_t bn, float* out, void* stream);
 
+/* uint8 image samples -> float32 in [0, 1] (v / 255, correctly rounded = the host pipeline's
+ * float32(v / 255.0), nlt/datasets/nlt.py:134-139): lets a batch cross PCIe as bytes. */
+int nlt_u8_to_f32(const uint8_t* in, int64_t n, float* out, void* stream);
+
 /* acc[i] += sum_k in[k*per_sample + i]  -- running per-level sum of the observation features over the samples
  * of a batch (the concat + tf.reduce_mean(axis=0) of nlt/nlt_test.py:114-124 without holding every sample). */
 int nlt_ksum_acc(const float* in, int32_t K, int64_t per_sample, float* acc, void* stream);

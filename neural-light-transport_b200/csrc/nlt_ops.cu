@@ -347,6 +347,24 @@ __global__ void mul_kernel(const float* __restrict__ a, const float* __restrict_
     out[i] = __ldg(a + i) * __ldg(b + i);
 }
 
+// uint8 image bytes (PNG samples) -> float32 in [0, 1]: out = v / 255, correctly rounded -- bit-identical to the
+// host pipeline's float32(v / 255.0) for all 256 values (nlt/datasets/nlt.py:134-139 via xiuminglib normalize_uint)
+__global__ void u8_to_f32_kernel(const uint8_t* __restrict__ in, size_t n, float* __restrict__ out) {
+  const size_t n16 = n / 16;
+  const uint4* in16 = reinterpret_cast<const uint4*>(in);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(in16 + i);
+    const unsigned int w[4] = {v.x, v.y, v.z, v.w};
+    float4* o = reinterpret_cast<float4*>(out + i * 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      o[j] = make_float4(__fdiv_rn((float)(w[j] & 0xffu), 255.f), __fdiv_rn((float)((w[j] >> 8) & 0xffu), 255.f),
+                         __fdiv_rn((float)((w[j] >> 16) & 0xffu), 255.f), __fdiv_rn((float)(w[j] >> 24), 255.f));
+  }
+  for (size_t i = n16 * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __fdiv_rn((float)in[i], 255.f);
+}
+
 // Same update with the step counter ON THE DEVICE, so that the optimiser launch can live inside a captured CUDA
 // graph (a host-computed bias-corrected learning rate would be frozen into the graph at capture time).
 // `step` holds the number of updates applied so far; it is advanced by amsgrad_step_inc_kernel right before.
@@ -525,6 +543,14 @@ int nlt_mul(const float* a, const float* b, int64_t n, float* out, void* stream)
   NLT_CHECK_ARG(a && b && out && n > 0, "mul: bad argument");
   mul_kernel<<<grid_for((size_t)n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, (size_t)n, out);
   NLT_CUDA_LAUNCH_CHECK("mul_kernel");
+  return NLT_OK;
+}
+
+int nlt_u8_to_f32(const uint8_t* in, int64_t n, float* out, void* stream) {
+  NLT_CHECK_ARG(in && out && n > 0, "u8_to_f32: bad argument");
+  NLT_CHECK_ARG((((uintptr_t)in) & 15) == 0 && (((uintptr_t)out) & 15) == 0, "u8_to_f32: pointers must be 16-byte aligned");
+  u8_to_f32_kernel<<<grid_for((size_t)n / 16 + 1, 256), 256, 0, (cudaStream_t)stream>>>(in, (size_t)n, out);
+  NLT_CUDA_LAUNCH_CHECK("u8_to_f32_kernel");
   return NLT_OK;
 }
 

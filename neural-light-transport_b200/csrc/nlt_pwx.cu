@@ -96,24 +96,35 @@ __device__ __forceinline__ void pwx_zero_rows(const PwxParams& p, float* xs, uin
 // ---------------------------------------------------------------------------------------------
 constexpr int PWX_OROW = 20;        // floats per staged output row (16 + 4: conflict-free STS.128 per pixel)
 
-__global__ void __launch_bounds__(PWX_THREADS, 1)
-pwx_fwd_kernel(const PwxParams p, const float* __restrict__ w, long long wc, long long wn,
-               const float* __restrict__ bias, const int act, float* __restrict__ out) {
-  extern __shared__ __align__(16) float smem[];
-  const int npair = p.K4 * 2;                                  // channel pairs
-  float* wp = smem;                                            // [npair][16][2]
-  float* xs0 = wp + npair * 32;
-  float* xs1 = xs0 + PWX_T * p.krow;
-  float* so = xs1 + PWX_T * p.krow;                            // [PWX_T][PWX_OROW]
-  const int tid = threadIdx.x;
+// The [K x 16] weight matrix lives in CONSTANT memory as (even, odd) channel pairs: every lane of a warp needs the same
+// weight at the same time, so it is fetched by the uniform datapath (LDCU -> uniform registers -> FFMA2 R, R, UR, R)
+// and costs neither an LSU slot nor a shared-memory wavefront.  ncu on the shared-memory version of this kernel
+// (profiles/r2_e_*): 272 broadcast LDS.128 per pixel kept the LSU pipe 58 % busy and the FFMA2s waiting on them
+// (short scoreboard) at 34 % issue utilisation.
+constexpr int PWX_CW_PAIRS = 64;                                   // K <= 128
+__constant__ float2 pwx_cw[PWX_CW_PAIRS * 16];                     // [pair][n] = (W[c_even][n], W[c_odd][n])
+__device__ float2 pwx_cw_stage[PWX_CW_PAIRS * 16];                 // written by the pack kernel, copied into pwx_cw
 
-  // weights as (even, odd) channel pairs in smem column order; pad columns contribute zero
-  for (int i = tid; i < npair * 16; i += PWX_THREADS) {
+__global__ void pwx_pack_w_kernel(const PwxParams p, const float* __restrict__ w, long long wc, long long wn) {
+  const int npair = p.K4 * 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npair * 16; i += gridDim.x * blockDim.x) {
     const int cp = i >> 4, n = i & 15;
     const int c0 = p.col_c[2 * cp], c1 = p.col_c[2 * cp + 1];
-    wp[i * 2 + 0] = c0 >= 0 ? __ldg(w + (long long)c0 * wc + (long long)n * wn) : 0.f;
-    wp[i * 2 + 1] = c1 >= 0 ? __ldg(w + (long long)c1 * wc + (long long)n * wn) : 0.f;
+    pwx_cw_stage[i] = make_float2(c0 >= 0 ? __ldg(w + (long long)c0 * wc + (long long)n * wn) : 0.f,
+                                  c1 >= 0 ? __ldg(w + (long long)c1 * wc + (long long)n * wn) : 0.f);
   }
+}
+
+template <int K4>
+__global__ void __launch_bounds__(PWX_THREADS, 1)
+pwx_fwd_kernel(const PwxParams p, const float* __restrict__ bias, const int act, float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int KROW = K4 * 4 + 4;
+  float* xs0 = smem;
+  float* xs1 = xs0 + PWX_T * KROW;
+  float* so = xs1 + PWX_T * KROW;                              // [PWX_T][PWX_OROW]
+  const int tid = threadIdx.x;
+
   pwx_zero_rows(p, xs0, 0);
   pwx_zero_rows(p, xs1, 0);
   float bv[16];
@@ -140,20 +151,15 @@ pwx_fwd_kernel(const PwxParams p, const float* __restrict__ w, long long wc, lon
     float2 acc[16];
 #pragma unroll
     for (int n = 0; n < 16; ++n) acc[n] = make_float2(bv[n], 0.f);
-    const float4* xrow = reinterpret_cast<const float4*>(xs + tid * p.krow);
-    const float4* wq = reinterpret_cast<const float4*>(wp);
-#pragma unroll 2
-    for (int q = 0; q < p.K4; ++q) {
+    const float4* xrow = reinterpret_cast<const float4*>(xs + tid * KROW);
+#pragma unroll
+    for (int q = 0; q < K4; ++q) {
       const float4 xv = xrow[q];
       const float2 xa = make_float2(xv.x, xv.y), xb = make_float2(xv.z, xv.w);
 #pragma unroll
-      for (int h = 0; h < 8; ++h) {
-        const float4 wa = wq[(2 * q) * 8 + h];                 // pair 2q:   (n = 2h), (n = 2h+1)
-        const float4 wb = wq[(2 * q + 1) * 8 + h];             // pair 2q+1
-        acc[2 * h] = __ffma2_rn(xa, make_float2(wa.x, wa.y), acc[2 * h]);
-        acc[2 * h + 1] = __ffma2_rn(xa, make_float2(wa.z, wa.w), acc[2 * h + 1]);
-        acc[2 * h] = __ffma2_rn(xb, make_float2(wb.x, wb.y), acc[2 * h]);
-        acc[2 * h + 1] = __ffma2_rn(xb, make_float2(wb.z, wb.w), acc[2 * h + 1]);
+      for (int n = 0; n < 16; ++n) {
+        acc[n] = __ffma2_rn(xa, pwx_cw[(2 * q) * 16 + n], acc[n]);
+        acc[n] = __ffma2_rn(xb, pwx_cw[(2 * q + 1) * 16 + n], acc[n]);
       }
     }
     float o[16];
@@ -173,8 +179,8 @@ pwx_fwd_kernel(const PwxParams p, const float* __restrict__ w, long long wc, lon
       const uint32_t px = qi >> 2, j = qi & 3;
       if (px < npx) dst[qi] = *reinterpret_cast<const float4*>(so + px * PWX_OROW + 4 * j);
     }
-    // so is rewritten only after the next tile's first barrier, xs[buf] after this loop's top-of-iteration staging of
-    // tile t + 2*grid, which follows that barrier too: one more barrier is not needed
+    // so is rewritten only after the next tile's first barrier, xs[buf] after the staging at the top of the iteration
+    // that follows it: one more barrier is not needed
   }
   cp_async_wait<0>();
 }
@@ -352,8 +358,8 @@ static bool pwx_build(const GConvK& k, bool for_wgrad, PwxParams* p, int* kd_pad
     }
   p->K = K;
   int K4 = (off + 3) / 4;
-  if (for_wgrad) K4 = (K4 + 7) / 8 * 8;           // lanes cover 8 groups per step
-  else K4 = (K4 + 0);
+  K4 = (K4 + 7) / 8 * 8;            // wgrad: lanes cover 8 groups per step; forward: instantiated for 8, 16, 24, 32
+  (void)for_wgrad;
   if (K4 * 4 > PWX_KMAX) return false;
   p->K4 = K4;
   p->krow = K4 * 4 + 4;
@@ -366,7 +372,7 @@ static bool pwx_build(const GConvK& k, bool for_wgrad, PwxParams* p, int* kd_pad
 }
 
 static size_t pwx_fwd_smem(const PwxParams& p) {
-  return ((size_t)p.K4 * 2 * 32 + 2 * (size_t)PWX_T * p.krow + (size_t)PWX_T * PWX_OROW) * sizeof(float);
+  return (2 * (size_t)PWX_T * p.krow + (size_t)PWX_T * PWX_OROW) * sizeof(float);
 }
 static size_t pwx_wgrad_smem(const PwxParams& p) {
   const size_t stage = (2 * (size_t)PWX_T * p.krow + 2 * (size_t)PWX_T * 32) * sizeof(float);
@@ -387,22 +393,41 @@ bool pwx_fwd_applicable(const GConvK& k, float beta, const float* mask_y, const 
   return pwx_build(k, false, &p, nullptr, nullptr, nullptr) && pwx_fwd_smem(p) <= PWX_SMEM_MAX;
 }
 
+template <int K4>
+static int pwx_fwd_launch(const PwxParams& p, const float* bias, int act, float* out, size_t smem, cudaStream_t st) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static bool attr_set[64] = {false};
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(pwx_fwd_kernel<K4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PWX_SMEM_MAX);
+    if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  const unsigned grid = p.ntiles < 148u ? p.ntiles : 148u;
+  pwx_fwd_kernel<K4><<<grid, PWX_THREADS, smem, st>>>(p, bias, act, out);
+  NLT_CUDA_LAUNCH_CHECK("pwx_fwd_kernel");
+  return NLT_OK;
+}
+
+// NOTE: the constant-memory weight table is one per device: launches of this forward on DIFFERENT streams of the
+// same device must not overlap (the model issues it from its main stream only).
 int launch_pwx_fwd(const GConvK& k, const float* bias, int act, float* out, cudaStream_t st) {
   PwxParams p;
   if (!pwx_build(k, false, &p, nullptr, nullptr, nullptr)) return set_err(NLT_ERR_INVALID, "pwx_fwd not applicable");
   const size_t smem = pwx_fwd_smem(p);
-  int dev = 0;
-  cudaGetDevice(&dev);
-  static bool attr_set[64] = {false};
-  if (dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(pwx_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PWX_SMEM_MAX);
-    if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set[dev] = true;
+  pwx_pack_w_kernel<<<4, 256, 0, st>>>(p, k.w, k.wc, k.wn);
+  NLT_CUDA_LAUNCH_CHECK("pwx_pack_w_kernel");
+  void* stage = nullptr;
+  cudaError_t e = cudaGetSymbolAddress(&stage, pwx_cw_stage);
+  if (e == cudaSuccess)
+    e = cudaMemcpyToSymbolAsync(pwx_cw, stage, (size_t)p.K4 * 2 * 16 * sizeof(float2), 0, cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "pwx weight table: %s", cudaGetErrorString(e));
+  switch (p.K4) {
+    case 8: return pwx_fwd_launch<8>(p, bias, act, out, smem, st);
+    case 16: return pwx_fwd_launch<16>(p, bias, act, out, smem, st);
+    case 24: return pwx_fwd_launch<24>(p, bias, act, out, smem, st);
+    default: return pwx_fwd_launch<32>(p, bias, act, out, smem, st);
   }
-  const unsigned grid = p.ntiles < 148u ? p.ntiles : 148u;
-  pwx_fwd_kernel<<<grid, PWX_THREADS, smem, st>>>(p, k.w, k.wc, k.wn, bias, act, out);
-  NLT_CUDA_LAUNCH_CHECK("pwx_fwd_kernel");
-  return NLT_OK;
 }
 
 bool pwx_wgrad_applicable(const GConvK& k, const float* G) {

@@ -149,7 +149,9 @@ class DataPipe:
             yield buf.pop()
 
     def _to_tensor(self, arr):
-        t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32))
+        arr = np.asarray(arr)
+        # uint8 stays uint8 (datasets with uint8_inputs: image samples travel as bytes, the model divides on the GPU)
+        t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.uint8 if arr.dtype == np.uint8 else np.float32))
         return t.pin_memory() if self.pin_memory else t
 
     def _collate(self, exs):

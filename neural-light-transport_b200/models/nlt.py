@@ -25,9 +25,16 @@ from .base import Model as BaseModel
 
 def _dev_tensor(x, device):
     """Moves a batch element to the device as contiguous fp32 (inputs may be
-    pinned host tensors: the H2D copy is part of the end-to-end path)."""
+    pinned host tensors: the H2D copy is part of the end-to-end path).
+    uint8 tensors are image samples still in PNG units: they cross PCIe as bytes and become v / 255 on the device
+    (bit-identical to the host pipeline's float32(v / 255.0); datasets with `uint8_inputs = True` emit them)."""
     if not torch.is_tensor(x):
         x = torch.as_tensor(np.asarray(x))
+    if x.dtype == torch.uint8:
+        xd = x.to(device=device, non_blocking=True).contiguous()
+        out = torch.empty(xd.shape, dtype=torch.float32, device=device)
+        nat.check(nat.lib().nlt_u8_to_f32(xd.data_ptr(), xd.numel(), nat.ptr(out), nat.stream()))
+        return out
     if x.device != device or x.dtype != torch.float32:
         x = x.to(device=device, dtype=torch.float32, non_blocking=True)
     return x.contiguous()
@@ -389,7 +396,9 @@ class Model(BaseModel):
         from PIL import Image
         self._validate_mode(mode)
         os.makedirs(outdir, exist_ok=True)
-        to_np = lambda t: t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
+        def to_np(t):
+            a = t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
+            return a.astype(np.float32) / 255 if a.dtype == np.uint8 else a       # uint8_inputs batches
         dec = lambda x: x.decode() if isinstance(x, bytes) else str(x)
         ids = [dec(x) for x in data_dict['id']]
         nn_ids = [dec(x) for x in data_dict['nn_id']]

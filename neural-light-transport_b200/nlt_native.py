@@ -85,6 +85,7 @@ _SIGS = {
     'nlt_instnorm_fwd': (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 3 + [C.c_int, C.c_float] + [C.c_void_p] * 5),
     'nlt_instnorm_bwd': (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 3 + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 2),
     'nlt_debug_tcts_probe': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    'nlt_u8_to_f32': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     'nlt_ksum_acc': (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     'nlt_scale': (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
     'nlt_mul': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

@@ -43,8 +43,8 @@ def extract_feat(model, datapipe, n_obs_batches=1):
     for batch in datapipe:
         _, base, _, _, _, rgb, _, _, _, _, _ = batch
         dev = model.device
-        rgb = rgb.to(dev, torch.float32).contiguous()
-        base = base.to(dev, torch.float32).contiguous()
+        from models.nlt import _dev_tensor
+        rgb, base = _dev_tensor(rgb, dev), _dev_tensor(base, dev)
         # Forward through the observation path; x = rgb - base is formed inside the first conv's operand loader
         segs = [Seg(Act(rgb), sub=base)]
         feat = []

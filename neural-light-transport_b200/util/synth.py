@@ -14,6 +14,21 @@ def _q255(x):
     return torch.round(x * 255.0) / 255.0
 
 
+def as_uint8(batch):
+    """The same batch with every k/255-quantised image tensor as uint8 (what a dataset with `uint8_inputs` emits);
+    the warp stays float32."""
+    out = []
+    for i, t in enumerate(batch):
+        if torch.is_tensor(t) and i != 4:
+            q = torch.round(t * 255.0)
+            assert float((q / 255.0 - t).abs().max()) == 0.0
+            u = q.to(torch.uint8)
+            out.append(u.pin_memory() if t.is_pinned() else u)
+        else:
+            out.append(t)
+    return tuple(out)
+
+
 def make_batch(B, uv, im, seed=1234, device='cpu', c_extra=0, pin=False, k_obs=1):
     """Returns the 11-tuple (id, base, cvis, lvis, warp, rgb, rgb_camspc,
     nn_id, nn_base, nn_rgb, nn_rgb_camspc).  c_extra > 0 widens cvis with

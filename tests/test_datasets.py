@@ -260,3 +260,30 @@ def test_trainvali_batch_source_real_and_synthetic(scene):
     cfg['DEFAULT']['imh'] = '16'
     syn = list(trainvali.batch_source(cfg, types.SimpleNamespace(world=1, rank=0), steps=2, device='cpu'))
     assert len(syn) == 2 and syn[0][1].shape == (2, 16, 16, 3) and not torch.equal(syn[0][1], syn[1][1])
+
+
+def test_uint8_inputs_option_keeps_lossless_images_as_bytes(scene):
+    """`uint8_inputs = True`: an 8-bit image that needs no resize is emitted as uint8 (the model divides by 255 on the
+    device, bit-identical to float32(v / 255.0)); everything that is resized, and the warp, stays float32."""
+    cfg, arrs = scene
+    cfg_native = configparser.ConfigParser()
+    cfg_native['DEFAULT'] = dict(cfg['DEFAULT'], uvh=str(UV_NATIVE), uvw=str(UV_NATIVE), imh=str(CAM_NATIVE[0]),
+                                 imw=str(CAM_NATIVE[1]))
+    id_ = 'trainvali_000000001_cam0_light1'
+    ref = _dataset(cfg_native, 'train')._process_example_precache(id_)
+    u8 = _dataset(cfg_native, 'train', uint8_inputs=True)._process_example_precache(id_)
+    for i, (a, b) in enumerate(zip(ref, u8)):
+        if i in (0, 7):
+            assert a == b
+        elif i == 4:
+            assert b.dtype == np.float32 and np.array_equal(a, b)          # the warp
+        else:
+            assert b.dtype == np.uint8 and a.dtype == np.float32
+            np.testing.assert_array_equal(a, b.astype(np.float32) / np.float32(255))
+    # at a size that needs the cv2 resize nothing is kept as bytes
+    rs = _dataset(cfg, 'train', uint8_inputs=True)._process_example_precache(id_)
+    assert all(t.dtype == np.float32 for t in rs if isinstance(t, np.ndarray))
+    # and the pipeline keeps the dtype through collation
+    pipe = _dataset(cfg_native, 'train', uint8_inputs=True).build_pipeline(seed=0, pin_memory=False)
+    b = next(iter(pipe))
+    assert b[1].dtype == torch.uint8 and b[4].dtype == torch.float32 and b[1].shape[0] == 2

@@ -285,3 +285,18 @@ def test_cfg5_relight_sweep_psnr_vs_oracle(path):
                                             'test', obs_override=want_feat)
             worst = min(worst, O.psnr_luma(got[0].cpu().numpy(), ref[0].numpy()))
     assert worst >= 80.0, worst
+
+
+def test_uint8_inputs_are_bit_identical_to_float32_inputs():
+    """A batch whose image tensors arrive as uint8 (datasets with `uint8_inputs`, a quarter of the PCIe bytes) gives
+    exactly the outputs of the float32 batch: v / 255 on the device is the host's float32(v / 255.0)."""
+    from util import synth
+    m, cfg = make_model(uvh=64, uvw=64, imh=64, imw=64)
+    m.build(5, 3)
+    bt = synth.make_batch(2, 64, 64, seed=3)
+    u8 = synth.as_uint8(bt)
+    assert u8[1].dtype == torch.uint8 and u8[4].dtype == torch.float32
+    a = m(bt, mode='vali')
+    b = m(u8, mode='vali')
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert torch.equal(a[3]['pred'], b[3]['pred'])
