@@ -161,3 +161,38 @@ def test_extract_feat_refuses_unbuilt_model():
     model.register_trainable()
     with pytest.raises(RuntimeError):
         nlt_test.extract_feat(model, [])
+
+
+def test_tf_tensor_bundle_round_trip_and_restore(tmp_path):
+    """util/tf_ckpt.py: a bundle written in the reference's object-graph key layout restores into the model through
+    util.ckpt.restore(prefix) / nlt_test.restore_model; table framing (footer magic, block handles, prefix-compressed
+    keys over several blocks), snappy block decoding and the proto fields are exercised."""
+    import trainvali
+    from util import ckpt, tf_ckpt
+    model = _cpu_model()
+    opt = trainvali.Adam(learning_rate=1e-3, amsgrad=True)
+    g = torch.Generator().manual_seed(9)
+    model.flat_params.copy_(torch.randn(model.flat_params.numel(), generator=g))
+    opt.m, opt.v, opt.vhat = (torch.rand(model.flat_params.numel(), generator=g) for _ in range(3))
+    opt.iterations = 43
+    prefix = str(tmp_path / 'checkpoints' / 'ckpt-43')
+    tf_ckpt.save_nlt_state(prefix, ckpt.state_dict(model, opt, step=43))
+    raw = tf_ckpt.load_bundle(prefix)
+    assert 'net/net_query_layer0/kernel/.ATTRIBUTES/VARIABLE_VALUE' in raw                       # bare Conv2D
+    assert 'net/net_obs_layer4/layer_with_weights-1/bias/.ATTRIBUTES/VARIABLE_VALUE' in raw       # Sequential block
+    assert raw['net/net_query_layer7/layer_with_weights-0/kernel/.ATTRIBUTES/VARIABLE_VALUE'].shape == (2, 2, 128, 1024)
+    assert len(tf_ckpt.read_index(prefix + '.index')) == len(raw) > 150                          # many blocks
+    other = _cpu_model()
+    other_opt = trainvali.Adam(learning_rate=1e-3, amsgrad=True)
+    assert ckpt.restore(prefix, other, other_opt) == 43 and other_opt.iterations == 43
+    for (n1, c1), (n2, c2) in zip(model.named_convs(), other.named_convs()):
+        assert torch.equal(c1.kernel, c2.kernel) and torch.equal(c1.bias, c2.bias)
+    a, b = ckpt._slot_views(model, opt.vhat), ckpt._slot_views(other, other_opt.vhat)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    # snappy-compressed blocks decode too (literal + copy elements)
+    payload = b'abcdabcdabcdabcdXYZ' * 3
+    comp = bytes([len(payload)]) + bytes([(4 - 1) << 2]) + b'abcd' + bytes([((12 - 1) << 2) | 2, 4, 0]) + \
+        bytes([(3 - 1) << 2]) + b'XYZ' + bytes([((38 - 1) << 2) | 2, 19, 0])
+    assert tf_ckpt._snappy_decompress(comp) == payload
+    with pytest.raises(ValueError):
+        tf_ckpt.read_index(__file__)
