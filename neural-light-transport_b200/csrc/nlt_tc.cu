@@ -359,15 +359,12 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32)
     float* stg = reinterpret_cast<float*>(smem + (size_t)TC_STAGES * STAGE_BYTES) + quarter * 32 * TC_EPI_PAD;
     const bool rmw = (p.beta != 0.f) || (p.mask_y != nullptr);
-    // 16-column chunks: 4 lanes = the 64 contiguous bytes of one pixel, 8 pixel rows per pass, 4 passes per chunk.
-    // The read-modify-write operands (old gradient for beta, saved activation for the derivative mask) of chunk i+1
-    // -- of the NEXT TILE after a tile's last chunk -- are in flight while chunk i is drained, converted and stored:
-    // ncu on the round-1 form (operands requested at the top of the chunk that consumes them) showed the input
-    // gradient launches of the mid / deep levels paying one exposed DRAM round trip per 32-column chunk.
-    constexpr int CW = 16;                        // columns per chunk
-    constexpr int NCH = BN / CW;                  // chunks per tile
-    constexpr int NPASS = 4;                      // passes per chunk: 32 rows / 8 rows per pass
-    const int lq = lane & 3, lr = lane >> 2;
+    constexpr int NCH = (BN + 31) / 32;           // 32-column chunks per tile (BN == 16: one half-used chunk)
+    constexpr int CW = BN < 32 ? BN : 32;         // columns per chunk
+    constexpr int QPR = CW / 4;                   // float4 quads per pixel row of a chunk
+    constexpr int RPI = 32 / QPR;                 // pixel rows covered per pass of the warp
+    constexpr int NPASS = 32 / RPI;               // passes per chunk (== QPR)
+    const int lq = lane % QPR, lr = lane / QPR;
 
     struct Coord { int n, ty0, tx0, nt; };
     auto tile_coord = [&](int tile) {
@@ -393,45 +390,37 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       }
       return (((size_t)c.n * p.Hout + oy) * p.Wout + ox) * p.cout_true + cb;
     };
-    float4 nx_old[NPASS], nx_y[NPASS];           // operands of the NEXT chunk (in flight)
+    float4 rm_old[NPASS], rm_y[NPASS];
     auto prefetch = [&](const Coord& c, int ch) {
 #pragma unroll
       for (int i = 0; i < NPASS; ++i) {
-        const size_t ob = out_off(c, quarter * 32 + i * 8 + lr, c.nt * BN + ch * CW + lq * 4);
-        nx_old[i] = (p.beta != 0.f) ? *reinterpret_cast<const float4*>(p.out + ob) : make_float4(0.f, 0.f, 0.f, 0.f);
-        nx_y[i] = (p.mask_y != nullptr) ? ld4(p.mask_y + ob) : make_float4(1.f, 1.f, 1.f, 1.f);
+        const size_t ob = out_off(c, quarter * 32 + i * RPI + lr, c.nt * BN + ch * 32 + lq * 4);
+        rm_old[i] = (p.beta != 0.f) ? *reinterpret_cast<const float4*>(p.out + ob) : make_float4(0.f, 0.f, 0.f, 0.f);
+        rm_y[i] = (p.mask_y != nullptr) ? ld4(p.mask_y + ob) : make_float4(1.f, 1.f, 1.f, 1.f);
       }
     };
     int it = 0;
-    int tile = blockIdx.x;
-    Coord tc = tile_coord(tile < p.total_tiles ? tile : 0);
-    if (rmw && tile < p.total_tiles) prefetch(tc, 0);
-    for (; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1;
-      const int tile_next = tile + (int)gridDim.x;
-      const Coord tcn = tile_coord(tile_next < p.total_tiles ? tile_next : tile);
+      const Coord tc = tile_coord(tile);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN);
 #pragma unroll 1
       for (int ch = 0; ch < NCH; ++ch) {
-        float4 rm_old[NPASS], rm_y[NPASS];
-        if (rmw) {
-#pragma unroll
-          for (int i = 0; i < NPASS; ++i) { rm_old[i] = nx_old[i]; rm_y[i] = nx_y[i]; }
-          if (ch + 1 < NCH) prefetch(tc, ch + 1);
-          else if (tile_next < p.total_tiles) prefetch(tcn, 0);
-        }
+        // read-modify-write operands first: their latency overlaps the accumulator wait / TMEM drain
+        if (rmw) prefetch(tc, ch);
         if (ch == 0) {
           mbar_wait(bar_accf(buf), acc_phase);
           tc_fence_after();
         }
-        const int col0 = tc.nt * BN + ch * CW;    // GEMM column of this chunk
-        {
+        const int col0 = tc.nt * BN + ch * 32;    // GEMM column of this chunk
+#pragma unroll
+        for (int h = 0; h < CW / 16; ++h) {
           uint32_t v[16];
-          tc_ld16(taddr + ch * CW, v);
+          tc_ld16(taddr + ch * 32 + h * 16, v);
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
-            int cb = col0 + q4 * 4;
+            int cb = col0 + h * 16 + q4 * 4;
             if (p.d2s) cb -= (cb / p.cout_true) * p.cout_true;
             float o[4];
 #pragma unroll
@@ -440,13 +429,13 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
               if (p.bias != nullptr) x += __ldg(p.bias + cb + e);
               o[e] = act_fwd(x, p.act);
             }
-            *reinterpret_cast<float4*>(stg + lane * TC_EPI_PAD + q4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(stg + lane * TC_EPI_PAD + h * 16 + q4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
           }
         }
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < NPASS; ++i) {
-          const int row = i * 8 + lr;
+          const int row = i * RPI + lr;
           float4 o = *reinterpret_cast<const float4*>(stg + row * TC_EPI_PAD + lq * 4);
           if (rmw) {
             o.x += p.beta * rm_old[i].x; o.y += p.beta * rm_old[i].y; o.z += p.beta * rm_old[i].z; o.w += p.beta * rm_old[i].w;
@@ -462,7 +451,6 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       }
       tc_fence_before();
       mbar_arrive(bar_acce(buf));
-      tc = tcn;
     }
   }
 
@@ -657,15 +645,12 @@ tcs_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32)
     float* stg = reinterpret_cast<float*>(smem + (size_t)TC_STAGES * STAGE_BYTES) + quarter * 32 * TC_EPI_PAD;
     const bool rmw = (p.beta != 0.f) || (p.mask_y != nullptr);
-    // 16-column chunks: 4 lanes = the 64 contiguous bytes of one pixel, 8 pixel rows per pass, 4 passes per chunk.
-    // The read-modify-write operands (old gradient for beta, saved activation for the derivative mask) of chunk i+1
-    // -- of the NEXT TILE after a tile's last chunk -- are in flight while chunk i is drained, converted and stored:
-    // ncu on the round-1 form (operands requested at the top of the chunk that consumes them) showed the input
-    // gradient launches of the mid / deep levels paying one exposed DRAM round trip per 32-column chunk.
-    constexpr int CW = 16;                        // columns per chunk
-    constexpr int NCH = BN / CW;                  // chunks per tile
-    constexpr int NPASS = 4;                      // passes per chunk: 32 rows / 8 rows per pass
-    const int lq = lane & 3, lr = lane >> 2;
+    constexpr int NCH = (BN + 31) / 32;           // 32-column chunks per tile (BN == 16: one half-used chunk)
+    constexpr int CW = BN < 32 ? BN : 32;         // columns per chunk
+    constexpr int QPR = CW / 4;                   // float4 quads per pixel row of a chunk
+    constexpr int RPI = 32 / QPR;                 // pixel rows covered per pass of the warp
+    constexpr int NPASS = 32 / RPI;               // passes per chunk (== QPR)
+    const int lq = lane % QPR, lr = lane / QPR;
 
     struct Coord { int n, ty0, tx0, nt; };
     auto tile_coord = [&](int tile) {
@@ -691,45 +676,37 @@ tcs_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       }
       return (((size_t)c.n * p.Hout + oy) * p.Wout + ox) * p.cout_true + cb;
     };
-    float4 nx_old[NPASS], nx_y[NPASS];           // operands of the NEXT chunk (in flight)
+    float4 rm_old[NPASS], rm_y[NPASS];
     auto prefetch = [&](const Coord& c, int ch) {
 #pragma unroll
       for (int i = 0; i < NPASS; ++i) {
-        const size_t ob = out_off(c, quarter * 32 + i * 8 + lr, c.nt * BN + ch * CW + lq * 4);
-        nx_old[i] = (p.beta != 0.f) ? *reinterpret_cast<const float4*>(p.out + ob) : make_float4(0.f, 0.f, 0.f, 0.f);
-        nx_y[i] = (p.mask_y != nullptr) ? ld4(p.mask_y + ob) : make_float4(1.f, 1.f, 1.f, 1.f);
+        const size_t ob = out_off(c, quarter * 32 + i * RPI + lr, c.nt * BN + ch * 32 + lq * 4);
+        rm_old[i] = (p.beta != 0.f) ? *reinterpret_cast<const float4*>(p.out + ob) : make_float4(0.f, 0.f, 0.f, 0.f);
+        rm_y[i] = (p.mask_y != nullptr) ? ld4(p.mask_y + ob) : make_float4(1.f, 1.f, 1.f, 1.f);
       }
     };
     int it = 0;
-    int tile = blockIdx.x;
-    Coord tc = tile_coord(tile < p.total_tiles ? tile : 0);
-    if (rmw && tile < p.total_tiles) prefetch(tc, 0);
-    for (; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1;
-      const int tile_next = tile + (int)gridDim.x;
-      const Coord tcn = tile_coord(tile_next < p.total_tiles ? tile_next : tile);
+      const Coord tc = tile_coord(tile);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN);
 #pragma unroll 1
       for (int ch = 0; ch < NCH; ++ch) {
-        float4 rm_old[NPASS], rm_y[NPASS];
-        if (rmw) {
-#pragma unroll
-          for (int i = 0; i < NPASS; ++i) { rm_old[i] = nx_old[i]; rm_y[i] = nx_y[i]; }
-          if (ch + 1 < NCH) prefetch(tc, ch + 1);
-          else if (tile_next < p.total_tiles) prefetch(tcn, 0);
-        }
+        // read-modify-write operands first: their latency overlaps the accumulator wait / TMEM drain
+        if (rmw) prefetch(tc, ch);
         if (ch == 0) {
           mbar_wait(bar_accf(buf), acc_phase);
           tc_fence_after();
         }
-        const int col0 = tc.nt * BN + ch * CW;    // GEMM column of this chunk
-        {
+        const int col0 = tc.nt * BN + ch * 32;    // GEMM column of this chunk
+#pragma unroll
+        for (int h = 0; h < CW / 16; ++h) {
           uint32_t v[16];
-          tc_ld16(taddr + ch * CW, v);
+          tc_ld16(taddr + ch * 32 + h * 16, v);
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
-            int cb = col0 + q4 * 4;
+            int cb = col0 + h * 16 + q4 * 4;
             if (p.d2s) cb -= (cb / p.cout_true) * p.cout_true;
             float o[4];
 #pragma unroll
@@ -738,13 +715,13 @@ tcs_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
               if (p.bias != nullptr) x += __ldg(p.bias + cb + e);
               o[e] = act_fwd(x, p.act);
             }
-            *reinterpret_cast<float4*>(stg + lane * TC_EPI_PAD + q4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(stg + lane * TC_EPI_PAD + h * 16 + q4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
           }
         }
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < NPASS; ++i) {
-          const int row = i * 8 + lr;
+          const int row = i * RPI + lr;
           float4 o = *reinterpret_cast<const float4*>(stg + row * TC_EPI_PAD + lq * 4);
           if (rmw) {
             o.x += p.beta * rm_old[i].x; o.y += p.beta * rm_old[i].y; o.z += p.beta * rm_old[i].z; o.w += p.beta * rm_old[i].w;
@@ -760,7 +737,6 @@ tcs_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       }
       tc_fence_before();
       mbar_arrive(bar_acce(buf));
-      tc = tcn;
     }
   }
 

@@ -73,7 +73,11 @@ def test_model_with_norm_forward_backward(kind):
     assert float((pred.double().cpu() - p64.detach()).abs().max()) <= 5e-5
     grads = m.export_grads()
     assert set(grads) == set(params)
-    worst = max((rel_fro(grads[k], params[k].grad), k) for k in params)
+    # a conv bias in front of an instance norm has an identically zero gradient (the norm removes the mean):
+    # compare those on an absolute scale, everything else relatively
+    scale = max(float(params[k].grad.norm()) for k in params)
+    worst = max((rel_fro(grads[k], params[k].grad) if float(params[k].grad.norm()) > 1e-9 * scale
+                 else float(grads[k].double().norm().cpu()) / scale, k) for k in params)
     assert worst[0] <= 3e-3, worst          # plain oracle: includes LeakyReLU derivative-bit flips
     # checkpoint keys carry the norm parameters
     if kind == 'instance':
