@@ -170,6 +170,12 @@ bool pwx_wgrad_applicable(const GConvK& k, const float* G);
 size_t pwx_wgrad_ws_floats(const GConvK& k);
 int launch_pwx_wgrad(const GConvK& k, const float* G, float* ws, WgradK* w, size_t* KD_pad, cudaStream_t st);
 
+// input gradient of the 2x2 / stride-2 convs into 16-channel sources (depth-to-space pointwise op, nlt_pwx.cu)
+bool pwd2s_applicable(const GConvK& k, const float* bias, int act, const float* out, const float* mask_y,
+                      const PwExtra* ex);
+int launch_pwd2s(const GConvK& k, float beta, const float* mask_y, int mask_act, float* out, cudaStream_t st,
+                 const PwExtra* ex);
+
 // tcgen05 tensor-core path (nlt_tc.cu)
 #define NLT_TCS_DEFAULT 0
 extern int g_opt_tcs;            // TS form of the forward kernel (A operand through tensor memory)

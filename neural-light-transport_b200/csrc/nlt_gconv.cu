@@ -720,6 +720,7 @@ int nlt_gconv_fwd_ws(const nlt_gconv_desc* d, const float* bias, int act, float 
     const GConvK& k = ph[i];
     if (k.M == 0) continue;
     if (pwx_fwd_applicable(k, beta, mask_y, out)) rc = launch_pwx_fwd(k, bias, act, out, st);
+    else if (pwd2s_applicable(k, bias, act, out, mask_y, nullptr)) rc = launch_pwd2s(k, beta, mask_y, mask_act, out, st, nullptr);
     else if (pw_conv_applicable(k)) rc = launch_pw_conv(k, bias, act, beta, mask_y, mask_act, out, st);
     // option "dconv_wide_first" (default on; measured -0.4 ms per cfg2 step together with the 8-output form,
     // profiles/r2_a_*): prefer the wide stencil kernel over the quad-per-thread one where both apply
@@ -755,7 +756,7 @@ int nlt_gconv_fwd_fused_supported(const nlt_gconv_desc* d, const nlt_pw_term* te
   GConvK k;
   PwExtra ex;
   if (pw_term_phase(d, term, &k, &ex) != NLT_OK) return 0;
-  return (k.M > 0 && pw_extra_applicable(k, ex, out, mask_y)) ? 1 : 0;
+  return (k.M > 0 && (pwd2s_applicable(k, nullptr, 0, out, mask_y, &ex) || pw_extra_applicable(k, ex, out, mask_y))) ? 1 : 0;
 }
 
 int nlt_gconv_fwd_fused(const nlt_gconv_desc* d, const nlt_pw_term* term, const float* bias, int act, float beta,
@@ -768,6 +769,8 @@ int nlt_gconv_fwd_fused(const nlt_gconv_desc* d, const nlt_pw_term* term, const 
   NLT_CHECK_ARG(out != nullptr, "null output");
   NLT_CHECK_ARG(act >= 0 && act <= 3 && mask_act >= 0 && mask_act <= 3, "bad activation code");
   NLT_CHECK_ARG(beta == 0.f || beta == 1.f, "beta must be 0 or 1");
+  if (k.M > 0 && pwd2s_applicable(k, bias, act, out, mask_y, &ex))
+    return launch_pwd2s(k, beta, mask_y, mask_act, out, (cudaStream_t)stream, &ex);
   if (k.M == 0 || !pw_extra_applicable(k, ex, out, mask_y))
     return set_err(NLT_ERR_UNSUPPORTED, "fused pointwise term: shape not served by the pointwise kernel");
   return launch_pw_conv(k, bias, act, beta, mask_y, mask_act, out, (cudaStream_t)stream, &ex);

@@ -476,4 +476,171 @@ int launch_pwx_wgrad(const GConvK& k, const float* G, float* ws, WgradK* w, size
   }
 }
 
+// =============================================================================================
+// Input gradient of a 2x2 / stride-2 convolution into 16-channel sources ("depth-to-space" pointwise op):
+//   every low-resolution gradient pixel dz[p, 0..K) (K = 16 or 32) produces the 2x2 block of 16-channel input
+//   gradients above it:  dx[2y+dy, 2x+dx, c] = sum_k dz[y, x, k] * W[tap(dy,dx), c, k]   (64 outputs per pixel).
+// This is the level-1 / level-2 step of the backward chain and, at 1024^2, the largest single launch group of the
+// whole step.  It is a pure stream (128-256 MB in, 0.5-1 GB out + the read-modify-write operands), so:
+//   * thread = gradient pixel: dz row straight from global memory (a warp reads one contiguous run), the 64 outputs
+//     as 32 float2 accumulators, weights from CONSTANT memory (LDCU + FFMA2, no LSU traffic);
+//   * a tile of 256 pixels of one lattice row owns two contiguous 32 KB runs of the output (rows 2y and 2y+1):
+//     results are staged in shared memory and leave as fully coalesced 16-byte stores, with the old gradient
+//     (beta = 1), the activation mask and the fused pointwise term (the final 1x1 conv's input gradient riding along,
+//     nlt_gconv_fwd_fused) applied in that same coalesced pass.
+// =============================================================================================
+constexpr int PWD_T = 256;
+constexpr int PWD_THREADS = 256;
+constexpr int PWD_SROW = 68;                                        // floats per staged pixel (64 + 4)
+__constant__ float2 pwd_cw[32 * 32];                               // [k][m] = (W[k][n' = 2m], W[k][2m + 1]), n' = tap*16 + c
+__device__ float2 pwd_cw_stage[32 * 32];
+
+struct PwdParams {
+  const float* dz;        // [M][K]
+  int K;
+  uint32_t M;             // lattice pixels = N * Hin * Win
+  int Win;                // multiple of PWD_T
+  int tiles_per_row;
+  uint32_t ntiles;
+  float beta;
+  const float* mask_y;
+  int mask_act;
+  float* out;             // [N*2Hin][2Win][16]
+  // fused pointwise term: out[opix, c] += sum_k ex_x[opix, k] * ex_w[k*wk + c*wn]
+  const float* ex_x;
+  int ex_K;
+  const float* ex_w;
+  long long ex_wk, ex_wn;
+};
+
+__global__ void pwd_pack_w_kernel(const GConvK g, int K) {
+  const int total = K * 32;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int kk = i >> 5, m = i & 31;
+    const int np = 2 * m, tap = np >> 4, c = np & 15;               // (n', n' + 1) share the tap: c is even
+    const float* w0 = g.w + (long long)tap * g.wt + (long long)kk * g.wc + (long long)c * g.wn;
+    pwd_cw_stage[i] = make_float2(__ldg(w0), __ldg(w0 + g.wn));
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(PWD_THREADS, 2)
+pwd2s_kernel(const PwdParams p) {
+  extern __shared__ __align__(16) float so[];                      // [PWD_T][PWD_SROW]
+  __shared__ float exw[PW_EX_KMAX * 16];
+  const int tid = threadIdx.x;
+  if (p.ex_x != nullptr && tid < p.ex_K * 16)
+    exw[tid] = __ldg(p.ex_w + (long long)(tid >> 4) * p.ex_wk + (long long)(tid & 15) * p.ex_wn);
+  const int Wout = 2 * p.Win;
+  for (uint32_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+    const uint32_t row = t / (uint32_t)p.tiles_per_row;             // flat lattice row n*Hin + y
+    const uint32_t x0 = (t - row * (uint32_t)p.tiles_per_row) * PWD_T;
+    const size_t pix = (size_t)row * p.Win + x0 + tid;
+    // ---- 64 outputs of this gradient pixel ----
+    float2 acc[32];                                                // (out[2m], out[2m + 1])
+#pragma unroll
+    for (int m = 0; m < 32; ++m) acc[m] = make_float2(0.f, 0.f);
+    const float4* xr = reinterpret_cast<const float4*>(p.dz + pix * K);
+#pragma unroll
+    for (int q = 0; q < K / 4; ++q) {
+      const float4 xv = __ldg(xr + q);
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 xx = make_float2(xs[e], xs[e]);
+#pragma unroll
+        for (int m = 0; m < 32; ++m) acc[m] = __ffma2_rn(xx, pwd_cw[(4 * q + e) * 32 + m], acc[m]);
+      }
+    }
+    __syncthreads();                                               // the previous tile's staged values have been read
+    float4* srow = reinterpret_cast<float4*>(so + tid * PWD_SROW);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) srow[j] = make_float4(acc[2 * j].x, acc[2 * j].y, acc[2 * j + 1].x, acc[2 * j + 1].y);
+    __syncthreads();
+    // ---- two contiguous output runs (rows 2*row and 2*row + 1), 2 * PWD_T pixels of 16 channels each ----
+#pragma unroll 1
+    for (int dy = 0; dy < 2; ++dy) {
+      const size_t obase = ((size_t)(2 * row + dy) * Wout + 2 * x0) * 16;     // floats
+#pragma unroll 2
+      for (int i = 0; i < (2 * PWD_T * 4) / PWD_THREADS; ++i) {
+        const int q = tid + i * PWD_THREADS;                       // float4 index inside the run
+        const int ox = q >> 2, j = q & 3;
+        const int px = ox >> 1, dx = ox & 1;
+        float4 v = *reinterpret_cast<const float4*>(so + px * PWD_SROW + (dy * 2 + dx) * 16 + j * 4);
+        const size_t o = obase + (size_t)q * 4;
+        if (p.ex_x != nullptr) {
+          const float* xe = p.ex_x + (o >> 4) * p.ex_K;             // output pixel index = o / 16
+          for (int k = 0; k < p.ex_K; ++k) {
+            const float xk = __ldg(xe + k);
+            const float* wk = exw + k * 16 + j * 4;
+            v.x = fmaf(xk, wk[0], v.x); v.y = fmaf(xk, wk[1], v.y); v.z = fmaf(xk, wk[2], v.z); v.w = fmaf(xk, wk[3], v.w);
+          }
+        }
+        if (p.beta != 0.f) {
+          const float4 old = *reinterpret_cast<const float4*>(p.out + o);
+          v.x += p.beta * old.x; v.y += p.beta * old.y; v.z += p.beta * old.z; v.w += p.beta * old.w;
+        }
+        if (p.mask_y != nullptr) {
+          const float4 y = ld4(p.mask_y + o);
+          v.x *= act_bwd_from_y(y.x, p.mask_act); v.y *= act_bwd_from_y(y.y, p.mask_act);
+          v.z *= act_bwd_from_y(y.z, p.mask_act); v.w *= act_bwd_from_y(y.w, p.mask_act);
+        }
+        *reinterpret_cast<float4*>(p.out + o) = v;
+      }
+    }
+  }
+}
+
+bool pwd2s_applicable(const GConvK& k, const float* bias, int act, const float* out, const float* mask_y,
+                      const PwExtra* ex) {
+  if (!pwx_enabled()) return false;
+  if (!k.d2s || k.d2s_s != 2 || k.nseg != 1 || k.cout_true != 16 || k.Cout != 64 || k.M == 0) return false;
+  const Seg& sg = k.seg[0];
+  if ((sg.C != 16 && sg.C != 32) || !sg.vec || sg.sub != nullptr || sg.bcast) return false;
+  if (bias != nullptr || act != 0) return false;
+  if (k.ax.nt != k.Win || k.ay.nt != k.Hin || k.Win % PWD_T != 0) return false;
+  if (k.Hout != 2 * k.Hin || k.Wout != 2 * k.Win) return false;
+  if (!aligned16(out) || (mask_y != nullptr && !aligned16(mask_y))) return false;
+  if (ex != nullptr && (ex->K < 1 || ex->K > PW_EX_KMAX || ex->x == nullptr || ex->w == nullptr)) return false;
+  return true;
+}
+
+template <int K>
+static int pwd2s_launch(const PwdParams& p, cudaStream_t st) {
+  const size_t smem = (size_t)PWD_T * PWD_SROW * sizeof(float);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static bool attr_set[64] = {false};
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(pwd2s_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  const unsigned grid = p.ntiles < 296u ? p.ntiles : 296u;          // 2 CTAs per SM
+  pwd2s_kernel<K><<<grid, PWD_THREADS, smem, st>>>(p);
+  NLT_CUDA_LAUNCH_CHECK("pwd2s_kernel");
+  return NLT_OK;
+}
+
+// NOTE (as for the forward above): one constant-memory weight table per device -- launches from different streams of
+// one device must not overlap; the engine issues input gradients from its main stream only.
+int launch_pwd2s(const GConvK& k, float beta, const float* mask_y, int mask_act, float* out, cudaStream_t st,
+                 const PwExtra* ex) {
+  const int K = k.seg[0].C;
+  pwd_pack_w_kernel<<<4, 256, 0, st>>>(k, K);
+  NLT_CUDA_LAUNCH_CHECK("pwd_pack_w_kernel");
+  void* stage = nullptr;
+  cudaError_t e = cudaGetSymbolAddress(&stage, pwd_cw_stage);
+  if (e == cudaSuccess)
+    e = cudaMemcpyToSymbolAsync(pwd_cw, stage, (size_t)K * 32 * sizeof(float2), 0, cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "pwd weight table: %s", cudaGetErrorString(e));
+  PwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.dz = k.seg[0].ptr; p.K = K; p.M = k.M; p.Win = k.Win; p.tiles_per_row = k.Win / PWD_T;
+  p.ntiles = k.M / PWD_T;
+  p.beta = beta; p.mask_y = mask_y; p.mask_act = mask_act; p.out = out;
+  if (ex != nullptr) { p.ex_x = ex->x; p.ex_K = ex->K; p.ex_w = ex->w; p.ex_wk = ex->wk; p.ex_wn = ex->wn; }
+  return K == 16 ? pwd2s_launch<16>(p, st) : pwd2s_launch<32>(p, st);
+}
+
 }  // namespace nlt

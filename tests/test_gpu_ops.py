@@ -84,6 +84,7 @@ GEOMS = [
     ('conv', 2, 2, 64, 64, [32, 16], 32),       # mixed 32/16 sources -> 16-wide blocks
     # wide pointwise conv into 16 channels (nlt_pwx.cu: level 0 of the 64-channel query stack): cp.async-staged
     # 256-pixel tiles, ragged last tile, float4-able and scalar sources mixed, K not a multiple of 32
+    ('conv', 2, 2, 8, 512, [16, 16], 32),       # its input gradients: depth-to-space K = 32 -> 4 x 16 (pwd2s kernel)
     ('conv', 1, 1, 33, 37, [3, 60, 1], 16),
     ('conv', 1, 1, 32, 32, [64], 16),
     ('conv', 1, 1, 24, 24, [20, 4], 16),
@@ -223,7 +224,8 @@ def test_wgrad_row_run_vs_flat_pixel_kernel(kind, k, s, H, W, segc, cout):
 
 @pytest.mark.parametrize('H,W,c_skip,c_other,down_cout,dk', [
     (16, 16, 16, 4, 16, 2), (8, 24, 16, 8, 32, 2), (6, 10, 12, 4, 8, 2),   # depth-to-space dgrad: shuffle / per-quad modes
-    (8, 8, 16, 4, 16, 1), (4, 12, 8, 4, 24, 1)])                            # 1x1 consumer: same-pixel mode
+    (8, 8, 16, 4, 16, 1), (4, 12, 8, 4, 24, 1),                             # 1x1 consumer: same-pixel mode
+    (8, 512, 16, 4, 16, 2), (4, 1024, 16, 4, 32, 2)])                       # lattice rows of 256 / 512: the streaming pwd2s kernel (K = 16 / 32)
 def test_final_conv_input_gradient_rides_on_down_conv_dgrad(H, W, c_skip, c_other, down_cout, dk):
     """Skip tensor consumed by a 2x2/s2 down-conv and, later, by the final 1x1 conv -> 3 (the level-0 skip
     of the network): with fusion on, the 1x1 conv's input gradient is added in the epilogue of the
