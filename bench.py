@@ -536,6 +536,7 @@ def run_b200(args):
                           key=lambda r: -r['ms_per_step'])
             json.dump({'ms_step': ms_step, 'sum_ms': total_ms / 2, 'rows': rows}, open(args.profile_out, 'w'), indent=1)
 
+    run_graph_full = run.graphed is not None and run.graphed.full_step_in_graph
     # ---- strong-scaling sub-record (N > 1): cfg4's FIXED global batch 32 ----
     strong = None
     if world > 1 and args.scaling == 'weak' and not args.no_extra and 32 % world == 0:
@@ -584,7 +585,8 @@ def run_b200(args):
                                      'note': 'same call with the image tensors as uint8 PNG samples (datasets '
                                              'uint8_inputs = True; v / 255 on the device, bit-identical results); the '
                                              'float32 number above is bounded by PCIe (h2d bytes / step time)'}},
-            'gpu_launches': launches, 'tcgen05_launches': tc_launches, 'clocks': clocks, 'parity': parity,
+            'gpu_launches': launches, 'tcgen05_launches': tc_launches,
+            'whole_step_in_cuda_graph': bool(run_graph_full), 'clocks': clocks, 'parity': parity,
             'roofline': roof, 'cpu_baseline': cpu,
         }
         if strong is not None:

@@ -55,6 +55,7 @@ struct TcParams {
   int d2s, d2s_s;
   int act, mask_act;
   int stages;               // smem ring depth
+  int ablate;               // DIAGNOSTIC (NLT_TC_ABLATE, wrong results!): 1 no B loads, 2 no transform, 4 no MMA, 8 no epilogue memory traffic, 16 no A loads
   float beta;
   const float* bias;
   const float* mask_y;
@@ -283,14 +284,18 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             for (int s = 0; s < p.nseg; ++s)
               for (int ch = 0; ch < p.seg_chunks[s]; ++ch, ++kb) {
                 mbar_wait(bar_empty(stage), phase ^ 1);
-                mbar_expect_tx(bar_full(stage), TC_A_BYTES + 2 * B_BYTES);
-                if (p.mode_patch)
-                  tma_load_5d(a_hi(stage), &maps.a[s], bar_full(stage), ch * TC_KB, ux, tx0, uy, n * p.Hs + ty0);
-                else
-                  tma_load_4d(a_hi(stage), &maps.a[s], bar_full(stage), ch * TC_KB, tx0 + ux * p.ux_step + p.x_off,
-                              ty0 + uy * p.uy_step + p.y_off, n);
-                tma_load_3d(b_hi(stage), &maps.bhi, bar_full(stage), 0, nt * BN, kb);
-                tma_load_3d(b_lo(stage), &maps.blo, bar_full(stage), 0, nt * BN, kb);
+                mbar_expect_tx(bar_full(stage), ((p.ablate & 16) ? 0 : TC_A_BYTES) + ((p.ablate & 1) ? 0 : 2 * B_BYTES));
+                if (!(p.ablate & 16)) {
+                  if (p.mode_patch)
+                    tma_load_5d(a_hi(stage), &maps.a[s], bar_full(stage), ch * TC_KB, ux, tx0, uy, n * p.Hs + ty0);
+                  else
+                    tma_load_4d(a_hi(stage), &maps.a[s], bar_full(stage), ch * TC_KB, tx0 + ux * p.ux_step + p.x_off,
+                                ty0 + uy * p.uy_step + p.y_off, n);
+                }
+                if (!(p.ablate & 1)) {
+                  tma_load_3d(b_hi(stage), &maps.bhi, bar_full(stage), 0, nt * BN, kb);
+                  tma_load_3d(b_lo(stage), &maps.blo, bar_full(stage), 0, nt * BN, kb);
+                }
                 if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
               }
       }
@@ -311,7 +316,7 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           mbar_wait(bar_ready(stage), phase);        // operands split and visible to the async proxy
           tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < TC_KB / 8; ++k) {
+          for (int k = 0; k < ((p.ablate & 4) ? 0 : TC_KB / 8); ++k) {
             const uint64_t ah = umma_desc_kmajor<ROWB>(a_hi(stage) + k * 32), al = umma_desc_kmajor<ROWB>(a_lo(stage) + k * 32);
             const uint64_t bh = umma_desc_kmajor<ROWB>(b_hi(stage) + k * 32), bl = umma_desc_kmajor<ROWB>(b_lo(stage) + k * 32);
             tc_mma_tf32(d_tmem, al, bh, IDESC, (kb | k) != 0);   // small terms first
@@ -336,7 +341,7 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         float4* ah = reinterpret_cast<float4*>(smem + (size_t)stage * STAGE_BYTES);
         float4* al = reinterpret_cast<float4*>(smem + (size_t)stage * STAGE_BYTES + TC_A_BYTES);
 #pragma unroll
-        for (int i = 0; i < TC_A_BYTES / 16 / 256; ++i) {
+        for (int i = 0; i < ((p.ablate & 2) ? 0 : TC_A_BYTES / 16 / 256); ++i) {
           const int q = t + i * 256;              // physical 16-byte chunk: elementwise, swizzle-agnostic
           const float4 v = ah[q];
           float4 h, l;
@@ -358,7 +363,7 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     // processed, so their DRAM latency overlaps the TMEM drain.
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32)
     float* stg = reinterpret_cast<float*>(smem + (size_t)TC_STAGES * STAGE_BYTES) + quarter * 32 * TC_EPI_PAD;
-    const bool rmw = (p.beta != 0.f) || (p.mask_y != nullptr);
+    const bool rmw = ((p.beta != 0.f) || (p.mask_y != nullptr)) && !(p.ablate & 8);
     constexpr int NCH = (BN + 31) / 32;           // 32-column chunks per tile (BN == 16: one half-used chunk)
     constexpr int CW = BN < 32 ? BN : 32;         // columns per chunk
     constexpr int QPR = CW / 4;                   // float4 quads per pixel row of a chunk
@@ -445,7 +450,7 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             }
           }
           const size_t ob = out_off(tc, quarter * 32 + row, col0 + lq * 4);
-          *reinterpret_cast<float4*>(p.out + ob) = o;
+          if (!(p.ablate & 8) || o.x == 123456.f) *reinterpret_cast<float4*>(p.out + ob) = o;
         }
         __syncwarp();
       }
@@ -876,6 +881,11 @@ static TcPlan tc_plan(const GConvK& k) {
     pl.smem_bytes = (size_t)st * stage_bytes + TC_EPI_BYTES + 1024;
   }
   if (get_encode() == nullptr) return pl;
+  {
+    static int ablate = -1;
+    if (ablate < 0) { const char* e = getenv("NLT_TC_ABLATE"); ablate = e ? atoi(e) : 0; }
+    p.ablate = ablate;
+  }
   pl.ok = true;
   return pl;
 }

@@ -256,6 +256,9 @@ class GraphedTrainStep:
                 for _ in range(2):
                     self._body(self.static_batch, with_update=False)
             torch.cuda.current_stream().wait_stream(side)
+            if self.strategy.world > 1:
+                # NCCL creates its communicator at the first collective, which cannot happen inside a capture
+                self.strategy.all_reduce_sum_(torch.zeros(1, device=dev))
             torch.cuda.synchronize()
             it0 = self.optimizer.iterations
             self.optimizer._state(self.model.flat_params)
