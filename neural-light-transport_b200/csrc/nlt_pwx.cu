@@ -529,22 +529,30 @@ pwd2s_kernel(const PwdParams p) {
   extern __shared__ __align__(16) float so[];                      // [PWD_T][PWD_SROW]
   __shared__ float exw[PW_EX_KMAX * 16];
   const int tid = threadIdx.x;
-  if (p.ex_x != nullptr && tid < p.ex_K * 16)
-    exw[tid] = __ldg(p.ex_w + (long long)(tid >> 4) * p.ex_wk + (long long)(tid & 15) * p.ex_wn);
+  if (tid < PW_EX_KMAX * 16)
+    exw[tid] = (p.ex_x != nullptr && tid < p.ex_K * 16)
+                   ? __ldg(p.ex_w + (long long)(tid >> 4) * p.ex_wk + (long long)(tid & 15) * p.ex_wn) : 0.f;
+  __syncthreads();
   const int Wout = 2 * p.Win;
+  auto load_x = [&](uint32_t t, float4 (&xv)[K / 4]) {
+    const uint32_t row = t / (uint32_t)p.tiles_per_row;
+    const uint32_t x0 = (t - row * (uint32_t)p.tiles_per_row) * PWD_T;
+    const float4* xr = reinterpret_cast<const float4*>(p.dz + ((size_t)row * p.Win + x0 + tid) * K);
+#pragma unroll
+    for (int q = 0; q < K / 4; ++q) xv[q] = __ldg(xr + q);
+  };
+  float4 xcur[K / 4];
+  if (blockIdx.x < p.ntiles) load_x(blockIdx.x, xcur);
   for (uint32_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
     const uint32_t row = t / (uint32_t)p.tiles_per_row;             // flat lattice row n*Hin + y
     const uint32_t x0 = (t - row * (uint32_t)p.tiles_per_row) * PWD_T;
-    const size_t pix = (size_t)row * p.Win + x0 + tid;
     // ---- 64 outputs of this gradient pixel ----
     float2 acc[32];                                                // (out[2m], out[2m + 1])
 #pragma unroll
     for (int m = 0; m < 32; ++m) acc[m] = make_float2(0.f, 0.f);
-    const float4* xr = reinterpret_cast<const float4*>(p.dz + pix * K);
 #pragma unroll
     for (int q = 0; q < K / 4; ++q) {
-      const float4 xv = __ldg(xr + q);
-      const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+      const float xs[4] = {xcur[q].x, xcur[q].y, xcur[q].z, xcur[q].w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 xx = make_float2(xs[e], xs[e]);
@@ -552,40 +560,56 @@ pwd2s_kernel(const PwdParams p) {
         for (int m = 0; m < 32; ++m) acc[m] = __ffma2_rn(xx, pwd_cw[(4 * q + e) * 32 + m], acc[m]);
       }
     }
+    if (t + gridDim.x < p.ntiles) load_x(t + gridDim.x, xcur);      // next tile's gradient rows: in flight during the write phase
     __syncthreads();                                               // the previous tile's staged values have been read
     float4* srow = reinterpret_cast<float4*>(so + tid * PWD_SROW);
 #pragma unroll
     for (int j = 0; j < 16; ++j) srow[j] = make_float4(acc[2 * j].x, acc[2 * j].y, acc[2 * j + 1].x, acc[2 * j + 1].y);
     __syncthreads();
     // ---- two contiguous output runs (rows 2*row and 2*row + 1), 2 * PWD_T pixels of 16 channels each ----
+    // 16 float4 per thread in batches of 4: every read-modify-write operand of a batch is requested before the first
+    // one is used (enough bytes in flight per SM to cover the DRAM latency)
+    constexpr int PER_RUN = (2 * PWD_T * 4) / PWD_THREADS;         // float4 per thread and run (8)
 #pragma unroll 1
-    for (int dy = 0; dy < 2; ++dy) {
-      const size_t obase = ((size_t)(2 * row + dy) * Wout + 2 * x0) * 16;     // floats
-#pragma unroll 2
-      for (int i = 0; i < (2 * PWD_T * 4) / PWD_THREADS; ++i) {
-        const int q = tid + i * PWD_THREADS;                       // float4 index inside the run
+    for (int b4 = 0; b4 < 2 * PER_RUN / 4; ++b4) {
+      float4 v[4], old[4], ym[4];
+      float xe[4][PW_EX_KMAX];
+      size_t off[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = b4 * 4 + u;                                  // 0 .. 15
+        const int dy = i / PER_RUN;
+        const int q = tid + (i - dy * PER_RUN) * PWD_THREADS;      // float4 index inside the run
         const int ox = q >> 2, j = q & 3;
         const int px = ox >> 1, dx = ox & 1;
-        float4 v = *reinterpret_cast<const float4*>(so + px * PWD_SROW + (dy * 2 + dx) * 16 + j * 4);
-        const size_t o = obase + (size_t)q * 4;
+        off[u] = ((size_t)(2 * row + dy) * Wout + 2 * x0) * 16 + (size_t)q * 4;
+        if (p.beta != 0.f) old[u] = *reinterpret_cast<const float4*>(p.out + off[u]);
+        if (p.mask_y != nullptr) ym[u] = ld4(p.mask_y + off[u]);
         if (p.ex_x != nullptr) {
-          const float* xe = p.ex_x + (o >> 4) * p.ex_K;             // output pixel index = o / 16
-          for (int k = 0; k < p.ex_K; ++k) {
-            const float xk = __ldg(xe + k);
+#pragma unroll
+          for (int k = 0; k < PW_EX_KMAX; ++k) xe[u][k] = k < p.ex_K ? __ldg(p.ex_x + (off[u] >> 4) * p.ex_K + k) : 0.f;
+        }
+        v[u] = *reinterpret_cast<const float4*>(so + px * PWD_SROW + (dy * 2 + dx) * 16 + j * 4);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = (tid + ((b4 * 4 + u) % PER_RUN) * PWD_THREADS) & 3;
+        if (p.ex_x != nullptr) {
+#pragma unroll
+          for (int k = 0; k < PW_EX_KMAX; ++k) {
             const float* wk = exw + k * 16 + j * 4;
-            v.x = fmaf(xk, wk[0], v.x); v.y = fmaf(xk, wk[1], v.y); v.z = fmaf(xk, wk[2], v.z); v.w = fmaf(xk, wk[3], v.w);
+            v[u].x = fmaf(xe[u][k], wk[0], v[u].x); v[u].y = fmaf(xe[u][k], wk[1], v[u].y);
+            v[u].z = fmaf(xe[u][k], wk[2], v[u].z); v[u].w = fmaf(xe[u][k], wk[3], v[u].w);
           }
         }
         if (p.beta != 0.f) {
-          const float4 old = *reinterpret_cast<const float4*>(p.out + o);
-          v.x += p.beta * old.x; v.y += p.beta * old.y; v.z += p.beta * old.z; v.w += p.beta * old.w;
+          v[u].x += p.beta * old[u].x; v[u].y += p.beta * old[u].y; v[u].z += p.beta * old[u].z; v[u].w += p.beta * old[u].w;
         }
         if (p.mask_y != nullptr) {
-          const float4 y = ld4(p.mask_y + o);
-          v.x *= act_bwd_from_y(y.x, p.mask_act); v.y *= act_bwd_from_y(y.y, p.mask_act);
-          v.z *= act_bwd_from_y(y.z, p.mask_act); v.w *= act_bwd_from_y(y.w, p.mask_act);
+          v[u].x *= act_bwd_from_y(ym[u].x, p.mask_act); v[u].y *= act_bwd_from_y(ym[u].y, p.mask_act);
+          v[u].z *= act_bwd_from_y(ym[u].z, p.mask_act); v[u].w *= act_bwd_from_y(ym[u].w, p.mask_act);
         }
-        *reinterpret_cast<float4*>(p.out + o) = v;
+        *reinterpret_cast<float4*>(p.out + off[u]) = v[u];
       }
     }
   }

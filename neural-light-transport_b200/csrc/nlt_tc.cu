@@ -85,8 +85,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// DIAGNOSTIC switch (NLT_TC_ABLATE bit 32): poll with the non-suspending test_wait instead of try_wait
+__device__ int g_tc_poll = 0;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
+  if (g_tc_poll) {
+    while (!mbar_test_wait(bar, parity)) {
+      if (++spins > TC_SPIN_LIMIT) { asm volatile("trap;"); }
+    }
+    return;
+  }
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > TC_SPIN_LIMIT) { asm volatile("trap;"); }
   }
@@ -883,7 +900,11 @@ static TcPlan tc_plan(const GConvK& k) {
   if (get_encode() == nullptr) return pl;
   {
     static int ablate = -1;
-    if (ablate < 0) { const char* e = getenv("NLT_TC_ABLATE"); ablate = e ? atoi(e) : 0; }
+    if (ablate < 0) {
+      const char* e = getenv("NLT_TC_ABLATE");
+      ablate = e ? atoi(e) : 0;
+      if (ablate & 32) { const int one = 1; cudaMemcpyToSymbol(g_tc_poll, &one, sizeof(int)); }
+    }
     p.ablate = ablate;
   }
   pl.ok = true;

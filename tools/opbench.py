@@ -62,6 +62,9 @@ def main():
     ap.add_argument('--iters', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--opt', nargs='*', default=[], help='nlt_set_option pairs, e.g. dconv_wide32=1 tc=0')
+    ap.add_argument('--graph', action='store_true',
+                    help='GPU-only times: capture the launches in a CUDA graph and time replays (eager CUDA-event times of '
+                         'microsecond kernels include the host latency between launches)')
     ap.add_argument('--cq-segs', dest='cq_segs', type=int, nargs='*', default=[3, 1, 1],
                     help='channel counts of the query input sources (cfg4: 3 60 1)')
     args = ap.parse_args()
@@ -79,13 +82,52 @@ def main():
     dev = torch.device('cuda')
     engine.USE_SIDE_STREAM = False
     want = set(args.layers) if args.layers else None
-    print('%-12s %10s %10s %10s   (ms per launch group; dgrad = all segments)' % ('layer', 'fwd', 'dgrad', 'wgrad'))
+    if args.graph:
+        print('%-12s %10s %10s   (ms per layer, CUDA-graph replay: fwd | fwd + dgrad + wgrad)' % ('layer', 'fwd', 'fwd+bwd'))
+    else:
+        print('%-12s %10s %10s %10s   (ms per launch group; dgrad = all segments)' % ('layer', 'fwd', 'dgrad', 'wgrad'))
     for name, kind, k, s, h, segc, cout, batch in table:
         if want is not None and name not in want:
             continue
         L = engine.ConvLayer(kind, k, s, cout, None if name.endswith('13.0') or name.endswith('.0.0') else 'leakyrelu')
         L.build(sum(segc), dev, torch.Generator().manual_seed(1))
         xs = [torch.randn(batch, h, h, c, device=dev) for c in segc]
+        if args.graph:
+            reps = 4
+
+            def body(bwd):
+                for _ in range(reps):
+                    acts = [engine.Act(x, act='leakyrelu', needs_grad=True) for x in xs]
+                    tape = engine.Tape() if bwd else None
+                    y = L.forward([engine.Seg(a) for a in acts], tape)
+                    if bwd:
+                        y.grad = torch.ones_like(y.t)
+                        tape.backward()
+            res = []
+            for bwd in (False, True):
+                ws = (engine.Workspace(), engine.Workspace())
+                with engine.use_workspaces(*ws):
+                    side = torch.cuda.Stream()
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        body(bwd)
+                    torch.cuda.current_stream().wait_stream(side)
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        body(bwd)
+                for _ in range(args.warmup):
+                    g.replay()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(args.iters):
+                    g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                res.append(e0.elapsed_time(e1) / args.iters / reps)
+                del g
+            print('%-12s %10.4f %10.4f' % (name, res[0], res[1]))
+            continue
         times = {'fwd': 0.0, 'dgrad': 0.0, 'wgrad': 0.0}
         for it in range(args.warmup + args.iters):
             engine.PROF.records = []
