@@ -22,8 +22,13 @@
 
 namespace nlt {
 
-constexpr int PWX_T = 256;          // pixels per tile
-constexpr int PWX_THREADS = 256;
+// Tile = 128 pixels per CTA of 128 threads, ONE shared-memory stage per CTA (45-51 KB): four to five CTAs share an SM and
+// cover each other's copy latency.  The first version (256-pixel tiles, double-buffered inside one 8-warp CTA per SM)
+// ran at 22 % issue utilisation: eight warps could not hide the LDCU / LDS latency in front of the FFMA2 chains.
+constexpr int PWX_T = 128;          // pixels per tile
+constexpr int PWX_THREADS = 128;
+constexpr int PWX_WARPS = PWX_THREADS / 32;
+constexpr int PWX_CTAS_PER_SM = 4;
 constexpr int PWX_N = 16;           // output channels
 constexpr int PWX_KMAX = 128;
 
@@ -116,36 +121,25 @@ __global__ void pwx_pack_w_kernel(const PwxParams p, const float* __restrict__ w
 }
 
 template <int K4>
-__global__ void __launch_bounds__(PWX_THREADS, 1)
+__global__ void __launch_bounds__(PWX_THREADS, PWX_CTAS_PER_SM)
 pwx_fwd_kernel(const PwxParams p, const float* __restrict__ bias, const int act, float* __restrict__ out) {
   extern __shared__ __align__(16) float smem[];
   constexpr int KROW = K4 * 4 + 4;
-  float* xs0 = smem;
-  float* xs1 = xs0 + PWX_T * KROW;
-  float* so = xs1 + PWX_T * KROW;                              // [PWX_T][PWX_OROW]
+  float* xs = smem;
+  float* so = xs + PWX_T * KROW;                               // [PWX_T][PWX_OROW]
   const int tid = threadIdx.x;
 
-  pwx_zero_rows(p, xs0, 0);
-  pwx_zero_rows(p, xs1, 0);
+  pwx_zero_rows(p, xs, 0);
   float bv[16];
 #pragma unroll
   for (int n = 0; n < 16; ++n) bv[n] = bias ? __ldg(bias + n) : 0.f;
   __syncthreads();
 
-  uint32_t t = blockIdx.x;
-  if (t < p.ntiles) pwx_stage_x(p, t, xs0);
-  cp_async_commit();
-  int buf = 0;
-  for (; t < p.ntiles; t += gridDim.x, buf ^= 1) {
-    float* xs = buf ? xs1 : xs0;
-    float* xn = buf ? xs0 : xs1;
-    const uint32_t tn = t + gridDim.x;
-    if (tn < p.ntiles) {
-      if (p.M - tn * PWX_T < (uint32_t)PWX_T) pwx_zero_rows(p, xn, p.M - tn * PWX_T);   // partial last tile
-      pwx_stage_x(p, tn, xn);
-    }
+  for (uint32_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+    if (p.M - t * PWX_T < (uint32_t)PWX_T) pwx_zero_rows(p, xs, p.M - t * PWX_T);   // partial last tile
+    pwx_stage_x(p, t, xs);
     cp_async_commit();
-    cp_async_wait<1>();
+    cp_async_wait<0>();
     __syncthreads();                                           // tile t has landed for every thread
 
     float2 acc[16];
@@ -179,29 +173,24 @@ pwx_fwd_kernel(const PwxParams p, const float* __restrict__ bias, const int act,
       const uint32_t px = qi >> 2, j = qi & 3;
       if (px < npx) dst[qi] = *reinterpret_cast<const float4*>(so + px * PWX_OROW + 4 * j);
     }
-    // so is rewritten only after the next tile's first barrier, xs[buf] after the staging at the top of the iteration
-    // that follows it: one more barrier is not needed
+    // the next iteration rewrites xs before its barrier and so only after it: no further barrier needed here
   }
-  cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------
 // weight gradient
 // ---------------------------------------------------------------------------------------------
 template <int NG>                  // float4 channel groups per lane (K4 <= 8*NG)
-__global__ void __launch_bounds__(PWX_THREADS, 1)
+__global__ void __launch_bounds__(PWX_THREADS, PWX_CTAS_PER_SM)
 pwx_wgrad_kernel(const PwxParams p, const float* __restrict__ G, float* __restrict__ ws, const int kd_pad,
                  const int bias_row) {
   extern __shared__ __align__(16) float smem[];
-  float* xs0 = smem;
-  float* xs1 = xs0 + PWX_T * p.krow;
-  float* gs0 = xs1 + PWX_T * p.krow;                           // [PWX_T][32]: dz duplicated (d, d)
-  float* gs1 = gs0 + PWX_T * 32;
+  float* xs = smem;
+  float* gs = xs + PWX_T * p.krow;                             // [PWX_T][32]: dz duplicated (d, d)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cg = lane & 7, ng = lane >> 3;
 
-  pwx_zero_rows(p, xs0, 0);
-  pwx_zero_rows(p, xs1, 0);
+  pwx_zero_rows(p, xs, 0);
   __syncthreads();
 
   float2 acc[NG][2][4];
@@ -213,56 +202,34 @@ pwx_wgrad_kernel(const PwxParams p, const float* __restrict__ G, float* __restri
 #pragma unroll
       for (int n = 0; n < 4; ++n) acc[g][h][n] = make_float2(0.f, 0.f);
 
-  // dz of a tile: PWX_T*16 floats = 1024 float4, 4 per thread; loaded one tile ahead into registers
-  auto load_g = [&](uint32_t t, float4 (&r)[4]) {
-    const uint32_t pix0 = t * PWX_T;
-    const uint32_t nq = min((uint32_t)PWX_T, p.M - pix0) * 4;
-    const float4* src = reinterpret_cast<const float4*>(G + (size_t)pix0 * 16);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t qi = tid + i * PWX_THREADS;
-      r[i] = qi < nq ? __ldg(src + qi) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
-  auto store_g = [&](float* gs, const float4 (&r)[4]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t qi = tid + i * PWX_THREADS;               // pixel = qi / 4, output quad = qi % 4
-      float4* d = reinterpret_cast<float4*>(gs + (qi >> 2) * 32 + (qi & 3) * 8);
-      d[0] = make_float4(r[i].x, r[i].x, r[i].y, r[i].y);
-      d[1] = make_float4(r[i].z, r[i].z, r[i].w, r[i].w);
-    }
-  };
-
-  uint32_t t = blockIdx.x;
-  float4 gr[4];
-  if (t < p.ntiles) {
-    if (p.M - t * PWX_T < (uint32_t)PWX_T) pwx_zero_rows(p, xs0, p.M - t * PWX_T);
-    pwx_stage_x(p, t, xs0);
-    load_g(t, gr);
-    store_g(gs0, gr);
-  }
-  cp_async_commit();
-  int buf = 0;
-  for (; t < p.ntiles; t += gridDim.x, buf ^= 1) {
-    float* xs = buf ? xs1 : xs0;
-    float* xn = buf ? xs0 : xs1;
-    float* gs = buf ? gs1 : gs0;
-    float* gn = buf ? gs0 : gs1;
-    const uint32_t tn = t + gridDim.x;
-    const bool more = tn < p.ntiles;
-    if (more) {
-      if (p.M - tn * PWX_T < (uint32_t)PWX_T) pwx_zero_rows(p, xn, p.M - tn * PWX_T);
-      pwx_stage_x(p, tn, xn);
-      load_g(tn, gr);
-    }
+  for (uint32_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+    if (p.M - t * PWX_T < (uint32_t)PWX_T) pwx_zero_rows(p, xs, p.M - t * PWX_T);
+    pwx_stage_x(p, t, xs);
     cp_async_commit();
-    cp_async_wait<1>();
+    {   // dz of the tile: PWX_T*16 floats = 512 float4, 4 per thread, stored duplicated (d, d)
+      const uint32_t pix0 = t * PWX_T;
+      const uint32_t nq = min((uint32_t)PWX_T, p.M - pix0) * 4;
+      const float4* src = reinterpret_cast<const float4*>(G + (size_t)pix0 * 16);
+      float4 r[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t qi = tid + i * PWX_THREADS;
+        r[i] = qi < nq ? __ldg(src + qi) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t qi = tid + i * PWX_THREADS;             // pixel = qi / 4, output quad = qi % 4
+        float4* d = reinterpret_cast<float4*>(gs + (qi >> 2) * 32 + (qi & 3) * 8);
+        d[0] = make_float4(r[i].x, r[i].x, r[i].y, r[i].y);
+        d[1] = make_float4(r[i].z, r[i].z, r[i].w, r[i].w);
+      }
+    }
+    cp_async_wait<0>();
     __syncthreads();                                           // x and dz of tile t are visible
 
 #pragma unroll 2
-    for (int i = 0; i < PWX_T / 8; ++i) {
-      const int px = warp + 8 * i;
+    for (int i = 0; i < PWX_T / PWX_WARPS; ++i) {
+      const int px = warp + PWX_WARPS * i;
       const float4* xr = reinterpret_cast<const float4*>(xs + px * p.krow);
       const float4* gq = reinterpret_cast<const float4*>(gs + px * 32 + ng * 8);
       const float4 g0 = gq[0], g1 = gq[1];                     // (d0,d0,d1,d1), (d2,d2,d3,d3)
@@ -280,13 +247,11 @@ pwx_wgrad_kernel(const PwxParams p, const float* __restrict__ G, float* __restri
         }
       }
     }
-    if (more) store_g(gn, gr);                                 // gn was last read in the previous iteration
     __syncthreads();                                           // everyone is done with xs / gs of tile t
   }
-  cp_async_wait<0>();
 
   // ---- cross-warp reduction in fixed order, one partial per CTA ----
-  float* red = smem;                                           // [8 warps][8*NG*4 columns][16]
+  float* red = smem;                                           // [warps][8*NG*4 columns][16]
   const int ncol = 8 * NG * 4;
 #pragma unroll
   for (int g = 0; g < NG; ++g)
@@ -297,7 +262,7 @@ pwx_wgrad_kernel(const PwxParams p, const float* __restrict__ G, float* __restri
       *reinterpret_cast<float4*>(r0) = make_float4(acc[g][h][0].x, acc[g][h][1].x, acc[g][h][2].x, acc[g][h][3].x);
       *reinterpret_cast<float4*>(r0 + 16) = make_float4(acc[g][h][0].y, acc[g][h][1].y, acc[g][h][2].y, acc[g][h][3].y);
     }
-  float* redb = red + (size_t)8 * ncol * 16;                   // [8 warps][16] bias partials
+  float* redb = red + (size_t)PWX_WARPS * ncol * 16;           // [warps][16] bias partials
   if (cg == 0) *reinterpret_cast<float4*>(redb + warp * 16 + ng * 4) = make_float4(bs[0], bs[1], bs[2], bs[3]);
   __syncthreads();
   float* dst = ws + (size_t)blockIdx.x * kd_pad * 16;
@@ -305,14 +270,14 @@ pwx_wgrad_kernel(const PwxParams p, const float* __restrict__ G, float* __restri
     const int col = i >> 4, n = i & 15;
     float s = 0.f;
 #pragma unroll
-    for (int wv = 0; wv < 8; ++wv) s += red[((size_t)wv * ncol + col) * 16 + n];
+    for (int wv = 0; wv < PWX_WARPS; ++wv) s += red[((size_t)wv * ncol + col) * 16 + n];
     const int row = col < PWX_KMAX ? p.col_row[col] : -1;
     if (row >= 0) dst[(size_t)row * 16 + n] = s;
   }
   if (tid < 16) {
     float s = 0.f;
 #pragma unroll
-    for (int wv = 0; wv < 8; ++wv) s += redb[wv * 16 + tid];
+    for (int wv = 0; wv < PWX_WARPS; ++wv) s += redb[wv * 16 + tid];
     dst[(size_t)bias_row * 16 + tid] = s;
   }
 }
@@ -372,14 +337,14 @@ static bool pwx_build(const GConvK& k, bool for_wgrad, PwxParams* p, int* kd_pad
 }
 
 static size_t pwx_fwd_smem(const PwxParams& p) {
-  return (2 * (size_t)PWX_T * p.krow + (size_t)PWX_T * PWX_OROW) * sizeof(float);
+  return ((size_t)PWX_T * p.krow + (size_t)PWX_T * PWX_OROW) * sizeof(float);
 }
 static size_t pwx_wgrad_smem(const PwxParams& p) {
-  const size_t stage = (2 * (size_t)PWX_T * p.krow + 2 * (size_t)PWX_T * 32) * sizeof(float);
-  const size_t red = ((size_t)8 * p.K4 * 4 * 16 + 8 * 16) * sizeof(float);
+  const size_t stage = ((size_t)PWX_T * p.krow + (size_t)PWX_T * 32) * sizeof(float);
+  const size_t red = ((size_t)PWX_WARPS * p.K4 * 4 * 16 + PWX_WARPS * 16) * sizeof(float);
   return stage > red ? stage : red;
 }
-constexpr size_t PWX_SMEM_MAX = 227 * 1024;
+constexpr size_t PWX_SMEM_MAX = 56 * 1024;      // four CTAs per SM
 
 int g_opt_pwx = -1;     // option "pwx" / NLT_PWX: 1 (default) the kernels of this file, 0 the general routes
 static bool pwx_enabled() {
@@ -403,7 +368,7 @@ static int pwx_fwd_launch(const PwxParams& p, const float* bias, int act, float*
     if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  const unsigned grid = p.ntiles < 148u ? p.ntiles : 148u;
+  const unsigned grid = p.ntiles < 148u * PWX_CTAS_PER_SM ? p.ntiles : 148u * PWX_CTAS_PER_SM;
   pwx_fwd_kernel<K4><<<grid, PWX_THREADS, smem, st>>>(p, bias, act, out);
   NLT_CUDA_LAUNCH_CHECK("pwx_fwd_kernel");
   return NLT_OK;
@@ -436,7 +401,9 @@ bool pwx_wgrad_applicable(const GConvK& k, const float* G) {
   return pwx_build(k, true, &p, nullptr, nullptr, nullptr) && pwx_wgrad_smem(p) <= PWX_SMEM_MAX;
 }
 
-static unsigned pwx_wgrad_grid(const PwxParams& p) { return p.ntiles < 148u ? p.ntiles : 148u; }
+static unsigned pwx_wgrad_grid(const PwxParams& p) {
+  return p.ntiles < 148u * PWX_CTAS_PER_SM ? p.ntiles : 148u * PWX_CTAS_PER_SM;
+}
 
 size_t pwx_wgrad_ws_floats(const GConvK& k) {
   PwxParams p;
