@@ -143,6 +143,7 @@ int launch_pw_conv(const GConvK& k, const float* bias, int act, float beta, cons
 // wide stencil kernel (pixel x 16 outputs per thread); option "dconv_wide" / NLT_DCONV_WIDE
 #define NLT_DCONV_WIDE_DEFAULT 1
 extern int g_opt_dconv_wide;
+extern int g_opt_dconv_cw;       // constant-memory weight table + FFMA2 form of the wide stencil kernel: 1 on (default)
 extern int g_opt_dconv_wide8;    // experimental 8-output form: 0 off (default), 1 on
 extern int g_opt_dconv_wide32;   // experimental 32-output form: 0 off (default), 1 one pixel / thread, 2 two pixels
 bool dconv_wide_applicable(const GConvK& k, const float* out, const float* mask_y);

@@ -688,6 +688,7 @@ int nlt_set_option(const char* name, int value) {
   if (strcmp(name, "wgrad_rows") == 0) { nlt::g_opt_wgrad_rows = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "tcs") == 0) { nlt::g_opt_tcs = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "pwx") == 0) { nlt::g_opt_pwx = value ? 1 : 0; return NLT_OK; }
+  if (strcmp(name, "dconv_cw") == 0) { nlt::g_opt_dconv_cw = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "dconv_wide") == 0) { nlt::g_opt_dconv_wide = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "dconv_wide32") == 0) { nlt::g_opt_dconv_wide32 = value; return NLT_OK; }
   if (strcmp(name, "dconv_wide8") == 0) { nlt::g_opt_dconv_wide8 = value; return NLT_OK; }

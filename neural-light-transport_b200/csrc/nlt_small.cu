@@ -539,17 +539,21 @@ dconv_small_kernel(const GConvK g, const float* __restrict__ bias, const int act
 // -----------------------------------------------------------------------------
 constexpr int DW_KMAX = 128;   // taps * channels of the widest routed stencil (32 -> 32 channels, 2x2)
 
-template <int DW_QT, int R, int MINB>
-__global__ void __launch_bounds__(PW_THREADS, MINB)
-dconv_wide_kernel(const GConvK g, const float* __restrict__ bias, const int act, const float beta,
-                  const float* __restrict__ mask_y, const int mask_act, float* __restrict__ out) {
-  __shared__ float4 Ws[(DW_QT == 4 ? PW_KMAX : DW_KMAX) * DW_QT];   // [k][quad]
-  const int tid = threadIdx.x;
+// CW = true: the weight table [k][quad] lives in CONSTANT memory (filled per launch by dconv_cw_pack_kernel + a
+// device-to-device symbol copy).  Every lane needs the same weight at the same time, so it arrives through the uniform
+// datapath (LDCU -> uniform registers) and the FMAs are issued as packed FFMA2 with a uniform operand: neither the
+// 128 broadcast LDS.128 per pixel of the shared-memory form nor half of its FMA instructions are issued.
+// One table per device: launches from different streams must not overlap (the engine issues forward convs and input
+// gradients from its main stream only; weight gradients, on the side stream, never use this kernel).
+__constant__ float4 dw_cw[DW_KMAX * 8];
+__device__ float4 dw_cw_stage[DW_KMAX * 8];
+
+__global__ void dconv_cw_pack_kernel(const GConvK g, int qt) {
   int ctot = 0;
   for (int s = 0; s < g.nseg; ++s) ctot += g.seg[s].C;
   const int ntaps = g.ay.nu * g.ax.nu;
-  for (int idx = tid; idx < ntaps * ctot * DW_QT; idx += PW_THREADS) {
-    const int k = idx / DW_QT, q = idx - k * DW_QT;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < ntaps * ctot * qt; idx += gridDim.x * blockDim.x) {
+    const int k = idx / qt, q = idx - k * qt;
     const int tapi = k / ctot, c = k - tapi * ctot;
     const int uy = tapi / g.ax.nu, ux = tapi - uy * g.ax.nu;
     const int tap = (g.ay.d0 + g.ay.ds * uy) * g.kw + (g.ax.d0 + g.ax.ds * ux);
@@ -559,9 +563,35 @@ dconv_wide_kernel(const GConvK g, const float* __restrict__ bias, const int act,
       const int n = q * 4 + e;
       v[e] = n < g.Cout ? __ldg(g.w + (long long)tap * g.wt + (long long)c * g.wc + (long long)n * g.wn) : 0.f;
     }
-    Ws[idx] = make_float4(v[0], v[1], v[2], v[3]);
+    dw_cw_stage[idx] = make_float4(v[0], v[1], v[2], v[3]);
   }
-  __syncthreads();
+}
+
+template <int DW_QT, int R, int MINB, bool CW = false>
+__global__ void __launch_bounds__(PW_THREADS, MINB)
+dconv_wide_kernel(const GConvK g, const float* __restrict__ bias, const int act, const float beta,
+                  const float* __restrict__ mask_y, const int mask_act, float* __restrict__ out) {
+  __shared__ float4 Ws[CW ? 1 : (DW_QT == 4 ? PW_KMAX : DW_KMAX) * DW_QT];   // [k][quad]
+  const int tid = threadIdx.x;
+  int ctot = 0;
+  for (int s = 0; s < g.nseg; ++s) ctot += g.seg[s].C;
+  const int ntaps = g.ay.nu * g.ax.nu;
+  if (!CW) {
+    for (int idx = tid; idx < ntaps * ctot * DW_QT; idx += PW_THREADS) {
+      const int k = idx / DW_QT, q = idx - k * DW_QT;
+      const int tapi = k / ctot, c = k - tapi * ctot;
+      const int uy = tapi / g.ax.nu, ux = tapi - uy * g.ax.nu;
+      const int tap = (g.ay.d0 + g.ay.ds * uy) * g.kw + (g.ax.d0 + g.ax.ds * ux);
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int n = q * 4 + e;
+        v[e] = n < g.Cout ? __ldg(g.w + (long long)tap * g.wt + (long long)c * g.wc + (long long)n * g.wn) : 0.f;
+      }
+      Ws[idx] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    __syncthreads();
+  }
 
   const uint32_t pbase = (uint32_t)blockIdx.x * (PW_THREADS * R) + tid;
   int pn[R], pty[R], ptx[R];
@@ -622,11 +652,22 @@ dconv_wide_kernel(const GConvK g, const float* __restrict__ bias, const int act,
           for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
             for (int j = 0; j < DW_QT; ++j) {
-              const float4 w = Ws[(k + kk) * DW_QT + j];
+              if constexpr (CW) {
+                const float4 w = dw_cw[(k + kk) * DW_QT + j];
 #pragma unroll
-              for (int r = 0; r < R; ++r) {
-                acc[r][j][0] = fmaf(a[r][kk], w.x, acc[r][j][0]); acc[r][j][1] = fmaf(a[r][kk], w.y, acc[r][j][1]);
-                acc[r][j][2] = fmaf(a[r][kk], w.z, acc[r][j][2]); acc[r][j][3] = fmaf(a[r][kk], w.w, acc[r][j][3]);
+                for (int r = 0; r < R; ++r) {
+                  const float2 aa = make_float2(a[r][kk], a[r][kk]);
+                  const float2 lo = __ffma2_rn(aa, make_float2(w.x, w.y), make_float2(acc[r][j][0], acc[r][j][1]));
+                  const float2 hi = __ffma2_rn(aa, make_float2(w.z, w.w), make_float2(acc[r][j][2], acc[r][j][3]));
+                  acc[r][j][0] = lo.x; acc[r][j][1] = lo.y; acc[r][j][2] = hi.x; acc[r][j][3] = hi.y;
+                }
+              } else {
+                const float4 w = Ws[(k + kk) * DW_QT + j];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                  acc[r][j][0] = fmaf(a[r][kk], w.x, acc[r][j][0]); acc[r][j][1] = fmaf(a[r][kk], w.y, acc[r][j][1]);
+                  acc[r][j][2] = fmaf(a[r][kk], w.z, acc[r][j][2]); acc[r][j][3] = fmaf(a[r][kk], w.w, acc[r][j][3]);
+                }
               }
             }
           }
@@ -714,8 +755,38 @@ bool dconv_wide_applicable(const GConvK& k, const float* out, const float* mask_
   return g_opt_dconv_wide8 > 0 && dconv_wide_common(k, out, mask_y, 8, DW_KMAX, true);
 }
 
+int g_opt_dconv_cw = -1;   // option "dconv_cw" / NLT_DCONV_CW: constant-memory weight table + FFMA2 (default on)
+
+static int dconv_cw_fill(const GConvK& k, int qt, cudaStream_t st) {
+  dconv_cw_pack_kernel<<<8, 256, 0, st>>>(k, qt);
+  NLT_CUDA_LAUNCH_CHECK("dconv_cw_pack_kernel");
+  int ctot = 0;
+  for (int s = 0; s < k.nseg; ++s) ctot += k.seg[s].C;
+  const size_t n = (size_t)k.ay.nu * k.ax.nu * ctot * qt;
+  void* stage = nullptr;
+  cudaError_t e = cudaGetSymbolAddress(&stage, dw_cw_stage);
+  if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(dw_cw, stage, n * sizeof(float4), 0, cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "dconv weight table: %s", cudaGetErrorString(e));
+  return NLT_OK;
+}
+
 int launch_dconv_wide(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
                       float* out, cudaStream_t st) {
+  if (g_opt_dconv_cw < 0) { const char* e = getenv("NLT_DCONV_CW"); g_opt_dconv_cw = (e && e[0] == '0') ? 0 : 1; }
+  if (g_opt_dconv_cw == 1 && (k.Cout == 16 || k.Cout == 8)) {
+    int rc = dconv_cw_fill(k, k.Cout / 4, st);
+    if (rc != NLT_OK) return rc;
+    if (k.Cout == 16) {
+      constexpr int R = 2;
+      const unsigned grid = (k.M + PW_THREADS * R - 1) / (PW_THREADS * R);
+      dconv_wide_kernel<4, R, 3, true><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
+    } else {
+      const unsigned grid = (k.M + PW_THREADS * 4 - 1) / (PW_THREADS * 4);
+      dconv_wide_kernel<2, 4, 3, true><<<grid, PW_THREADS, 0, st>>>(k, bias, act, beta, mask_y, mask_act, out);
+    }
+    NLT_CUDA_LAUNCH_CHECK("dconv_wide_kernel");
+    return NLT_OK;
+  }
   if (k.Cout == 16) {
     constexpr int R = 2;
     const unsigned grid = (k.M + PW_THREADS * R - 1) / (PW_THREADS * R);
