@@ -299,12 +299,13 @@ class TrainRun:
         """roofline leg: per-call CUDA events in a separate eager pass on ONE stream (not the timed value)"""
         import engine
         engine.PROF.enabled = (rank == 0)
+        side = engine.USE_SIDE_STREAM
         engine.USE_SIDE_STREAM = False
         try:
             for i in range(2):
                 self.step(self.resident[i % 2], eager=True)
         finally:
-            engine.USE_SIDE_STREAM = True
+            engine.USE_SIDE_STREAM = side
         if rank != 0:
             return None
         summ = engine.PROF.summary()

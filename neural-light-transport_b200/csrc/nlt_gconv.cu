@@ -786,7 +786,8 @@ int64_t nlt_gconv_wgrad_workspace_bytes(const nlt_gconv_desc* d) {
   GConvK ph[16];
   int np = 0;
   if (build_phases(d, ph, &np, /*allow_d2s=*/true) != NLT_OK) return -1;
-  if (np == 1 && ph[0].d2s && !wgrad_small_applicable(ph[0]) && build_phases(d, ph, &np, false) != NLT_OK) return -1;
+  if (np == 1 && ph[0].d2s && !wgrad_small_applicable(ph[0]) && !use_tc_wgrad(ph[0]) &&
+      build_phases(d, ph, &np, false) != NLT_OK) return -1;
   size_t mx = 0;
   for (int i = 0; i < np; ++i) {
     if (ph[i].M == 0) continue;
@@ -805,7 +806,9 @@ int nlt_gconv_wgrad(const nlt_gconv_desc* d, const float* G, float* dW, float* d
   int np = 0;
   int rc = build_phases(d, ph, &np, /*allow_d2s=*/true);
   if (rc != NLT_OK) return rc;
-  if (np == 1 && ph[0].d2s && !wgrad_small_applicable(ph[0])) rc = build_phases(d, ph, &np, false);
+  // a k == stride transposed conv keeps its one-pass depth-to-space form when a kernel takes it (the warp-stream
+  // kernel for narrow tiles, the tcgen05 kernel from K_d = 128 up); otherwise s*s phases
+  if (np == 1 && ph[0].d2s && !wgrad_small_applicable(ph[0]) && !use_tc_wgrad(ph[0])) rc = build_phases(d, ph, &np, false);
   if (rc != NLT_OK) return rc;
   NLT_CHECK_ARG(G != nullptr && dW != nullptr && workspace != nullptr, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;

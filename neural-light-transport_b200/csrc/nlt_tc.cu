@@ -983,7 +983,8 @@ struct WgPiece {
 struct WgParams {
   int N, Hl, Wl, TW, TH, tiles_x, tiles_y, total_ptiles;
   int mode_patch, ux_step, x_off, uy_step, y_off, Hs;     // A coordinate map (as TcParams)
-  int g_patch, g_px, g_py, g_Hs;                          // G on a strided sub-lattice (transposed phases)
+  int g_patch, g_px, g_py, g_Hs;                          // G on a strided sub-lattice (transposed phases); g_patch == 2: depth-to-space
+  int g_ct, g_s;                                          // depth-to-space: channels of the gradient tensor, stride
   int ntap_x, nseg, ctot, Kd;
   int seg_C[NLT_MAX_SEG], seg_coff[NLT_MAX_SEG];
   int n_mtiles, n_ntiles;
@@ -1057,10 +1058,17 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
       off += (WG_PT * w * 4 + 1023) & ~1023;
       k += w;
     }
-    const int gw = BN < 32 ? BN : 32;
+    const int gw = p.g_patch == 2 ? min(min(BN, 32), p.g_ct) : (BN < 32 ? BN : 32);
     for (int c = 0; c < BN; c += gw) {
       WgPiece& pc = pieces[np++];
       pc.is_g = 1; pc.seg = 0; pc.uy = 0; pc.ux = 0; pc.c0 = (int16_t)(ntile * BN + c); pc.w = (int16_t)gw;
+      if (p.g_patch == 2) {
+        // depth-to-space weight gradient: GEMM column n' = tap * cout + n is channel n of the gradient pixel
+        // (s*y + dy, s*x + dx) above lattice pixel (y, x)
+        const int ncol = ntile * BN + c, tap = ncol / p.g_ct;
+        pc.c0 = (int16_t)(ncol - tap * p.g_ct);
+        pc.uy = (int16_t)(tap / p.g_s); pc.ux = (int16_t)(tap % p.g_s);
+      }
       pc.row = (int16_t)c; pc.pad = 0; pc.raw_off = off;
       off += (WG_PT * gw * 4 + 1023) & ~1023;
     }
@@ -1110,7 +1118,9 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
         for (int i = 0; i < n_pieces; ++i) {
           const WgPiece pc = pieces[i];
           if (pc.is_g) {
-            if (p.g_patch)
+            if (p.g_patch == 2)
+              tma_load_5d(base + pc.raw_off, &maps.g, bar_rfull(stage), pc.c0, pc.ux, tx0, pc.uy, n * p.g_Hs + ty0);
+            else if (p.g_patch)
               tma_load_5d(base + pc.raw_off, &maps.g, bar_rfull(stage), pc.c0, p.g_px, tx0, p.g_py, n * p.g_Hs + ty0);
             else
               tma_load_4d(base + pc.raw_off, &maps.g, bar_rfull(stage), pc.c0, tx0, ty0, n);
@@ -1264,7 +1274,8 @@ struct WgPlan {
 static WgPlan wg_plan(const GConvK& k) {
   WgPlan pl;
   memset(&pl, 0, sizeof(pl));
-  if (k.d2s || k.M == 0 || k.Cout % 16 != 0) return pl;
+  if (k.M == 0 || k.Cout % 16 != 0) return pl;
+  if (k.d2s && (k.cout_true % 4 != 0 || (k.cout_true & (k.cout_true - 1)) != 0) && k.cout_true % 32 != 0) return pl;
   int ctot = 0;
   for (int s = 0; s < k.nseg; ++s) {
     const Seg& sg = k.seg[s];
@@ -1295,7 +1306,12 @@ static WgPlan wg_plan(const GConvK& k) {
   p.ux_step = k.ax.iu; p.x_off = k.ax.i0; p.uy_step = k.ay.iu; p.y_off = k.ay.i0;
   p.Hs = patch ? k.Hin / k.ay.it : 0;
   if (k.ay.os != k.ax.os) return pl;
-  if (k.ay.os == 1) {
+  if (k.d2s) {
+    // ONE pass over the input lattice for all s*s taps (instead of s*s phases that each re-read the input):
+    // the gradient pieces of a stage come from the s*s pixels above each lattice pixel
+    if (k.Hout != p.Hl * k.d2s_s || k.Wout != p.Wl * k.d2s_s) return pl;
+    p.g_patch = 2; p.g_py = 0; p.g_px = 0; p.g_Hs = k.Hout / k.d2s_s; p.g_ct = k.cout_true; p.g_s = k.d2s_s;
+  } else if (k.ay.os == 1) {
     if (k.ay.o0 != 0 || k.ax.o0 != 0 || k.Hout != p.Hl || k.Wout != p.Wl) return pl;
     p.g_patch = 0;
   } else {
@@ -1336,7 +1352,8 @@ static WgPlan wg_plan(const GConvK& k) {
       if (bytes > worst) worst = bytes;
     }
     (void)k_hi;
-    const int gw = pl.bn < 32 ? pl.bn : 32;
+    int gw = pl.bn < 32 ? pl.bn : 32;
+    if (k.d2s && k.cout_true < gw) gw = k.cout_true;
     worst += (pl.bn / gw) * ((WG_PT * gw * 4 + 1023) & ~1023);
     p.raw_stage_bytes = worst;
   }
@@ -1420,8 +1437,10 @@ int launch_tc_wgrad(const GConvK& k, const float* G, float* ws, WgradK* w, size_
       if (r != CUDA_SUCCESS) return set_err(NLT_ERR_CUDA, "cuTensorMapEncodeTiled(wgrad A %d/%d) failed: %d", s, widths[wi], (int)r);
     }
   {
-    const int gw = pl.bn < 32 ? pl.bn : 32;
-    CUresult r = wg_encode(enc, &maps.g, G, k.Cout, k.Wout, k.Hout, k.N, gw, p.TW, p.TH, p.g_patch ? k.ay.os : 1);
+    int gw = pl.bn < 32 ? pl.bn : 32;
+    if (k.d2s && k.cout_true < gw) gw = k.cout_true;
+    CUresult r = k.d2s ? wg_encode(enc, &maps.g, G, k.cout_true, k.Wout, k.Hout, k.N, gw, p.TW, p.TH, k.d2s_s)
+                       : wg_encode(enc, &maps.g, G, k.Cout, k.Wout, k.Hout, k.N, gw, p.TW, p.TH, p.g_patch ? k.ay.os : 1);
     if (r != CUDA_SUCCESS) return set_err(NLT_ERR_CUDA, "cuTensorMapEncodeTiled(wgrad G) failed: %d", (int)r);
   }
   pl.p.ws = ws;

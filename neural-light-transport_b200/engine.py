@@ -154,7 +154,7 @@ def side_stream():
     return _SIDE[dev]
 
 
-USE_SIDE_STREAM = True
+USE_SIDE_STREAM = os.environ.get('NLT_NO_SIDE_STREAM', '0') != '1'
 # called as WGRAD_HOOK(layer) right after a layer's weight-gradient launch has been issued (on the side stream when
 # USE_SIDE_STREAM): trainvali.GradReducer starts the early part of the gradient all-reduce from it
 WGRAD_HOOK = None
