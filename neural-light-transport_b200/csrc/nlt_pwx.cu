@@ -456,23 +456,21 @@ int launch_pwx_wgrad(const GConvK& k, const float* G, float* ws, WgradK* w, size
 //     (beta = 1), the activation mask and the fused pointwise term (the final 1x1 conv's input gradient riding along,
 //     nlt_gconv_fwd_fused) applied in that same coalesced pass.
 // =============================================================================================
-constexpr int PWD_T = 256;
 constexpr int PWD_THREADS = 256;
-constexpr int PWD_SROW = 68;                                        // floats per staged pixel (64 + 4)
-__constant__ float2 pwd_cw[32 * 32];                               // [k][m] = (W[k][n' = 2m], W[k][2m + 1]), n' = tap*16 + c
-__device__ float2 pwd_cw_stage[32 * 32];
+constexpr int PWD_KMAX = 64, PWD_NMAX = 128;                       // gradient channels, outputs per gradient pixel
+__constant__ float2 pwd_cw[PWD_KMAX * PWD_NMAX / 2];               // [k][m] = (W[k][n' = 2m], W[k][2m + 1]), n' = tap*CS + c
+__device__ float2 pwd_cw_stage[PWD_KMAX * PWD_NMAX / 2];
 
 struct PwdParams {
   const float* dz;        // [M][K]
   int K;
   uint32_t M;             // lattice pixels = N * Hin * Win
-  int Win;                // multiple of PWD_T
-  int tiles_per_row;
+  int Win;                // power of two; a tile is TP consecutive lattice pixels: part of a row or whole rows
   uint32_t ntiles;
   float beta;
   const float* mask_y;
   int mask_act;
-  float* out;             // [N*2Hin][2Win][16]
+  float* out;             // [N*2Hin][2Win][CS]
   // fused pointwise term: out[opix, c] += sum_k ex_x[opix, k] * ex_w[k*wk + c*wn]
   const float* ex_x;
   int ex_K;
@@ -480,91 +478,108 @@ struct PwdParams {
   long long ex_wk, ex_wn;
 };
 
-__global__ void pwd_pack_w_kernel(const GConvK g, int K) {
-  const int total = K * 32;
+__global__ void pwd_pack_w_kernel(const GConvK g, int K, int CS) {
+  const int half = 2 * CS;                                         // pairs per k: 4*CS / 2
+  const int total = K * half;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int kk = i >> 5, m = i & 31;
-    const int np = 2 * m, tap = np >> 4, c = np & 15;               // (n', n' + 1) share the tap: c is even
+    const int kk = i / half, m = i - kk * half;
+    const int np = 2 * m, tap = np / CS, c = np - tap * CS;         // (n', n' + 1) share the tap: c is even
     const float* w0 = g.w + (long long)tap * g.wt + (long long)kk * g.wc + (long long)c * g.wn;
     pwd_cw_stage[i] = make_float2(__ldg(w0), __ldg(w0 + g.wn));
   }
 }
 
-template <int K>
+// K gradient channels, CS channels of the source whose gradient is produced (16: thread = pixel, all four taps;
+// 32: two threads per pixel, thread half h owns the taps of output row 2y + h -- a warp is uniform in h, so the
+// constant-memory operands stay warp-uniform).
+template <int K, int CS>
 __global__ void __launch_bounds__(PWD_THREADS, 2)
 pwd2s_kernel(const PwdParams p) {
-  extern __shared__ __align__(16) float so[];                      // [PWD_T][PWD_SROW]
-  __shared__ float exw[PW_EX_KMAX * 16];
+  constexpr int TPP = CS / 16;                                     // threads per gradient pixel
+  constexpr int TP = PWD_THREADS / TPP;                            // gradient pixels per tile
+  constexpr int NP = 4 * CS;                                       // outputs per gradient pixel
+  constexpr int SROW = NP + 4;                                     // floats per staged pixel
+  constexpr int C4 = CS / 4;
+  extern __shared__ __align__(16) float so[];                      // [TP][SROW]
+  __shared__ float exw[PW_EX_KMAX * CS];
   const int tid = threadIdx.x;
-  if (tid < PW_EX_KMAX * 16)
-    exw[tid] = (p.ex_x != nullptr && tid < p.ex_K * 16)
-                   ? __ldg(p.ex_w + (long long)(tid >> 4) * p.ex_wk + (long long)(tid & 15) * p.ex_wn) : 0.f;
+  const int half = tid / TP, lp = tid - half * TP;                 // tap-row half, pixel inside the tile
+  for (int i = tid; i < PW_EX_KMAX * CS; i += PWD_THREADS)
+    exw[i] = (p.ex_x != nullptr && i < p.ex_K * CS)
+                 ? __ldg(p.ex_w + (long long)(i / CS) * p.ex_wk + (long long)(i % CS) * p.ex_wn) : 0.f;
   __syncthreads();
   const int Wout = 2 * p.Win;
+  const int wtile = p.Win < TP ? p.Win : TP;                       // lattice pixels per row inside a tile
   auto load_x = [&](uint32_t t, float4 (&xv)[K / 4]) {
-    const uint32_t row = t / (uint32_t)p.tiles_per_row;
-    const uint32_t x0 = (t - row * (uint32_t)p.tiles_per_row) * PWD_T;
-    const float4* xr = reinterpret_cast<const float4*>(p.dz + ((size_t)row * p.Win + x0 + tid) * K);
+    const float4* xr = reinterpret_cast<const float4*>(p.dz + ((size_t)t * TP + lp) * K);
 #pragma unroll
     for (int q = 0; q < K / 4; ++q) xv[q] = __ldg(xr + q);
   };
-  float4 xcur[K / 4];
-  if (blockIdx.x < p.ntiles) load_x(blockIdx.x, xcur);
+  constexpr bool PREFETCH = K <= 32;                               // K = 64: the 64 extra registers would spill
+  float4 xcur[PREFETCH ? K / 4 : 1];
+  if (PREFETCH && blockIdx.x < p.ntiles) load_x(blockIdx.x, reinterpret_cast<float4(&)[K / 4]>(xcur));
   for (uint32_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-    const uint32_t row = t / (uint32_t)p.tiles_per_row;             // flat lattice row n*Hin + y
-    const uint32_t x0 = (t - row * (uint32_t)p.tiles_per_row) * PWD_T;
-    // ---- 64 outputs of this gradient pixel ----
-    float2 acc[32];                                                // (out[2m], out[2m + 1])
+    const uint32_t start = t * TP;                                 // first lattice pixel (flat: (n*Hin + y)*Win + x)
+    const uint32_t row0 = start / (uint32_t)p.Win, x0 = start - row0 * (uint32_t)p.Win;
+    // ---- this thread's 64 outputs ----
+    float2 acc[32];
 #pragma unroll
     for (int m = 0; m < 32; ++m) acc[m] = make_float2(0.f, 0.f);
+    const float2* cw = pwd_cw + (TPP == 1 ? 0 : half * 32);        // warp-uniform: a warp lies in one half
+    const float4* xrow = reinterpret_cast<const float4*>(p.dz + ((size_t)t * TP + lp) * K);
 #pragma unroll
     for (int q = 0; q < K / 4; ++q) {
-      const float xs[4] = {xcur[q].x, xcur[q].y, xcur[q].z, xcur[q].w};
+      const float4 xq = PREFETCH ? xcur[q] : __ldg(xrow + q);
+      const float xs[4] = {xq.x, xq.y, xq.z, xq.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 xx = make_float2(xs[e], xs[e]);
 #pragma unroll
-        for (int m = 0; m < 32; ++m) acc[m] = __ffma2_rn(xx, pwd_cw[(4 * q + e) * 32 + m], acc[m]);
+        for (int m = 0; m < 32; ++m) acc[m] = __ffma2_rn(xx, cw[(4 * q + e) * (NP / 2) + m], acc[m]);
       }
     }
-    if (t + gridDim.x < p.ntiles) load_x(t + gridDim.x, xcur);      // next tile's gradient rows: in flight during the write phase
+    if (PREFETCH && t + gridDim.x < p.ntiles)                      // next tile's gradient rows: in flight during the write phase
+      load_x(t + gridDim.x, reinterpret_cast<float4(&)[K / 4]>(xcur));
     __syncthreads();                                               // the previous tile's staged values have been read
-    float4* srow = reinterpret_cast<float4*>(so + tid * PWD_SROW);
+    float4* srow = reinterpret_cast<float4*>(so + lp * SROW + half * 64);
 #pragma unroll
     for (int j = 0; j < 16; ++j) srow[j] = make_float4(acc[2 * j].x, acc[2 * j].y, acc[2 * j + 1].x, acc[2 * j + 1].y);
     __syncthreads();
-    // ---- two contiguous output runs (rows 2*row and 2*row + 1), 2 * PWD_T pixels of 16 channels each ----
-    // 16 float4 per thread in batches of 4: every read-modify-write operand of a batch is requested before the first
-    // one is used (enough bytes in flight per SM to cover the DRAM latency)
-    constexpr int PER_RUN = (2 * PWD_T * 4) / PWD_THREADS;         // float4 per thread and run (8)
+    // ---- coalesced output runs: per lattice row of the tile, rows 2*row and 2*row + 1 of the output, 2*wtile
+    // pixels of CS channels each.  TP*CS float4 per tile = 16 per thread, in batches of 4: every read-modify-write
+    // operand of a batch is requested before the first one is used ----
+    constexpr int PER_THREAD = TP * CS / PWD_THREADS;              // 16
 #pragma unroll 1
-    for (int b4 = 0; b4 < 2 * PER_RUN / 4; ++b4) {
+    for (int b4 = 0; b4 < PER_THREAD / 4; ++b4) {
       float4 v[4], old[4], ym[4];
       float xe[4][PW_EX_KMAX];
       size_t off[4];
+      int jq[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int i = b4 * 4 + u;                                  // 0 .. 15
-        const int dy = i / PER_RUN;
-        const int q = tid + (i - dy * PER_RUN) * PWD_THREADS;      // float4 index inside the run
-        const int ox = q >> 2, j = q & 3;
-        const int px = ox >> 1, dx = ox & 1;
-        off[u] = ((size_t)(2 * row + dy) * Wout + 2 * x0) * 16 + (size_t)q * 4;
+        const int f = tid + (b4 * 4 + u) * PWD_THREADS;            // float4 index inside the tile's outputs
+        const int j = f % C4;
+        int r = f / C4;
+        const int ox = r % (2 * wtile);
+        r /= 2 * wtile;
+        const int dy = r & 1, lr = r >> 1;                         // output row parity, lattice row inside the tile
+        const int px = lr * wtile + (ox >> 1), dx = ox & 1;
+        jq[u] = j;
+        off[u] = (((size_t)(2 * (row0 + lr) + dy) * Wout + 2 * x0 + ox) * CS) + (size_t)j * 4;
         if (p.beta != 0.f) old[u] = *reinterpret_cast<const float4*>(p.out + off[u]);
         if (p.mask_y != nullptr) ym[u] = ld4(p.mask_y + off[u]);
         if (p.ex_x != nullptr) {
 #pragma unroll
-          for (int k = 0; k < PW_EX_KMAX; ++k) xe[u][k] = k < p.ex_K ? __ldg(p.ex_x + (off[u] >> 4) * p.ex_K + k) : 0.f;
+          for (int k = 0; k < PW_EX_KMAX; ++k) xe[u][k] = k < p.ex_K ? __ldg(p.ex_x + (off[u] / CS) * p.ex_K + k) : 0.f;
         }
-        v[u] = *reinterpret_cast<const float4*>(so + px * PWD_SROW + (dy * 2 + dx) * 16 + j * 4);
+        v[u] = *reinterpret_cast<const float4*>(so + px * SROW + (dy * 2 + dx) * CS + j * 4);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int j = (tid + ((b4 * 4 + u) % PER_RUN) * PWD_THREADS) & 3;
         if (p.ex_x != nullptr) {
 #pragma unroll
           for (int k = 0; k < PW_EX_KMAX; ++k) {
-            const float* wk = exw + k * 16 + j * 4;
+            const float* wk = exw + k * CS + jq[u] * 4;
             v[u].x = fmaf(xe[u][k], wk[0], v[u].x); v[u].y = fmaf(xe[u][k], wk[1], v[u].y);
             v[u].z = fmaf(xe[u][k], wk[2], v[u].z); v[u].w = fmaf(xe[u][k], wk[3], v[u].w);
           }
@@ -582,33 +597,43 @@ pwd2s_kernel(const PwdParams p) {
   }
 }
 
+static bool pwd_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
 bool pwd2s_applicable(const GConvK& k, const float* bias, int act, const float* out, const float* mask_y,
                       const PwExtra* ex) {
   if (!pwx_enabled()) return false;
-  if (!k.d2s || k.d2s_s != 2 || k.nseg != 1 || k.cout_true != 16 || k.Cout != 64 || k.M == 0) return false;
+  if (!k.d2s || k.d2s_s != 2 || k.nseg != 1 || (k.cout_true != 16 && k.cout_true != 32) || k.Cout != 4 * k.cout_true ||
+      k.M == 0) return false;
   const Seg& sg = k.seg[0];
-  if ((sg.C != 16 && sg.C != 32) || !sg.vec || sg.sub != nullptr || sg.bcast) return false;
+  const int K = sg.C;
+  if (!sg.vec || sg.sub != nullptr || sg.bcast) return false;
+  if (k.cout_true == 16 ? (K != 16 && K != 32) : (K != 32 && K != 64)) return false;
   if (bias != nullptr || act != 0) return false;
-  if (k.ax.nt != k.Win || k.ay.nt != k.Hin || k.Win % PWD_T != 0) return false;
+  const int TP = PWD_THREADS / (k.cout_true / 16);
+  if (k.ax.nt != k.Win || k.ay.nt != k.Hin || !pwd_pow2(k.Win) || k.M % TP != 0) return false;
+  if (k.Win < TP && (TP % k.Win != 0 || ((long long)k.N * k.Hin) % (TP / k.Win) != 0)) return false;
   if (k.Hout != 2 * k.Hin || k.Wout != 2 * k.Win) return false;
   if (!aligned16(out) || (mask_y != nullptr && !aligned16(mask_y))) return false;
   if (ex != nullptr && (ex->K < 1 || ex->K > PW_EX_KMAX || ex->x == nullptr || ex->w == nullptr)) return false;
   return true;
 }
 
-template <int K>
-static int pwd2s_launch(const PwdParams& p, cudaStream_t st) {
-  const size_t smem = (size_t)PWD_T * PWD_SROW * sizeof(float);
+template <int K, int CS>
+static int pwd2s_launch(const PwdParams& p0, cudaStream_t st) {
+  constexpr int TP = PWD_THREADS / (CS / 16);
+  PwdParams p = p0;
+  p.ntiles = p.M / TP;
+  const size_t smem = (size_t)TP * (4 * CS + 4) * sizeof(float);
   int dev = 0;
   cudaGetDevice(&dev);
   static bool attr_set[64] = {false};
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(pwd2s_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(pwd2s_kernel<K, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const unsigned grid = p.ntiles < 296u ? p.ntiles : 296u;          // 2 CTAs per SM
-  pwd2s_kernel<K><<<grid, PWD_THREADS, smem, st>>>(p);
+  pwd2s_kernel<K, CS><<<grid, PWD_THREADS, smem, st>>>(p);
   NLT_CUDA_LAUNCH_CHECK("pwd2s_kernel");
   return NLT_OK;
 }
@@ -617,21 +642,21 @@ static int pwd2s_launch(const PwdParams& p, cudaStream_t st) {
 // one device must not overlap; the engine issues input gradients from its main stream only.
 int launch_pwd2s(const GConvK& k, float beta, const float* mask_y, int mask_act, float* out, cudaStream_t st,
                  const PwExtra* ex) {
-  const int K = k.seg[0].C;
-  pwd_pack_w_kernel<<<4, 256, 0, st>>>(k, K);
+  const int K = k.seg[0].C, CS = k.cout_true;
+  pwd_pack_w_kernel<<<8, 256, 0, st>>>(k, K, CS);
   NLT_CUDA_LAUNCH_CHECK("pwd_pack_w_kernel");
   void* stage = nullptr;
   cudaError_t e = cudaGetSymbolAddress(&stage, pwd_cw_stage);
   if (e == cudaSuccess)
-    e = cudaMemcpyToSymbolAsync(pwd_cw, stage, (size_t)K * 32 * sizeof(float2), 0, cudaMemcpyDeviceToDevice, st);
+    e = cudaMemcpyToSymbolAsync(pwd_cw, stage, (size_t)K * 2 * CS * sizeof(float2), 0, cudaMemcpyDeviceToDevice, st);
   if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "pwd weight table: %s", cudaGetErrorString(e));
   PwdParams p;
   memset(&p, 0, sizeof(p));
-  p.dz = k.seg[0].ptr; p.K = K; p.M = k.M; p.Win = k.Win; p.tiles_per_row = k.Win / PWD_T;
-  p.ntiles = k.M / PWD_T;
+  p.dz = k.seg[0].ptr; p.K = K; p.M = k.M; p.Win = k.Win;
   p.beta = beta; p.mask_y = mask_y; p.mask_act = mask_act; p.out = out;
   if (ex != nullptr) { p.ex_x = ex->x; p.ex_K = ex->K; p.ex_w = ex->w; p.ex_wk = ex->wk; p.ex_wn = ex->wn; }
-  return K == 16 ? pwd2s_launch<16>(p, st) : pwd2s_launch<32>(p, st);
+  if (CS == 16) return K == 16 ? pwd2s_launch<16, 16>(p, st) : pwd2s_launch<32, 16>(p, st);
+  return K == 32 ? pwd2s_launch<32, 32>(p, st) : pwd2s_launch<64, 32>(p, st);
 }
 
 }  // namespace nlt

@@ -85,6 +85,10 @@ GEOMS = [
     # wide pointwise conv into 16 channels (nlt_pwx.cu: level 0 of the 64-channel query stack): cp.async-staged
     # 256-pixel tiles, ragged last tile, float4-able and scalar sources mixed, K not a multiple of 32
     ('conv', 2, 2, 8, 512, [16, 16], 32),       # its input gradients: depth-to-space K = 32 -> 4 x 16 (pwd2s kernel)
+    ('conv', 2, 2, 16, 256, [32], 64),          # pwd2s with 32-channel sources (two threads per gradient pixel), K = 64
+    ('conv', 2, 2, 32, 128, [32, 32], 64),      # ... lattice rows narrower than a tile: two rows per tile
+    ('conv', 2, 2, 32, 128, [16], 16),          # ... four lattice rows per tile, 16-channel source
+    ('conv', 2, 2, 32, 128, [32], 32),          # K = 32 -> 4 x 32
     ('conv', 1, 1, 33, 37, [3, 60, 1], 16),
     ('conv', 1, 1, 32, 32, [64], 16),
     ('conv', 1, 1, 24, 24, [20, 4], 16),
