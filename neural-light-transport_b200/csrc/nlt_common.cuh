@@ -177,6 +177,11 @@ bool pwd2s_applicable(const GConvK& k, const float* bias, int act, const float* 
 int launch_pwd2s(const GConvK& k, float beta, const float* mask_y, int mask_act, float* out, cudaStream_t st,
                  const PwExtra* ex);
 
+// weight gradient of the 2x2 convs of the 16- / 32-channel levels (staged input patch + FFMA2, nlt_pwx.cu)
+bool pws_wgrad_applicable(const GConvK& k, const float* G);
+size_t pws_wgrad_ws_floats(const GConvK& k);
+int launch_pws_wgrad(const GConvK& k, const float* G, float* ws, WgradK* w, size_t* KD_pad, cudaStream_t st);
+
 // tcgen05 tensor-core path (nlt_tc.cu)
 #define NLT_TCS_DEFAULT 0
 extern int g_opt_tcs;            // TS form of the forward kernel (A operand through tensor memory)

@@ -714,6 +714,9 @@ int nlt_gconv_fwd_ws(const nlt_gconv_desc* d, const float* bias, int act, float 
   NLT_CHECK_ARG(act >= 0 && act <= 3 && mask_act >= 0 && mask_act <= 3, "bad activation code");
   NLT_CHECK_ARG(beta == 0.f || beta == 1.f, "beta must be 0 or 1");
   cudaStream_t st = (cudaStream_t)stream;
+  // the streaming depth-to-space kernel outruns the tcgen05 kernel on its shapes (level-3 input gradients: 64 -> 4 x 32)
+  if (np == 1 && ph[0].M > 0 && pwd2s_applicable(ph[0], bias, act, out, mask_y, nullptr))
+    return launch_pwd2s(ph[0], beta, mask_y, mask_act, out, st, nullptr);
   if (np == 1 && workspace != nullptr && tc_enabled() && ph[0].M > 0 && tc_applicable(ph[0]) &&
       (int64_t)tc_workspace_bytes(ph[0]) <= workspace_bytes)
     return launch_tc(ph[0], bias, act, beta, mask_y, mask_act, out, workspace, (size_t)workspace_bytes, st);
@@ -792,6 +795,7 @@ int64_t nlt_gconv_wgrad_workspace_bytes(const nlt_gconv_desc* d) {
   for (int i = 0; i < np; ++i) {
     if (ph[i].M == 0) continue;
     size_t need = pwx_wgrad_applicable(ph[i], nullptr) ? pwx_wgrad_ws_floats(ph[i])
+                  : pws_wgrad_applicable(ph[i], nullptr) ? pws_wgrad_ws_floats(ph[i])
                   : use_tc_wgrad(ph[i]) ? tc_wgrad_ws_floats(ph[i])
                   : wgrad_tpp_applicable(ph[i]) ? wgrad_tpp_ws_floats(ph[i])
                   : wgrad_small_applicable(ph[i]) ? wgrad_small_ws_floats(ph[i]) : plan_wgrad(ph[i]).ws_floats;
@@ -821,6 +825,9 @@ int nlt_gconv_wgrad(const nlt_gconv_desc* d, const float* G, float* dW, float* d
     size_t KD_pad = 0;
     if (pwx_wgrad_applicable(k, G) && (int64_t)(pwx_wgrad_ws_floats(k) * sizeof(float)) <= workspace_bytes) {
       rc = launch_pwx_wgrad(k, G, ws, &w, &KD_pad, st);
+      if (rc != NLT_OK) return rc;
+    } else if (pws_wgrad_applicable(k, G) && (int64_t)(pws_wgrad_ws_floats(k) * sizeof(float)) <= workspace_bytes) {
+      rc = launch_pws_wgrad(k, G, ws, &w, &KD_pad, st);
       if (rc != NLT_OK) return rc;
     } else if (use_tc_wgrad(k)) {
       NLT_CHECK_ARG((int64_t)(tc_wgrad_ws_floats(k) * sizeof(float)) <= workspace_bytes, "workspace too small");

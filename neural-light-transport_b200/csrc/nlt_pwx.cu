@@ -466,6 +466,7 @@ struct PwdParams {
   int K;
   uint32_t M;             // lattice pixels = N * Hin * Win
   int Win;                // power of two; a tile is TP consecutive lattice pixels: part of a row or whole rows
+  int lwin, lw2;          // log2(Win), log2(2 * min(Win, TP))
   uint32_t ntiles;
   float beta;
   const float* mask_y;
@@ -520,7 +521,7 @@ pwd2s_kernel(const PwdParams p) {
   if (PREFETCH && blockIdx.x < p.ntiles) load_x(blockIdx.x, reinterpret_cast<float4(&)[K / 4]>(xcur));
   for (uint32_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
     const uint32_t start = t * TP;                                 // first lattice pixel (flat: (n*Hin + y)*Win + x)
-    const uint32_t row0 = start / (uint32_t)p.Win, x0 = start - row0 * (uint32_t)p.Win;
+    const uint32_t row0 = start >> p.lwin, x0 = start & ((uint32_t)p.Win - 1u);
     // ---- this thread's 64 outputs ----
     float2 acc[32];
 #pragma unroll
@@ -558,10 +559,10 @@ pwd2s_kernel(const PwdParams p) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int f = tid + (b4 * 4 + u) * PWD_THREADS;            // float4 index inside the tile's outputs
-        const int j = f % C4;
+        const int j = f % C4;                                      // C4, 2 * wtile: powers of two
         int r = f / C4;
-        const int ox = r % (2 * wtile);
-        r /= 2 * wtile;
+        const int ox = r & (2 * wtile - 1);
+        r >>= p.lw2;
         const int dy = r & 1, lr = r >> 1;                         // output row parity, lattice row inside the tile
         const int px = lr * wtile + (ox >> 1), dx = ox & 1;
         jq[u] = j;
@@ -623,6 +624,11 @@ static int pwd2s_launch(const PwdParams& p0, cudaStream_t st) {
   constexpr int TP = PWD_THREADS / (CS / 16);
   PwdParams p = p0;
   p.ntiles = p.M / TP;
+  p.lwin = 0;
+  while ((1 << p.lwin) < p.Win) ++p.lwin;
+  const int w2 = 2 * (p.Win < TP ? p.Win : TP);
+  p.lw2 = 0;
+  while ((1 << p.lw2) < w2) ++p.lw2;
   const size_t smem = (size_t)TP * (4 * CS + 4) * sizeof(float);
   int dev = 0;
   cudaGetDevice(&dev);
@@ -657,6 +663,258 @@ int launch_pwd2s(const GConvK& k, float beta, const float* mask_y, int mask_act,
   if (ex != nullptr) { p.ex_x = ex->x; p.ex_K = ex->K; p.ex_w = ex->w; p.ex_wk = ex->wk; p.ex_wn = ex->wn; }
   if (CS == 16) return K == 16 ? pwd2s_launch<16, 16>(p, st) : pwd2s_launch<32, 16>(p, st);
   return K == 32 ? pwd2s_launch<32, 32>(p, st) : pwd2s_launch<64, 32>(p, st);
+}
+
+// =============================================================================================
+// Weight gradient of the 2x2 convolutions (stride 1 or 2) of the 16- / 32-channel levels:
+//   dW[tap, c, n] = sum_p x[(s*y + dy, s*x + dx), c] * dz[(y, x), n]     K = 4 * sum_seg C <= 128, N = 16 or 32.
+// Same arithmetic shape as pwx_wgrad_kernel (an outer product per pixel, FFMA2 with the gradient staged duplicated),
+// with the pixel's K-vector gathered from a staged input patch: a tile is 64 output pixels of one output row, its
+// input is two row segments per source (s*64 (+1 halo) pixels, contiguous in memory) copied by cp.async.  warp =
+// pixel, lane = (channel group, output quad); for N = 32, K = 128 two warps split the K rows of a pixel.  One fp32
+// partial per CTA in the k-group layout of WgradK (row = 4 * group + e, groups in (tap, source, channel quad) order).
+// =============================================================================================
+constexpr int PWS_TP = 64;            // output pixels per tile
+constexpr int PWS_THREADS = 128;
+constexpr int PWS_WARPS = 4;
+constexpr int PWS_CTAS_PER_SM = 4;
+
+struct PwsParams {
+  const float* seg_ptr[NLT_MAX_SEG];
+  int seg_C[NLT_MAX_SEG];
+  int seg_soff[NLT_MAX_SEG];     // float offset of the source's patch inside the x stage
+  int nseg, ctot;                // sum of channels
+  int s;                         // stride (1 or 2)
+  int pw;                        // staged pixels per row: s * TP + (s == 1)
+  int N, Hin, Win, Hout, Wout;
+  int tiles_per_row;
+  uint32_t ntiles;
+  int xfloats;                   // floats of the x stage
+  int kd_pad, bias_row;
+};
+
+template <int NQ, int NG, int KSPLIT>     // output quads (N / 4), channel groups per lane, warps sharing a pixel's K rows
+__global__ void __launch_bounds__(PWS_THREADS, PWS_CTAS_PER_SM)
+pws_wgrad_kernel(const PwsParams p, const float* __restrict__ G, float* __restrict__ ws) {
+  constexpr int NCG = 32 / NQ;                  // channel-group lanes
+  constexpr int N = NQ * 4;
+  extern __shared__ __align__(16) float smem[];
+  float* xs = smem;                             // per source: [2 rows][pw pixels][C]
+  float* gs = xs + p.xfloats;                   // [TP][2N]: dz duplicated (d, d)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cg = lane / NQ, ng = lane % NQ;
+  const int khalf = warp % KSPLIT, pwarp = warp / KSPLIT;
+  constexpr int PSTEP = PWS_WARPS / KSPLIT;     // warps that walk the tile's pixels
+
+  // this lane's channel groups: g = (khalf * NG + j) * NCG + cg over (tap, source, channel quad)
+  int goff[NG], gstr[NG];
+#pragma unroll
+  for (int j = 0; j < NG; ++j) {
+    const int g = (khalf * NG + j) * NCG + cg;
+    const int gpt = p.ctot >> 2;                // groups per tap
+    const int tap = g / gpt;
+    int r = g - tap * gpt, sidx = 0;
+    while (sidx < p.nseg - 1 && r >= (p.seg_C[sidx] >> 2)) { r -= p.seg_C[sidx] >> 2; ++sidx; }
+    const int C = p.seg_C[sidx];
+    const int dy = tap >> 1, dx = tap & 1;
+    goff[j] = p.seg_soff[sidx] + (dy * p.pw + dx) * C + r * 4;
+    gstr[j] = p.s * C;
+  }
+
+  float2 acc[NG][2][4];
+  float bs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < NG; ++j)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int n = 0; n < 4; ++n) acc[j][h][n] = make_float2(0.f, 0.f);
+
+  const uint32_t xs_u = pwx_smem_u32(xs);
+  for (uint32_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+    const uint32_t orow = t / (uint32_t)p.tiles_per_row;              // flat output row n*Hout + y
+    const int x0 = (int)(t - orow * (uint32_t)p.tiles_per_row) * PWS_TP;
+    const int n = (int)(orow / (uint32_t)p.Hout), y = (int)(orow - (uint32_t)n * p.Hout);
+    // ---- stage the input patch: per source two row segments; out-of-image parts (SAME padding) are zeroed ----
+    for (int sidx = 0; sidx < p.nseg; ++sidx) {
+      const int C = p.seg_C[sidx], c4 = C >> 2;
+      for (int dy = 0; dy < 2; ++dy) {
+        const int iy = p.s * y + dy;
+        const int ix0 = p.s * x0;
+        const int npx = min(p.pw, p.Win - ix0);                       // pixels of the run that exist
+        float* dst = xs + p.seg_soff[sidx] + dy * p.pw * C;
+        if (iy < p.Hin) {
+          const float4* src = reinterpret_cast<const float4*>(p.seg_ptr[sidx] + (((size_t)n * p.Hin + iy) * p.Win + ix0) * C);
+          const int n4 = npx * c4;
+          for (int i = tid; i < n4; i += PWS_THREADS) cp_async16(xs_u + (uint32_t)((dst - xs) + i * 4) * 4, src + i);
+          for (int i = npx * C + tid; i < p.pw * C; i += PWS_THREADS) dst[i] = 0.f;
+        } else {
+          for (int i = tid; i < p.pw * C; i += PWS_THREADS) dst[i] = 0.f;
+        }
+      }
+    }
+    cp_async_commit();
+    {   // dz of the tile: TP * N floats, stored duplicated (d, d)
+      const float4* src = reinterpret_cast<const float4*>(G + ((size_t)orow * p.Wout + x0) * N);
+      constexpr int NQT = PWS_TP * NQ;                                  // float4 of the tile
+#pragma unroll
+      for (int i = 0; i < (NQT + PWS_THREADS - 1) / PWS_THREADS; ++i) {
+        const int qi = tid + i * PWS_THREADS;
+        if (qi < NQT) {
+          const float4 r = __ldg(src + qi);
+          float4* d = reinterpret_cast<float4*>(gs + (qi / NQ) * (2 * N) + (qi % NQ) * 8);
+          d[0] = make_float4(r.x, r.x, r.y, r.y);
+          d[1] = make_float4(r.z, r.z, r.w, r.w);
+        }
+      }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+#pragma unroll 2
+    for (int i = 0; i < PWS_TP / PSTEP; ++i) {
+      const int px = pwarp + PSTEP * i;
+      const float4* gq = reinterpret_cast<const float4*>(gs + px * (2 * N) + ng * 8);
+      const float4 g0 = gq[0], g1 = gq[1];
+      const float2 gd[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y),
+                            make_float2(g1.z, g1.w)};
+      bs[0] += g0.x; bs[1] += g0.z; bs[2] += g1.x; bs[3] += g1.z;
+#pragma unroll
+      for (int j = 0; j < NG; ++j) {
+        const float4 xv = *reinterpret_cast<const float4*>(xs + goff[j] + px * gstr[j]);
+        const float2 xa = make_float2(xv.x, xv.y), xb = make_float2(xv.z, xv.w);
+#pragma unroll
+        for (int nn = 0; nn < 4; ++nn) {
+          acc[j][0][nn] = __ffma2_rn(xa, gd[nn], acc[j][0][nn]);
+          acc[j][1][nn] = __ffma2_rn(xb, gd[nn], acc[j][1][nn]);
+        }
+      }
+    }
+    __syncthreads();                                                   // everyone is done with this tile's stages
+  }
+
+  // ---- reduce the warps of each K half in fixed order, one partial per CTA ----
+  constexpr int ROWS_H = NG * NCG * 4;                                 // weight rows of one K half
+  float* red = smem;                                                   // [warp][ROWS_H][N]
+#pragma unroll
+  for (int j = 0; j < NG; ++j)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int row = (j * NCG + cg) * 4 + 2 * h;                      // row inside this warp's K half
+      float* r0 = red + ((size_t)warp * ROWS_H + row) * N + ng * 4;
+      *reinterpret_cast<float4*>(r0) = make_float4(acc[j][h][0].x, acc[j][h][1].x, acc[j][h][2].x, acc[j][h][3].x);
+      *reinterpret_cast<float4*>(r0 + N) = make_float4(acc[j][h][0].y, acc[j][h][1].y, acc[j][h][2].y, acc[j][h][3].y);
+    }
+  float* redb = red + (size_t)PWS_WARPS * ROWS_H * N;                  // [warp][N] bias partials (K half 0 only)
+  if (cg == 0 && khalf == 0) *reinterpret_cast<float4*>(redb + pwarp * N + ng * 4) = make_float4(bs[0], bs[1], bs[2], bs[3]);
+  __syncthreads();
+  float* dst = ws + (size_t)blockIdx.x * p.kd_pad * N;
+  for (int i = tid; i < KSPLIT * ROWS_H * N; i += PWS_THREADS) {
+    const int nn = i % N, r = i / N;                                   // r = global weight row = kh * ROWS_H + row
+    const int kh = r / ROWS_H, row = r - kh * ROWS_H;
+    float sum = 0.f;
+#pragma unroll
+    for (int pwv = 0; pwv < PSTEP; ++pwv) sum += red[((size_t)(pwv * KSPLIT + kh) * ROWS_H + row) * N + nn];
+    dst[(size_t)r * N + nn] = sum;
+  }
+  if (tid < N) {
+    float sum = 0.f;
+#pragma unroll
+    for (int pwv = 0; pwv < PSTEP; ++pwv) sum += redb[pwv * N + tid];
+    dst[(size_t)p.bias_row * N + tid] = sum;
+  }
+}
+
+struct PwsPlan {
+  bool ok;
+  int nq, ng, ksplit;
+  PwsParams p;
+  size_t smem;
+  unsigned grid;
+};
+
+static PwsPlan pws_plan(const GConvK& k) {
+  PwsPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  if (!pwx_enabled() || k.d2s || k.M == 0) return pl;
+  if (k.Cout != k.cout_true || (k.Cout != 16 && k.Cout != 32)) return pl;
+  if (k.ay.nu != 2 || k.ax.nu != 2 || k.ay.iu != 1 || k.ax.iu != 1 || k.ay.i0 != 0 || k.ax.i0 != 0) return pl;
+  if (k.ay.it != k.ax.it || (k.ay.it != 1 && k.ay.it != 2)) return pl;
+  if (k.ay.os != 1 || k.ax.os != 1 || k.ay.o0 != 0 || k.ax.o0 != 0 || k.ay.d0 != 0 || k.ax.d0 != 0 || k.ay.ds != 1 ||
+      k.ax.ds != 1 || k.kw != 2) return pl;
+  if (k.ay.nt != k.Hout || k.ax.nt != k.Wout || k.Wout % PWS_TP != 0) return pl;
+  PwsParams& p = pl.p;
+  p.s = k.ay.it;
+  if (p.s == 2 && (k.Hin != 2 * k.Hout || k.Win != 2 * k.Wout)) return pl;
+  if (p.s == 1 && (k.Hin != k.Hout || k.Win != k.Wout)) return pl;
+  p.pw = p.s * PWS_TP + (p.s == 1 ? 1 : 0);
+  int off = 0;
+  for (int s = 0; s < k.nseg; ++s) {
+    const Seg& sg = k.seg[s];
+    if (!sg.vec || sg.sub != nullptr || sg.bcast) return pl;
+    p.seg_ptr[s] = sg.ptr; p.seg_C[s] = sg.C; p.seg_soff[s] = off;
+    off += 2 * p.pw * sg.C;
+    p.ctot += sg.C;
+  }
+  p.nseg = k.nseg;
+  const int K4 = p.ctot;                       // float4 groups: 4 taps * ctot / 4
+  pl.nq = k.Cout / 4;
+  const int ncg = 32 / pl.nq;
+  if (K4 % ncg != 0) return pl;
+  int groups = K4 / ncg;                       // per lane without K split
+  pl.ksplit = 1;
+  if (groups > 4) { if (groups % 2 != 0) return pl; pl.ksplit = 2; groups /= 2; }
+  if (groups != 2 && groups != 4) return pl;
+  pl.ng = groups;
+  p.N = k.N; p.Hin = k.Hin; p.Win = k.Win; p.Hout = k.Hout; p.Wout = k.Wout;
+  p.tiles_per_row = k.Wout / PWS_TP;
+  const long long nt = (long long)k.N * k.Hout * p.tiles_per_row;
+  if (nt < 4 || nt > (1ll << 31)) return pl;
+  p.ntiles = (uint32_t)nt;
+  p.xfloats = (off + 3) / 4 * 4;
+  p.kd_pad = (K4 + 1) * 4;
+  p.bias_row = K4 * 4;
+  const size_t stage = ((size_t)p.xfloats + (size_t)PWS_TP * 2 * k.Cout) * sizeof(float);
+  const size_t red = ((size_t)PWS_WARPS * (pl.ng * ncg * 4) * k.Cout + PWS_WARPS * k.Cout) * sizeof(float);
+  pl.smem = stage > red ? stage : red;
+  if (pl.smem > 56 * 1024) return pl;
+  pl.grid = p.ntiles < 148u * PWS_CTAS_PER_SM ? p.ntiles : 148u * PWS_CTAS_PER_SM;
+  pl.ok = true;
+  return pl;
+}
+
+bool pws_wgrad_applicable(const GConvK& k, const float* G) {
+  return (G == nullptr || aligned16(G)) && pws_plan(k).ok;
+}
+
+size_t pws_wgrad_ws_floats(const GConvK& k) {
+  PwsPlan pl = pws_plan(k);
+  return pl.ok ? (size_t)pl.grid * pl.p.kd_pad * k.Cout : 0;
+}
+
+template <int NQ, int NG, int KS>
+static int pws_launch(const PwsPlan& pl, const float* G, float* ws, cudaStream_t st) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static bool attr_set[64] = {false};
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(pws_wgrad_kernel<NQ, NG, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+    if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  pws_wgrad_kernel<NQ, NG, KS><<<pl.grid, PWS_THREADS, pl.smem, st>>>(pl.p, G, ws);
+  NLT_CUDA_LAUNCH_CHECK("pws_wgrad_kernel");
+  return NLT_OK;
+}
+
+int launch_pws_wgrad(const GConvK& k, const float* G, float* ws, WgradK* w, size_t* KD_pad, cudaStream_t st) {
+  PwsPlan pl = pws_plan(k);
+  if (!pl.ok) return set_err(NLT_ERR_INVALID, "pws_wgrad not applicable");
+  w->g = k; w->GS = pl.p.ctot / 4; w->KG = pl.p.ctot + 1; w->ld = k.Cout; w->nsplit = (int)pl.grid; w->pix_per_split = 0;
+  *KD_pad = (size_t)pl.p.kd_pad;
+  if (pl.nq == 4) return pl.ng == 2 ? pws_launch<4, 2, 1>(pl, G, ws, st) : pws_launch<4, 4, 1>(pl, G, ws, st);
+  if (pl.ksplit == 1) return pl.ng == 2 ? pws_launch<8, 2, 1>(pl, G, ws, st) : pws_launch<8, 4, 1>(pl, G, ws, st);
+  return pl.ng == 2 ? pws_launch<8, 2, 2>(pl, G, ws, st) : pws_launch<8, 4, 2>(pl, G, ws, st);
 }
 
 }  // namespace nlt

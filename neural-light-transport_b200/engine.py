@@ -155,6 +155,7 @@ def side_stream():
 
 
 USE_SIDE_STREAM = os.environ.get('NLT_NO_SIDE_STREAM', '0') != '1'
+_SKIP_WGRAD = os.environ.get('NLT_SKIP_WGRAD', '0') == '1'
 # called as WGRAD_HOOK(layer) right after a layer's weight-gradient launch has been issued (on the side stream when
 # USE_SIDE_STREAM): trainvali.GradReducer starts the early part of the gradient all-reduce from it
 WGRAD_HOOK = None
@@ -367,7 +368,9 @@ class ConvLayer:
             nat.check(-1)
         nb = 4 * (sum(sg.a.t.numel() * (2 if sg.sub is not None else 1) for sg in segs) + dz.numel())
         acc = 1 if self.grad_written else 0
-        if USE_SIDE_STREAM:
+        if _SKIP_WGRAD:          # DIAGNOSTIC (NLT_SKIP_WGRAD=1, wrong results): time the forward + input-gradient chain alone
+            pass
+        elif USE_SIDE_STREAM:
             main, side = torch.cuda.current_stream(), side_stream()
             side.wait_stream(main)                      # dz (and the inputs) are complete on the main stream
             with torch.cuda.stream(side):

@@ -89,6 +89,12 @@ GEOMS = [
     ('conv', 2, 2, 32, 128, [32, 32], 64),      # ... lattice rows narrower than a tile: two rows per tile
     ('conv', 2, 2, 32, 128, [16], 16),          # ... four lattice rows per tile, 16-channel source
     ('conv', 2, 2, 32, 128, [32], 32),          # K = 32 -> 4 x 32
+    # staged-patch FFMA2 weight gradient of the 2x2 convs (pws_wgrad_kernel): all four lane layouts, both strides,
+    # SAME padding at the right / bottom edge
+    ('conv', 2, 2, 16, 256, [16, 16], 16),      # K = 128, N = 16
+    ('conv', 2, 1, 8, 128, [16], 32),           # K = 64, N = 32, stride 1
+    ('conv', 2, 1, 8, 64, [32], 32),            # K = 128, N = 32 (two warps share a pixel's K rows), stride 1
+    ('conv', 2, 1, 5, 192, [16], 16),           # K = 64, N = 16, stride 1, three tiles per row
     ('conv', 1, 1, 33, 37, [3, 60, 1], 16),
     ('conv', 1, 1, 32, 32, [64], 16),
     ('conv', 1, 1, 24, 24, [20, 4], 16),
