@@ -714,9 +714,6 @@ int nlt_gconv_fwd_ws(const nlt_gconv_desc* d, const float* bias, int act, float 
   NLT_CHECK_ARG(act >= 0 && act <= 3 && mask_act >= 0 && mask_act <= 3, "bad activation code");
   NLT_CHECK_ARG(beta == 0.f || beta == 1.f, "beta must be 0 or 1");
   cudaStream_t st = (cudaStream_t)stream;
-  // the streaming depth-to-space kernel outruns the tcgen05 kernel on its shapes (level-3 input gradients: 64 -> 4 x 32)
-  if (np == 1 && ph[0].M > 0 && pwd2s_applicable(ph[0], bias, act, out, mask_y, nullptr))
-    return launch_pwd2s(ph[0], beta, mask_y, mask_act, out, st, nullptr);
   if (np == 1 && workspace != nullptr && tc_enabled() && ph[0].M > 0 && tc_applicable(ph[0]) &&
       (int64_t)tc_workspace_bytes(ph[0]) <= workspace_bytes)
     return launch_tc(ph[0], bias, act, beta, mask_y, mask_act, out, workspace, (size_t)workspace_bytes, st);
