@@ -165,8 +165,14 @@ int launch_wgrad_tpp(const GConvK& k, const float* G, float* ws, WgradK* w, size
 
 // wide pointwise conv into 16 channels (nlt_pwx.cu): level 0 of the 64-channel query stack
 extern int g_opt_pwx;
+extern int g_opt_tiny;
+bool tiny_stencil_applicable(const GConvK& k, const float* out, const float* mask_y);
+int launch_tiny_stencil(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
+                        float* out, cudaStream_t st);
 bool pwx_fwd_applicable(const GConvK& k, float beta, const float* mask_y, const float* out);
 int launch_pwx_fwd(const GConvK& k, const float* bias, int act, float* out, cudaStream_t st);
+bool pwx_d2s_fwd_applicable(const GConvK& k, float beta, const float* mask_y, const float* out);
+int launch_pwx_d2s_fwd(const GConvK& k, const float* bias, int act, float* out, cudaStream_t st);
 bool pwx_wgrad_applicable(const GConvK& k, const float* G);
 size_t pwx_wgrad_ws_floats(const GConvK& k);
 int launch_pwx_wgrad(const GConvK& k, const float* G, float* ws, WgradK* w, size_t* KD_pad, cudaStream_t st);

@@ -688,6 +688,7 @@ int nlt_set_option(const char* name, int value) {
   if (strcmp(name, "wgrad_rows") == 0) { nlt::g_opt_wgrad_rows = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "tcs") == 0) { nlt::g_opt_tcs = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "pwx") == 0) { nlt::g_opt_pwx = value ? 1 : 0; return NLT_OK; }
+  if (strcmp(name, "tiny") == 0) { nlt::g_opt_tiny = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "dconv_cw") == 0) { nlt::g_opt_dconv_cw = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "dconv_wide") == 0) { nlt::g_opt_dconv_wide = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "dconv_wide32") == 0) { nlt::g_opt_dconv_wide32 = value; return NLT_OK; }
@@ -714,6 +715,12 @@ int nlt_gconv_fwd_ws(const nlt_gconv_desc* d, const float* bias, int act, float 
   NLT_CHECK_ARG(act >= 0 && act <= 3 && mask_act >= 0 && mask_act <= 3, "bad activation code");
   NLT_CHECK_ARG(beta == 0.f || beta == 1.f, "beta must be 0 or 1");
   cudaStream_t st = (cudaStream_t)stream;
+  // few-channel stride-1 stencils (4/8/16 -> same): the row-stream kernel of nlt_tiny.cu, ahead of the tensor path
+  // (16 -> 16 at 512^2 is a 130 B/pixel stream: the tcgen05 pipeline's fixed costs exceed its 0.5 kFMA/pixel)
+  if (np == 1 && ph[0].M > 0 && tiny_stencil_applicable(ph[0], out, mask_y))
+    return launch_tiny_stencil(ph[0], bias, act, beta, mask_y, mask_act, out, st);
+  // up-convs into 4 / 8 channels: depth-to-space pointwise kernel with constant-bank weights (nlt_pwx.cu)
+  if (np == 1 && pwx_d2s_fwd_applicable(ph[0], beta, mask_y, out)) return launch_pwx_d2s_fwd(ph[0], bias, act, out, st);
   if (np == 1 && workspace != nullptr && tc_enabled() && ph[0].M > 0 && tc_applicable(ph[0]) &&
       (int64_t)tc_workspace_bytes(ph[0]) <= workspace_bytes)
     return launch_tc(ph[0], bias, act, beta, mask_y, mask_act, out, workspace, (size_t)workspace_bytes, st);
@@ -723,6 +730,7 @@ int nlt_gconv_fwd_ws(const nlt_gconv_desc* d, const float* bias, int act, float 
     if (pwx_fwd_applicable(k, beta, mask_y, out)) rc = launch_pwx_fwd(k, bias, act, out, st);
     else if (pwd2s_applicable(k, bias, act, out, mask_y, nullptr)) rc = launch_pwd2s(k, beta, mask_y, mask_act, out, st, nullptr);
     else if (pw_conv_applicable(k)) rc = launch_pw_conv(k, bias, act, beta, mask_y, mask_act, out, st);
+    else if (tiny_stencil_applicable(k, out, mask_y)) rc = launch_tiny_stencil(k, bias, act, beta, mask_y, mask_act, out, st);
     // option "dconv_wide_first" (default on; measured -0.4 ms per cfg2 step together with the 8-output form,
     // profiles/r2_a_*): prefer the wide stencil kernel over the quad-per-thread one where both apply
     // (16 / 8 outputs, K <= 32: the up-conv input gradients of levels 11-12)

@@ -45,6 +45,8 @@ struct PwxParams {
   int nseg;
   int K, K4;           // channels, float4 groups per smem row (incl. zero padding up to a multiple of 8 groups for wgrad)
   int krow;            // smem row stride in floats
+  int kpad0;           // first zero-padded smem column (== K4 * 4 when there is none)
+  int ct, lw;          // depth-to-space forward: true output channels per tap, log2(row tiles) unused otherwise
   uint32_t M;          // pixels
   uint32_t ntiles;
   int16_t col_c[PWX_KMAX];    // smem column -> concat channel (weight row), -1 pad
@@ -107,8 +109,8 @@ constexpr int PWX_OROW = 20;        // floats per staged output row (16 + 4: con
 // (profiles/r2_e_*): 272 broadcast LDS.128 per pixel kept the LSU pipe 58 % busy and the FFMA2s waiting on them
 // (short scoreboard) at 34 % issue utilisation.
 constexpr int PWX_CW_PAIRS = 64;                                   // K <= 128
-__constant__ float2 pwx_cw[PWX_CW_PAIRS * 16];                     // [pair][n] = (W[c_even][n], W[c_odd][n])
-__device__ float2 pwx_cw_stage[PWX_CW_PAIRS * 16];                 // written by the pack kernel, copied into pwx_cw
+__constant__ float2 pwx_cw[PWX_CW_PAIRS * 32];                     // [pair][n] = (W[c_even][n], W[c_odd][n]); n < 16 (or 32: d2s form)
+__device__ float2 pwx_cw_stage[PWX_CW_PAIRS * 32];                 // written by the pack kernel, copied into pwx_cw
 
 __global__ void pwx_pack_w_kernel(const PwxParams p, const float* __restrict__ w, long long wc, long long wn) {
   const int npair = p.K4 * 2;
@@ -298,7 +300,8 @@ static bool pwx_shape_ok(const GConvK& k) {
   return K > 16 && K <= PWX_KMAX - 8 && k.M >= 4 * PWX_T;
 }
 
-static bool pwx_build(const GConvK& k, bool for_wgrad, PwxParams* p, int* kd_pad, int* bias_row, int* GS_out) {
+static bool pwx_build(const GConvK& k, bool for_wgrad, PwxParams* p, int* kd_pad, int* bias_row, int* GS_out,
+                      bool k4_even = false) {
   memset(p, 0, sizeof(*p));
   for (int i = 0; i < PWX_KMAX; ++i) { p->col_c[i] = -1; p->col_row[i] = -1; }
   int gbase[NLT_MAX_SEG], GS = 0;
@@ -323,7 +326,10 @@ static bool pwx_build(const GConvK& k, bool for_wgrad, PwxParams* p, int* kd_pad
     }
   p->K = K;
   int K4 = (off + 3) / 4;
-  K4 = (K4 + 7) / 8 * 8;            // wgrad: lanes cover 8 groups per step; forward: instantiated for 8, 16, 24, 32
+  // wgrad: lanes cover 8 groups per step; forward: instantiated for 8, 16, 24, 32; depth-to-space forward
+  // (k4_even): any even count (an even K4 keeps the LDS.128 row stride K4*4 + 4 conflict-free)
+  K4 = k4_even ? (K4 + 1) / 2 * 2 : (K4 + 7) / 8 * 8;
+  p->kpad0 = off;
   (void)for_wgrad;
   if (K4 * 4 > PWX_KMAX) return false;
   p->K4 = K4;
@@ -393,6 +399,173 @@ int launch_pwx_fwd(const GConvK& k, const float* bias, int act, float* out, cuda
     case 24: return pwx_fwd_launch<24>(p, bias, act, out, smem, st);
     default: return pwx_fwd_launch<32>(p, bias, act, out, smem, st);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward of a 2x2 / stride-2 transposed convolution into 4 or 8 channels (levels 11-12 of the decoder,
+// nlt/networks/convnet.py:67-76): a pointwise [K] -> [4 taps x CT] product per INPUT pixel whose four CT-channel
+// groups land on the 2x2 output block of that pixel ("depth-to-space").  Same staging and constant-bank weights as
+// pwx_fwd_kernel, NOUT = 4 * CT columns; a tile is 128 consecutive pixels of one input row, so that each of its two
+// output rows is one contiguous run of 128 * 2 * CT floats.
+// ---------------------------------------------------------------------------------------------
+__global__ void pwx_pack_w_d2s_kernel(const PwxParams p, const float* __restrict__ w, long long wt, long long wc,
+                                      long long wn, int nout) {
+  const int npair = p.K4 * 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npair * nout; i += gridDim.x * blockDim.x) {
+    const int cp = i / nout, n = i - cp * nout;
+    const int tap = n / p.ct, nn = n - tap * p.ct;
+    const int c0 = p.col_c[2 * cp], c1 = p.col_c[2 * cp + 1];
+    const float* wb = w + (long long)tap * wt + (long long)nn * wn;
+    pwx_cw_stage[i] = make_float2(c0 >= 0 ? __ldg(wb + (long long)c0 * wc) : 0.f, c1 >= 0 ? __ldg(wb + (long long)c1 * wc) : 0.f);
+  }
+}
+
+template <int K4, int NOUT>
+__global__ void __launch_bounds__(PWX_THREADS, NOUT == 16 ? 4 : 3)
+pwx_d2s_fwd_kernel(const PwxParams p, const float* __restrict__ bias, const int act, float* __restrict__ out,
+                   const int Win) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int KROW = K4 * 4 + 4;
+  constexpr int OROW = NOUT + 4;
+  constexpr int CT = NOUT / 4;
+  float* xs = smem;
+  float* so = smem;                                            // aliases xs: written after every thread has consumed its row
+  const int tid = threadIdx.x;
+  pwx_zero_rows(p, xs, 0);
+  __syncthreads();
+
+  for (uint32_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+    pwx_stage_x(p, t, xs);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+
+    float2 acc[NOUT];
+#pragma unroll
+    for (int n = 0; n < NOUT; ++n) acc[n] = make_float2(0.f, 0.f);
+    const float4* xrow = reinterpret_cast<const float4*>(xs + tid * KROW);
+#pragma unroll
+    for (int q = 0; q < K4; ++q) {
+      const float4 xv = xrow[q];
+      const float2 xa = make_float2(xv.x, xv.y), xb = make_float2(xv.z, xv.w);
+#pragma unroll
+      for (int n = 0; n < NOUT; ++n) {
+        acc[n] = __ffma2_rn(xa, pwx_cw[(2 * q) * NOUT + n], acc[n]);
+        acc[n] = __ffma2_rn(xb, pwx_cw[(2 * q + 1) * NOUT + n], acc[n]);
+      }
+    }
+    __syncthreads();                                           // every row of xs has been read
+    float4* srow = reinterpret_cast<float4*>(so + tid * OROW);
+#pragma unroll
+    for (int j = 0; j < NOUT / 4; ++j) {
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int n = 4 * j + e;
+        o[e] = act_fwd(acc[n].x + acc[n].y + (bias ? __ldg(bias + (n % CT)) : 0.f), act);
+      }
+      srow[j] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    __syncthreads();
+    // tile = pixels [x0, x0 + 128) of input row r = n * Hin + y; output rows 2r and 2r + 1 (Hout = 2 Hin), columns from 2 x0
+    const uint32_t pix0 = t * PWX_T;
+    const uint32_t r = pix0 / (uint32_t)Win, x0 = pix0 - r * (uint32_t)Win;
+    constexpr int Q = 2 * CT / 4;                              // float4 per input pixel per output row
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      float4* dst = reinterpret_cast<float4*>(out + ((size_t)(2 * r + dy) * (2 * (size_t)Win) + 2 * x0) * CT);
+#pragma unroll
+      for (int i = 0; i < Q; ++i) {
+        const uint32_t qi = tid + i * PWX_THREADS;
+        const uint32_t px = qi / Q, j = qi % Q;
+        dst[qi] = *reinterpret_cast<const float4*>(so + px * OROW + dy * 2 * CT + 4 * j);
+      }
+    }
+    __syncthreads();                                           // so is xs: the next tile's copies must wait for these reads
+    if (p.kpad0 < K4 * 4)
+      for (int c = p.kpad0; c < K4 * 4; ++c) xs[tid * KROW + c] = 0.f;      // the zero pad held outputs
+  }
+}
+
+static size_t pwx_d2s_smem(const PwxParams& p, int nout) {
+  const int row = p.krow > nout + 4 ? p.krow : nout + 4;
+  return (size_t)PWX_T * row * sizeof(float);
+}
+
+static int pwx_d2s_k4(int k4) {          // instantiated widths
+  const int opts[] = {6, 10, 12, 16, 20, 24, 28};
+  for (int o : opts) if (k4 <= o) return o;
+  return 0;
+}
+
+static bool pwx_d2s_build(const GConvK& k, PwxParams* p) {
+  if (!pwx_build(k, false, p, nullptr, nullptr, nullptr, /*k4_even=*/true)) return false;
+  const int k4 = pwx_d2s_k4(p->K4);
+  if (k4 == 0) return false;
+  p->K4 = k4;
+  p->krow = k4 * 4 + 4;
+  p->ct = k.cout_true;
+  return true;
+}
+
+bool pwx_d2s_fwd_applicable(const GConvK& k, float beta, const float* mask_y, const float* out) {
+  if (!pwx_enabled() || !k.d2s || k.d2s_s != 2 || k.M == 0 || beta != 0.f || mask_y != nullptr || !aligned16(out)) return false;
+  if ((k.cout_true != 4 && k.cout_true != 8) || k.Cout != 4 * k.cout_true) return false;
+  if (k.ax.nt != k.Win || k.ay.nt != k.Hin || k.Hout != 2 * k.Hin || k.Wout != 2 * k.Win || k.Win % PWX_T != 0) return false;
+  int K = 0;
+  for (int s = 0; s < k.nseg; ++s) {
+    if (k.seg[s].sub != nullptr || k.seg[s].bcast || !k.seg[s].vec) return false;
+    K += k.seg[s].C;
+  }
+  if (K < k.Cout || K > 112) return false;
+  PwxParams p;
+  return pwx_d2s_build(k, &p) && pwx_d2s_smem(p, k.Cout) <= PWX_SMEM_MAX;
+}
+
+template <int K4, int NOUT>
+static int pwx_d2s_launch(const PwxParams& p, const float* bias, int act, float* out, int Win, size_t smem, cudaStream_t st) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static bool attr_set[64] = {false};
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(pwx_d2s_fwd_kernel<K4, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PWX_SMEM_MAX);
+    if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  const unsigned per_sm = NOUT == 16 ? 4u : 3u;
+  const unsigned grid = p.ntiles < 148u * per_sm ? p.ntiles : 148u * per_sm;
+  pwx_d2s_fwd_kernel<K4, NOUT><<<grid, PWX_THREADS, smem, st>>>(p, bias, act, out, Win);
+  NLT_CUDA_LAUNCH_CHECK("pwx_d2s_fwd_kernel");
+  return NLT_OK;
+}
+
+template <int NOUT>
+static int pwx_d2s_dispatch(const PwxParams& p, const float* bias, int act, float* out, int Win, size_t smem, cudaStream_t st) {
+  switch (p.K4) {
+    case 6: return pwx_d2s_launch<6, NOUT>(p, bias, act, out, Win, smem, st);
+    case 10: return pwx_d2s_launch<10, NOUT>(p, bias, act, out, Win, smem, st);
+    case 12: return pwx_d2s_launch<12, NOUT>(p, bias, act, out, Win, smem, st);
+    case 16: return pwx_d2s_launch<16, NOUT>(p, bias, act, out, Win, smem, st);
+    case 20: return pwx_d2s_launch<20, NOUT>(p, bias, act, out, Win, smem, st);
+    case 24: return pwx_d2s_launch<24, NOUT>(p, bias, act, out, Win, smem, st);
+    default: return pwx_d2s_launch<28, NOUT>(p, bias, act, out, Win, smem, st);
+  }
+}
+
+// main-stream only (shares pwx_cw with the forward above)
+int launch_pwx_d2s_fwd(const GConvK& k, const float* bias, int act, float* out, cudaStream_t st) {
+  PwxParams p;
+  if (!pwx_d2s_build(k, &p)) return set_err(NLT_ERR_INVALID, "pwx_d2s_fwd not applicable");
+  const size_t smem = pwx_d2s_smem(p, k.Cout);
+  pwx_pack_w_d2s_kernel<<<4, 256, 0, st>>>(p, k.w, k.wt, k.wc, k.wn, k.Cout);
+  NLT_CUDA_LAUNCH_CHECK("pwx_pack_w_d2s_kernel");
+  void* stage = nullptr;
+  cudaError_t e = cudaGetSymbolAddress(&stage, pwx_cw_stage);
+  if (e == cudaSuccess)
+    e = cudaMemcpyToSymbolAsync(pwx_cw, stage, (size_t)p.K4 * 2 * k.Cout * sizeof(float2), 0, cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "pwx weight table: %s", cudaGetErrorString(e));
+  if (k.Cout == 16) return pwx_d2s_dispatch<16>(p, bias, act, out, k.Win, smem, st);
+  return pwx_d2s_dispatch<32>(p, bias, act, out, k.Win, smem, st);
 }
 
 bool pwx_wgrad_applicable(const GConvK& k, const float* G) {

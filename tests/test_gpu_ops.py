@@ -95,6 +95,17 @@ GEOMS = [
     ('conv', 2, 1, 8, 128, [16], 32),           # K = 64, N = 32, stride 1
     ('conv', 2, 1, 8, 64, [32], 32),            # K = 128, N = 32 (two warps share a pixel's K rows), stride 1
     ('conv', 2, 1, 5, 192, [16], 16),           # K = 64, N = 16, stride 1, three tiles per row
+    # row-stream stencil kernel (nlt_tiny.cu): 4 / 8 / 16 channels, ragged last tile, SAME padding either side
+    ('deconv', 2, 1, 12, 200, [4], 4),
+    ('deconv', 2, 1, 9, 128, [8], 8),
+    ('conv', 2, 1, 7, 130, [8], 8),
+    ('deconv', 2, 1, 6, 96, [16], 16),
+    ('conv', 2, 1, 6, 64, [4], 4),
+    # depth-to-space forward of the up-convs into 4 / 8 channels (pwx_d2s_fwd_kernel): 128-pixel row tiles
+    ('deconv', 2, 2, 3, 128, [8, 32], 4),
+    ('deconv', 2, 2, 2, 256, [16, 32, 32], 8),
+    ('deconv', 2, 2, 2, 128, [4, 20], 4),
+    ('deconv', 2, 2, 2, 128, [8, 28], 8),       # K = 36: zero-padded to 40 columns
     ('conv', 1, 1, 33, 37, [3, 60, 1], 16),
     ('conv', 1, 1, 32, 32, [64], 16),
     ('conv', 1, 1, 24, 24, [20, 4], 16),
