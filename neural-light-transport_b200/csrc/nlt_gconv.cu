@@ -658,6 +658,11 @@ uint64_t nlt_launch_count(void) { return __atomic_load_n(&nlt::g_launches, __ATO
 uint64_t nlt_tc_launch_count(void) { return __atomic_load_n(&nlt::g_tc_launches, __ATOMIC_RELAXED); }
 
 static int g_opt_tc = -1, g_opt_tc_wgrad = -1;   // -1: take the environment default
+static int g_opt_pf = -1;                        // option "pf" / NLT_PF (default 1): staged-patch forward of nlt_pwx.cu
+static bool pf_enabled() {
+  if (g_opt_pf < 0) { const char* e = getenv("NLT_PF"); g_opt_pf = (e && e[0] == '0') ? 0 : 1; }
+  return g_opt_pf == 1;
+}
 static int g_opt_dconv_wide_first = -1;          // routing switch (NLT_DCONV_WIDE_FIRST, default 1), see nlt_gconv_fwd_ws
 static bool dconv_wide_first() {
   if (g_opt_dconv_wide_first < 0) { const char* e = getenv("NLT_DCONV_WIDE_FIRST"); g_opt_dconv_wide_first = (e && e[0] == '0') ? 0 : 1; }
@@ -688,6 +693,7 @@ int nlt_set_option(const char* name, int value) {
   if (strcmp(name, "wgrad_rows") == 0) { nlt::g_opt_wgrad_rows = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "tcs") == 0) { nlt::g_opt_tcs = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "pwx") == 0) { nlt::g_opt_pwx = value ? 1 : 0; return NLT_OK; }
+  if (strcmp(name, "pf") == 0) { g_opt_pf = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "tiny") == 0) { nlt::g_opt_tiny = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "dconv_cw") == 0) { nlt::g_opt_dconv_cw = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "dconv_wide") == 0) { nlt::g_opt_dconv_wide = value ? 1 : 0; return NLT_OK; }
@@ -719,6 +725,8 @@ int nlt_gconv_fwd_ws(const nlt_gconv_desc* d, const float* bias, int act, float 
   // (16 -> 16 at 512^2 is a 130 B/pixel stream: the tcgen05 pipeline's fixed costs exceed its 0.5 kFMA/pixel)
   if (np == 1 && ph[0].M > 0 && tiny_stencil_applicable(ph[0], out, mask_y))
     return launch_tiny_stencil(ph[0], bias, act, beta, mask_y, mask_act, out, st);
+  // 2x2 / stride-2 convs of levels 1-2 (K = 64 / 128 into 16 / 32 channels): staged-patch FFMA2 forward (nlt_pwx.cu)
+  if (np == 1 && pf_enabled() && pf_fwd_applicable(ph[0], beta, mask_y, out)) return launch_pf_fwd(ph[0], bias, act, out, st);
   // up-convs into 4 / 8 channels: depth-to-space pointwise kernel with constant-bank weights (nlt_pwx.cu)
   if (np == 1 && pwx_d2s_fwd_applicable(ph[0], beta, mask_y, out)) return launch_pwx_d2s_fwd(ph[0], bias, act, out, st);
   if (np == 1 && workspace != nullptr && tc_enabled() && ph[0].M > 0 && tc_applicable(ph[0]) &&

@@ -568,6 +568,178 @@ int launch_pwx_d2s_fwd(const GConvK& k, const float* bias, int act, float* out, 
   return pwx_d2s_dispatch<32>(p, bias, act, out, k.Win, smem, st);
 }
 
+// ---------------------------------------------------------------------------------------------
+// forward of the 2x2 / stride-2 convolutions of levels 1-2 (nlt/networks/convnet.py:50-59): 16- or 32-channel sources
+// into 16 or 32 channels, K = 4 * sum C = 64 or 128.  Per output pixel this is the pointwise product above with the
+// pixel's K-vector gathered from its 2x2 input patch: a tile is TP output pixels of one output row, whose input is, per
+// source and patch row, ONE contiguous run of TP * 2 * C floats; cp.async scatters it into the padded per-pixel rows
+// (columns in (source, dy, dx, c) order).  No padding case: H_in = 2 H_out exactly.
+// ---------------------------------------------------------------------------------------------
+struct PfParams {
+  const float* seg_ptr[NLT_MAX_SEG];
+  int seg_C[NLT_MAX_SEG], seg_col[NLT_MAX_SEG], seg_coff[NLT_MAX_SEG], seg_l[NLT_MAX_SEG];   // l = log2(C / 2)
+  int nseg, K;
+  int Hin, Win, Wout;
+  int tiles_per_row;
+  uint32_t ntiles;
+};
+
+__global__ void pf_pack_w_kernel(const PfParams p, const float* __restrict__ w, long long wt, long long wc, long long wn,
+                                 int nout) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (p.K / 2) * nout; i += gridDim.x * blockDim.x) {
+    const int cp = i / nout, n = i - cp * nout;
+    float v[2];
+    for (int h = 0; h < 2; ++h) {
+      const int col = 2 * cp + h;
+      int s = 0;
+      while (s + 1 < p.nseg && col >= p.seg_col[s + 1]) ++s;
+      const int r = col - p.seg_col[s], C = p.seg_C[s];
+      const int tap = r / C, c = r - tap * C;                  // tap = dy * 2 + dx
+      v[h] = __ldg(w + (long long)tap * wt + (long long)(p.seg_coff[s] + c) * wc + (long long)n * wn);
+    }
+    pwx_cw_stage[i] = make_float2(v[0], v[1]);
+  }
+}
+
+template <int K4, int NOUT, int TP>
+__global__ void __launch_bounds__(TP, (K4 * 4 + 4) * TP * 4 <= 36 * 1024 ? (NOUT == 16 ? 6 : 4) : 3)
+pf_fwd_kernel(const PfParams p, const float* __restrict__ bias, const int act, float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int KROW = K4 * 4 + 4;
+  constexpr int OROW = NOUT + 4;
+  float* xs = smem;
+  float* so = smem;                                            // aliases xs
+  const int tid = threadIdx.x;
+  const uint32_t xs_u = pwx_smem_u32(xs);
+
+  for (uint32_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+    const uint32_t orow = t / (uint32_t)p.tiles_per_row;       // n * Hout + y; input rows 2 * orow + dy (Hin = 2 Hout)
+    const uint32_t x0 = (t - orow * (uint32_t)p.tiles_per_row) * TP;
+#pragma unroll
+    for (int s = 0; s < NLT_MAX_SEG; ++s) {
+      if (s >= p.nseg) break;
+      const int C = p.seg_C[s], l = p.seg_l[s];
+      const int n4 = TP << l;                                  // float4 per patch row of the tile: TP * 2C / 4
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const float4* src = reinterpret_cast<const float4*>(p.seg_ptr[s] + ((size_t)(2 * orow + dy) * p.Win + 2 * x0) * C);
+        const uint32_t col = p.seg_col[s] + dy * 2 * C;
+        for (int i = tid; i < n4; i += TP) {
+          const uint32_t px = (uint32_t)i >> l, j = (uint32_t)i & ((1u << l) - 1u);
+          cp_async16(xs_u + (px * KROW + col + 4 * j) * 4, src + i);
+        }
+      }
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+
+    float2 acc[NOUT];
+#pragma unroll
+    for (int n = 0; n < NOUT; ++n) acc[n] = make_float2(0.f, 0.f);
+    const float4* xrow = reinterpret_cast<const float4*>(xs + tid * KROW);
+#pragma unroll
+    for (int q = 0; q < K4; ++q) {
+      const float4 xv = xrow[q];
+      const float2 xa = make_float2(xv.x, xv.y), xb = make_float2(xv.z, xv.w);
+#pragma unroll
+      for (int n = 0; n < NOUT; ++n) {
+        acc[n] = __ffma2_rn(xa, pwx_cw[(2 * q) * NOUT + n], acc[n]);
+        acc[n] = __ffma2_rn(xb, pwx_cw[(2 * q + 1) * NOUT + n], acc[n]);
+      }
+    }
+    __syncthreads();                                           // every row of xs has been read
+    float4* srow = reinterpret_cast<float4*>(so + tid * OROW);
+#pragma unroll
+    for (int j = 0; j < NOUT / 4; ++j) {
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int n = 4 * j + e;
+        o[e] = act_fwd(acc[n].x + acc[n].y + (bias ? __ldg(bias + n) : 0.f), act);
+      }
+      srow[j] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    __syncthreads();
+    float4* dst = reinterpret_cast<float4*>(out + ((size_t)orow * p.Wout + x0) * NOUT);
+    constexpr int Q = NOUT / 4;
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+      const uint32_t qi = tid + i * TP;
+      dst[qi] = *reinterpret_cast<const float4*>(so + (qi / Q) * OROW + 4 * (qi % Q));
+    }
+    __syncthreads();                                           // so is xs
+  }
+}
+
+static bool pf_build(const GConvK& k, PfParams* p, int* tp) {
+  memset(p, 0, sizeof(*p));
+  if (!pwx_enabled() || k.d2s || k.M == 0) return false;
+  if (k.Cout != k.cout_true || (k.Cout != 16 && k.Cout != 32)) return false;
+  if (k.ay.nu != 2 || k.ax.nu != 2 || k.ay.iu != 1 || k.ax.iu != 1 || k.ay.i0 != 0 || k.ax.i0 != 0) return false;
+  if (k.ay.it != 2 || k.ax.it != 2 || k.ay.os != 1 || k.ax.os != 1 || k.ay.o0 != 0 || k.ax.o0 != 0) return false;
+  if (k.ay.d0 != 0 || k.ax.d0 != 0 || k.ay.ds != 1 || k.ax.ds != 1 || k.kw != 2) return false;
+  if (k.ay.nt != k.Hout || k.ax.nt != k.Wout || k.Hin != 2 * k.Hout || k.Win != 2 * k.Wout) return false;
+  int col = 0;
+  for (int s = 0; s < k.nseg; ++s) {
+    const Seg& sg = k.seg[s];
+    if (!sg.vec || sg.sub != nullptr || sg.bcast || (sg.C != 16 && sg.C != 32)) return false;
+    p->seg_ptr[s] = sg.ptr; p->seg_C[s] = sg.C; p->seg_col[s] = col; p->seg_coff[s] = sg.coff;
+    p->seg_l[s] = sg.C == 16 ? 3 : 4;
+    col += 4 * sg.C;
+  }
+  if (col != 64 && col != 128) return false;
+  p->nseg = k.nseg; p->K = col;
+  *tp = col == 64 ? 128 : 64;
+  if (k.Wout % *tp != 0) return false;
+  p->Hin = k.Hin; p->Win = k.Win; p->Wout = k.Wout;
+  p->tiles_per_row = k.Wout / *tp;
+  const long long nt = (long long)k.N * k.Hout * p->tiles_per_row;
+  if (nt < 4 || nt > (1ll << 31)) return false;
+  p->ntiles = (uint32_t)nt;
+  return true;
+}
+
+bool pf_fwd_applicable(const GConvK& k, float beta, const float* mask_y, const float* out) {
+  PfParams p;
+  int tp = 0;
+  return beta == 0.f && mask_y == nullptr && aligned16(out) && pf_build(k, &p, &tp);
+}
+
+template <int K4, int NOUT, int TP>
+static int pf_launch(const PfParams& p, const float* bias, int act, float* out, cudaStream_t st) {
+  constexpr size_t smem = (size_t)TP * (K4 * 4 + 4) * sizeof(float);
+  constexpr unsigned per_sm = smem <= 36 * 1024 ? (NOUT == 16 ? 6u : 4u) : 3u;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static bool attr_set[64] = {false};
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(pf_fwd_kernel<K4, NOUT, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  const unsigned grid = p.ntiles < 148u * per_sm ? p.ntiles : 148u * per_sm;
+  pf_fwd_kernel<K4, NOUT, TP><<<grid, TP, smem, st>>>(p, bias, act, out);
+  NLT_CUDA_LAUNCH_CHECK("pf_fwd_kernel");
+  return NLT_OK;
+}
+
+// main-stream only (shares pwx_cw)
+int launch_pf_fwd(const GConvK& k, const float* bias, int act, float* out, cudaStream_t st) {
+  PfParams p;
+  int tp = 0;
+  if (!pf_build(k, &p, &tp)) return set_err(NLT_ERR_INVALID, "pf_fwd not applicable");
+  pf_pack_w_kernel<<<4, 256, 0, st>>>(p, k.w, k.wt, k.wc, k.wn, k.Cout);
+  NLT_CUDA_LAUNCH_CHECK("pf_pack_w_kernel");
+  void* stage = nullptr;
+  cudaError_t e = cudaGetSymbolAddress(&stage, pwx_cw_stage);
+  if (e == cudaSuccess)
+    e = cudaMemcpyToSymbolAsync(pwx_cw, stage, (size_t)(p.K / 2) * k.Cout * sizeof(float2), 0, cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "pwx weight table: %s", cudaGetErrorString(e));
+  if (p.K == 64) return k.Cout == 16 ? pf_launch<16, 16, 128>(p, bias, act, out, st) : pf_launch<16, 32, 128>(p, bias, act, out, st);
+  return k.Cout == 16 ? pf_launch<32, 16, 64>(p, bias, act, out, st) : pf_launch<32, 32, 64>(p, bias, act, out, st);
+}
+
 bool pwx_wgrad_applicable(const GConvK& k, const float* G) {
   if (!pwx_enabled() || !pwx_shape_ok(k) || (G != nullptr && !aligned16(G))) return false;
   PwxParams p;

@@ -101,6 +101,10 @@ GEOMS = [
     ('conv', 2, 1, 7, 130, [8], 8),
     ('deconv', 2, 1, 6, 96, [16], 16),
     ('conv', 2, 1, 6, 64, [4], 4),
+    # staged-patch forward of the stride-2 2x2 convs (pf_fwd_kernel): K = 64 / 128 into 16 / 32 channels
+    ('conv', 2, 2, 4, 512, [16], 32),
+    ('conv', 2, 2, 4, 256, [32], 16),
+    ('conv', 2, 2, 6, 256, [16, 16], 32),
     # depth-to-space forward of the up-convs into 4 / 8 channels (pwx_d2s_fwd_kernel): 128-pixel row tiles
     ('deconv', 2, 2, 3, 128, [8, 32], 4),
     ('deconv', 2, 2, 2, 256, [16, 32, 32], 8),
