@@ -5,7 +5,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -I../../include"
 OBJS=""
-for f in nlt_gconv nlt_ops nlt_small nlt_tc nlt_barron nlt_pwx nlt_tcts nlt_norm nlt_tiny ${NLT_EXTRA_SRCS}; do
+for f in nlt_gconv nlt_ops nlt_small nlt_tc nlt_barron nlt_pwx nlt_tcts nlt_norm nlt_tiny nlt_wop ${NLT_EXTRA_SRCS}; do
   if [ ! -f $f.o ] || [ $f.cu -nt $f.o ] || [ nlt_common.cuh -nt $f.o ] || [ nlt_barron_core.h -nt $f.o ] || [ ../../include/nlt_b200.h -nt $f.o ]; then
     echo "nvcc $f.cu"
     $NVCC $FLAGS ${NLT_PTXAS_V:+-Xptxas -v} -c $f.cu -o $f.o

@@ -166,6 +166,10 @@ int launch_wgrad_tpp(const GConvK& k, const float* G, float* ws, WgradK* w, size
 // wide pointwise conv into 16 channels (nlt_pwx.cu): level 0 of the 64-channel query stack
 extern int g_opt_pwx;
 extern int g_opt_tiny;
+extern int g_opt_wop;
+bool wop_wgrad_applicable(const GConvK& k, const float* G);
+size_t wop_wgrad_ws_floats(const GConvK& k);
+int launch_wop_wgrad(const GConvK& k, const float* G, float* ws, WgradK* w, size_t* KD_pad, cudaStream_t st);
 bool tiny_stencil_applicable(const GConvK& k, const float* out, const float* mask_y);
 int launch_tiny_stencil(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act,
                         float* out, cudaStream_t st);

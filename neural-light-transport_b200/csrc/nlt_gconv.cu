@@ -694,6 +694,7 @@ int nlt_set_option(const char* name, int value) {
   if (strcmp(name, "tcs") == 0) { nlt::g_opt_tcs = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "pwx") == 0) { nlt::g_opt_pwx = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "pf") == 0) { g_opt_pf = value ? 1 : 0; return NLT_OK; }
+  if (strcmp(name, "wop") == 0) { nlt::g_opt_wop = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "tiny") == 0) { nlt::g_opt_tiny = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "dconv_cw") == 0) { nlt::g_opt_dconv_cw = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "dconv_wide") == 0) { nlt::g_opt_dconv_wide = value ? 1 : 0; return NLT_OK; }
@@ -802,12 +803,13 @@ int64_t nlt_gconv_wgrad_workspace_bytes(const nlt_gconv_desc* d) {
   GConvK ph[16];
   int np = 0;
   if (build_phases(d, ph, &np, /*allow_d2s=*/true) != NLT_OK) return -1;
-  if (np == 1 && ph[0].d2s && !wgrad_small_applicable(ph[0]) && !use_tc_wgrad(ph[0]) &&
-      build_phases(d, ph, &np, false) != NLT_OK) return -1;
+  if (np == 1 && ph[0].d2s && !wop_wgrad_applicable(ph[0], nullptr) && !wgrad_small_applicable(ph[0]) &&
+      !use_tc_wgrad(ph[0]) && build_phases(d, ph, &np, false) != NLT_OK) return -1;
   size_t mx = 0;
   for (int i = 0; i < np; ++i) {
     if (ph[i].M == 0) continue;
     size_t need = pwx_wgrad_applicable(ph[i], nullptr) ? pwx_wgrad_ws_floats(ph[i])
+                  : wop_wgrad_applicable(ph[i], nullptr) ? wop_wgrad_ws_floats(ph[i])
                   : pws_wgrad_applicable(ph[i], nullptr) ? pws_wgrad_ws_floats(ph[i])
                   : use_tc_wgrad(ph[i]) ? tc_wgrad_ws_floats(ph[i])
                   : wgrad_tpp_applicable(ph[i]) ? wgrad_tpp_ws_floats(ph[i])
@@ -825,7 +827,8 @@ int nlt_gconv_wgrad(const nlt_gconv_desc* d, const float* G, float* dW, float* d
   if (rc != NLT_OK) return rc;
   // a k == stride transposed conv keeps its one-pass depth-to-space form when a kernel takes it (the warp-stream
   // kernel for narrow tiles, the tcgen05 kernel from K_d = 128 up); otherwise s*s phases
-  if (np == 1 && ph[0].d2s && !wgrad_small_applicable(ph[0]) && !use_tc_wgrad(ph[0])) rc = build_phases(d, ph, &np, false);
+  if (np == 1 && ph[0].d2s && !wop_wgrad_applicable(ph[0], G) && !wgrad_small_applicable(ph[0]) && !use_tc_wgrad(ph[0]))
+    rc = build_phases(d, ph, &np, false);
   if (rc != NLT_OK) return rc;
   NLT_CHECK_ARG(G != nullptr && dW != nullptr && workspace != nullptr, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
@@ -838,6 +841,10 @@ int nlt_gconv_wgrad(const nlt_gconv_desc* d, const float* G, float* dW, float* d
     size_t KD_pad = 0;
     if (pwx_wgrad_applicable(k, G) && (int64_t)(pwx_wgrad_ws_floats(k) * sizeof(float)) <= workspace_bytes) {
       rc = launch_pwx_wgrad(k, G, ws, &w, &KD_pad, st);
+      if (rc != NLT_OK) return rc;
+    } else if (wop_wgrad_applicable(k, G) && (int64_t)(wop_wgrad_ws_floats(k) * sizeof(float)) <= workspace_bytes) {
+      // few-channel layers at (near) full resolution: register-tile outer products, one warp per unit kind (nlt_wop.cu)
+      rc = launch_wop_wgrad(k, G, ws, &w, &KD_pad, st);
       if (rc != NLT_OK) return rc;
     } else if (pws_wgrad_applicable(k, G) && (int64_t)(pws_wgrad_ws_floats(k) * sizeof(float)) <= workspace_bytes) {
       rc = launch_pws_wgrad(k, G, ws, &w, &KD_pad, st);

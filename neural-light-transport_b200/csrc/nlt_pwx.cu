@@ -689,6 +689,9 @@ static bool pf_build(const GConvK& k, PfParams* p, int* tp) {
     col += 4 * sg.C;
   }
   if (col != 64 && col != 128) return false;
+  // K = 128 into 32 channels needs 64 float2 accumulators next to a 64-pixel tile: 6 warps per SM, measured 3x slower
+  // than the tensor path on level 2 of the 64-channel workload (profiles/r2_p_*)
+  if (col == 128 && k.Cout == 32) return false;
   p->nseg = k.nseg; p->K = col;
   *tp = col == 64 ? 128 : 64;
   if (k.Wout % *tp != 0) return false;
@@ -737,7 +740,7 @@ int launch_pf_fwd(const GConvK& k, const float* bias, int act, float* out, cudaS
     e = cudaMemcpyToSymbolAsync(pwx_cw, stage, (size_t)(p.K / 2) * k.Cout * sizeof(float2), 0, cudaMemcpyDeviceToDevice, st);
   if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "pwx weight table: %s", cudaGetErrorString(e));
   if (p.K == 64) return k.Cout == 16 ? pf_launch<16, 16, 128>(p, bias, act, out, st) : pf_launch<16, 32, 128>(p, bias, act, out, st);
-  return k.Cout == 16 ? pf_launch<32, 16, 64>(p, bias, act, out, st) : pf_launch<32, 32, 64>(p, bias, act, out, st);
+  return pf_launch<32, 16, 64>(p, bias, act, out, st);
 }
 
 bool pwx_wgrad_applicable(const GConvK& k, const float* G) {

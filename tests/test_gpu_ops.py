@@ -105,6 +105,9 @@ GEOMS = [
     ('conv', 2, 2, 4, 512, [16], 32),
     ('conv', 2, 2, 4, 256, [32], 16),
     ('conv', 2, 2, 6, 256, [16, 16], 32),
+    # register-tile outer-product weight gradient (nlt_wop.cu), up-conv into 16 channels: 16 warps per CTA
+    ('deconv', 2, 2, 4, 64, [32, 64, 64], 16),
+    ('deconv', 2, 2, 5, 48, [16], 16),
     # depth-to-space forward of the up-convs into 4 / 8 channels (pwx_d2s_fwd_kernel): 128-pixel row tiles
     ('deconv', 2, 2, 3, 128, [8, 32], 4),
     ('deconv', 2, 2, 2, 256, [16, 32, 32], 8),
