@@ -175,8 +175,9 @@ int launch_tiny_stencil(const GConvK& k, const float* bias, int act, float beta,
                         float* out, cudaStream_t st);
 bool pwx_fwd_applicable(const GConvK& k, float beta, const float* mask_y, const float* out);
 int launch_pwx_fwd(const GConvK& k, const float* bias, int act, float* out, cudaStream_t st);
-bool pf_fwd_applicable(const GConvK& k, float beta, const float* mask_y, const float* out);
-int launch_pf_fwd(const GConvK& k, const float* bias, int act, float* out, cudaStream_t st);
+bool pf_fwd_applicable(const GConvK& k, const float* mask_y, const float* out);
+int launch_pf_fwd(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act, float* out,
+                  cudaStream_t st);
 bool pwx_d2s_fwd_applicable(const GConvK& k, float beta, const float* mask_y, const float* out);
 int launch_pwx_d2s_fwd(const GConvK& k, const float* bias, int act, float* out, cudaStream_t st);
 bool pwx_wgrad_applicable(const GConvK& k, const float* G);

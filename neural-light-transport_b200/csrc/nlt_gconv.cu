@@ -694,7 +694,7 @@ int nlt_set_option(const char* name, int value) {
   if (strcmp(name, "tcs") == 0) { nlt::g_opt_tcs = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "pwx") == 0) { nlt::g_opt_pwx = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "pf") == 0) { g_opt_pf = value ? 1 : 0; return NLT_OK; }
-  if (strcmp(name, "wop") == 0) { nlt::g_opt_wop = value ? 1 : 0; return NLT_OK; }
+  if (strcmp(name, "wop") == 0) { nlt::g_opt_wop = value; return NLT_OK; }
   if (strcmp(name, "tiny") == 0) { nlt::g_opt_tiny = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "dconv_cw") == 0) { nlt::g_opt_dconv_cw = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "dconv_wide") == 0) { nlt::g_opt_dconv_wide = value ? 1 : 0; return NLT_OK; }
@@ -727,7 +727,8 @@ int nlt_gconv_fwd_ws(const nlt_gconv_desc* d, const float* bias, int act, float 
   if (np == 1 && ph[0].M > 0 && tiny_stencil_applicable(ph[0], out, mask_y))
     return launch_tiny_stencil(ph[0], bias, act, beta, mask_y, mask_act, out, st);
   // 2x2 / stride-2 convs of levels 1-2 (K = 64 / 128 into 16 / 32 channels): staged-patch FFMA2 forward (nlt_pwx.cu)
-  if (np == 1 && pf_enabled() && pf_fwd_applicable(ph[0], beta, mask_y, out)) return launch_pf_fwd(ph[0], bias, act, out, st);
+  if (np == 1 && pf_enabled() && pf_fwd_applicable(ph[0], mask_y, out))
+    return launch_pf_fwd(ph[0], bias, act, beta, mask_y, mask_act, out, st);
   // up-convs into 4 / 8 channels: depth-to-space pointwise kernel with constant-bank weights (nlt_pwx.cu)
   if (np == 1 && pwx_d2s_fwd_applicable(ph[0], beta, mask_y, out)) return launch_pwx_d2s_fwd(ph[0], bias, act, out, st);
   if (np == 1 && workspace != nullptr && tc_enabled() && ph[0].M > 0 && tc_applicable(ph[0]) &&

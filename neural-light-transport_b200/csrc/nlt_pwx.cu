@@ -585,7 +585,7 @@ struct PfParams {
 };
 
 __global__ void pf_pack_w_kernel(const PfParams p, const float* __restrict__ w, long long wt, long long wc, long long wn,
-                                 int nout) {
+                                 int nout, int4 tapmap) {        // weight tap = (d0y + dsy * dy) * 2 + d0x + dsx * dx
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (p.K / 2) * nout; i += gridDim.x * blockDim.x) {
     const int cp = i / nout, n = i - cp * nout;
     float v[2];
@@ -594,7 +594,8 @@ __global__ void pf_pack_w_kernel(const PfParams p, const float* __restrict__ w, 
       int s = 0;
       while (s + 1 < p.nseg && col >= p.seg_col[s + 1]) ++s;
       const int r = col - p.seg_col[s], C = p.seg_C[s];
-      const int tap = r / C, c = r - tap * C;                  // tap = dy * 2 + dx
+      const int pt = r / C, c = r - pt * C;                    // patch position dy * 2 + dx
+      const int tap = (tapmap.x + tapmap.y * (pt >> 1)) * 2 + tapmap.z + tapmap.w * (pt & 1);
       v[h] = __ldg(w + (long long)tap * wt + (long long)(p.seg_coff[s] + c) * wc + (long long)n * wn);
     }
     pwx_cw_stage[i] = make_float2(v[0], v[1]);
@@ -603,7 +604,8 @@ __global__ void pf_pack_w_kernel(const PfParams p, const float* __restrict__ w, 
 
 template <int K4, int NOUT, int TP>
 __global__ void __launch_bounds__(TP, (K4 * 4 + 4) * TP * 4 <= 36 * 1024 ? (NOUT == 16 ? 6 : 4) : 3)
-pf_fwd_kernel(const PfParams p, const float* __restrict__ bias, const int act, float* __restrict__ out) {
+pf_fwd_kernel(const PfParams p, const float* __restrict__ bias, const int act, float* __restrict__ out,
+              const float beta, const float* __restrict__ mask_y, const int mask_act) {
   extern __shared__ __align__(16) float smem[];
   constexpr int KROW = K4 * 4 + 4;
   constexpr int OROW = NOUT + 4;
@@ -661,12 +663,31 @@ pf_fwd_kernel(const PfParams p, const float* __restrict__ bias, const int act, f
       srow[j] = make_float4(o[0], o[1], o[2], o[3]);
     }
     __syncthreads();
-    float4* dst = reinterpret_cast<float4*>(out + ((size_t)orow * p.Wout + x0) * NOUT);
+    const size_t o4 = ((size_t)orow * p.Wout + x0) * (NOUT / 4);
+    float4* dst = reinterpret_cast<float4*>(out) + o4;
     constexpr int Q = NOUT / 4;
+    // input-gradient use: + beta * (what the buffer holds), * activation derivative of the source (from its output y)
+    constexpr int CH = Q < 4 ? Q : 4;                          // float4 in flight per thread
 #pragma unroll
-    for (int i = 0; i < Q; ++i) {
-      const uint32_t qi = tid + i * TP;
-      dst[qi] = *reinterpret_cast<const float4*>(so + (qi / Q) * OROW + 4 * (qi % Q));
+    for (int i0 = 0; i0 < Q; i0 += CH) {
+      float4 oldv[CH], yv[CH];
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        const uint32_t qi = tid + (i0 + i) * TP;
+        if (beta != 0.f) oldv[i] = dst[qi];
+        if (mask_y != nullptr) yv[i] = __ldg(reinterpret_cast<const float4*>(mask_y) + o4 + qi);
+      }
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        const uint32_t qi = tid + (i0 + i) * TP;
+        float4 v = *reinterpret_cast<const float4*>(so + (qi / Q) * OROW + 4 * (qi % Q));
+        if (beta != 0.f) { v.x += beta * oldv[i].x; v.y += beta * oldv[i].y; v.z += beta * oldv[i].z; v.w += beta * oldv[i].w; }
+        if (mask_y != nullptr) {
+          v.x *= act_bwd_from_y(yv[i].x, mask_act); v.y *= act_bwd_from_y(yv[i].y, mask_act);
+          v.z *= act_bwd_from_y(yv[i].z, mask_act); v.w *= act_bwd_from_y(yv[i].w, mask_act);
+        }
+        dst[qi] = v;
+      }
     }
     __syncthreads();                                           // so is xs
   }
@@ -678,22 +699,24 @@ static bool pf_build(const GConvK& k, PfParams* p, int* tp) {
   if (k.Cout != k.cout_true || (k.Cout != 16 && k.Cout != 32)) return false;
   if (k.ay.nu != 2 || k.ax.nu != 2 || k.ay.iu != 1 || k.ax.iu != 1 || k.ay.i0 != 0 || k.ax.i0 != 0) return false;
   if (k.ay.it != 2 || k.ax.it != 2 || k.ay.os != 1 || k.ax.os != 1 || k.ay.o0 != 0 || k.ax.o0 != 0) return false;
-  if (k.ay.d0 != 0 || k.ax.d0 != 0 || k.ay.ds != 1 || k.ax.ds != 1 || k.kw != 2) return false;
+  if (k.kw != 2 || (k.ay.d0 + k.ay.ds) < 0 || (k.ay.d0 + k.ay.ds) > 1 || (k.ax.d0 + k.ax.ds) < 0 || (k.ax.d0 + k.ax.ds) > 1 ||
+      k.ay.d0 < 0 || k.ay.d0 > 1 || k.ax.d0 < 0 || k.ax.d0 > 1) return false;
   if (k.ay.nt != k.Hout || k.ax.nt != k.Wout || k.Hin != 2 * k.Hout || k.Win != 2 * k.Wout) return false;
   int col = 0;
   for (int s = 0; s < k.nseg; ++s) {
     const Seg& sg = k.seg[s];
-    if (!sg.vec || sg.sub != nullptr || sg.bcast || (sg.C != 16 && sg.C != 32)) return false;
+    if (!sg.vec || sg.sub != nullptr || sg.bcast || (sg.C != 4 && sg.C != 8 && sg.C != 16 && sg.C != 32)) return false;
     p->seg_ptr[s] = sg.ptr; p->seg_C[s] = sg.C; p->seg_col[s] = col; p->seg_coff[s] = sg.coff;
-    p->seg_l[s] = sg.C == 16 ? 3 : 4;
+    p->seg_l[s] = sg.C == 4 ? 1 : (sg.C == 8 ? 2 : (sg.C == 16 ? 3 : 4));
     col += 4 * sg.C;
   }
-  if (col != 64 && col != 128) return false;
+  if (col != 16 && col != 32 && col != 64 && col != 128) return false;
+  if (col == 16 && k.Cout != 16) return false;
   // K = 128 into 32 channels needs 64 float2 accumulators next to a 64-pixel tile: 6 warps per SM, measured 3x slower
   // than the tensor path on level 2 of the 64-channel workload (profiles/r2_p_*)
   if (col == 128 && k.Cout == 32) return false;
   p->nseg = k.nseg; p->K = col;
-  *tp = col == 64 ? 128 : 64;
+  *tp = col <= 64 ? 128 : 64;
   if (k.Wout % *tp != 0) return false;
   p->Hin = k.Hin; p->Win = k.Win; p->Wout = k.Wout;
   p->tiles_per_row = k.Wout / *tp;
@@ -703,15 +726,16 @@ static bool pf_build(const GConvK& k, PfParams* p, int* tp) {
   return true;
 }
 
-bool pf_fwd_applicable(const GConvK& k, float beta, const float* mask_y, const float* out) {
+bool pf_fwd_applicable(const GConvK& k, const float* mask_y, const float* out) {
   PfParams p;
   int tp = 0;
-  return beta == 0.f && mask_y == nullptr && aligned16(out) && pf_build(k, &p, &tp);
+  return aligned16(out) && (mask_y == nullptr || aligned16(mask_y)) && pf_build(k, &p, &tp);
 }
 
 template <int K4, int NOUT, int TP>
-static int pf_launch(const PfParams& p, const float* bias, int act, float* out, cudaStream_t st) {
-  constexpr size_t smem = (size_t)TP * (K4 * 4 + 4) * sizeof(float);
+static int pf_launch(const PfParams& p, const float* bias, int act, float* out, float beta, const float* mask_y,
+                     int mask_act, cudaStream_t st) {
+  constexpr size_t smem = (size_t)TP * (K4 * 4 + 4 > NOUT + 4 ? K4 * 4 + 4 : NOUT + 4) * sizeof(float);
   constexpr unsigned per_sm = smem <= 36 * 1024 ? (NOUT == 16 ? 6u : 4u) : 3u;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -722,25 +746,30 @@ static int pf_launch(const PfParams& p, const float* bias, int act, float* out, 
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const unsigned grid = p.ntiles < 148u * per_sm ? p.ntiles : 148u * per_sm;
-  pf_fwd_kernel<K4, NOUT, TP><<<grid, TP, smem, st>>>(p, bias, act, out);
+  pf_fwd_kernel<K4, NOUT, TP><<<grid, TP, smem, st>>>(p, bias, act, out, beta, mask_y, mask_act);
   NLT_CUDA_LAUNCH_CHECK("pf_fwd_kernel");
   return NLT_OK;
 }
 
 // main-stream only (shares pwx_cw)
-int launch_pf_fwd(const GConvK& k, const float* bias, int act, float* out, cudaStream_t st) {
+int launch_pf_fwd(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act, float* out,
+                  cudaStream_t st) {
   PfParams p;
   int tp = 0;
   if (!pf_build(k, &p, &tp)) return set_err(NLT_ERR_INVALID, "pf_fwd not applicable");
-  pf_pack_w_kernel<<<4, 256, 0, st>>>(p, k.w, k.wt, k.wc, k.wn, k.Cout);
+  pf_pack_w_kernel<<<4, 256, 0, st>>>(p, k.w, k.wt, k.wc, k.wn, k.Cout, make_int4(k.ay.d0, k.ay.ds, k.ax.d0, k.ax.ds));
   NLT_CUDA_LAUNCH_CHECK("pf_pack_w_kernel");
   void* stage = nullptr;
   cudaError_t e = cudaGetSymbolAddress(&stage, pwx_cw_stage);
   if (e == cudaSuccess)
     e = cudaMemcpyToSymbolAsync(pwx_cw, stage, (size_t)(p.K / 2) * k.Cout * sizeof(float2), 0, cudaMemcpyDeviceToDevice, st);
   if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "pwx weight table: %s", cudaGetErrorString(e));
-  if (p.K == 64) return k.Cout == 16 ? pf_launch<16, 16, 128>(p, bias, act, out, st) : pf_launch<16, 32, 128>(p, bias, act, out, st);
-  return pf_launch<32, 16, 64>(p, bias, act, out, st);
+#define PF_GO(K4_, N_, TP_) return pf_launch<K4_, N_, TP_>(p, bias, act, out, beta, mask_y, mask_act, st)
+  if (p.K == 16) PF_GO(4, 16, 128);
+  if (p.K == 32) { if (k.Cout == 16) PF_GO(8, 16, 128); PF_GO(8, 32, 128); }
+  if (p.K == 64) { if (k.Cout == 16) PF_GO(16, 16, 128); PF_GO(16, 32, 128); }
+  PF_GO(32, 16, 64);
+#undef PF_GO
 }
 
 bool pwx_wgrad_applicable(const GConvK& k, const float* G) {

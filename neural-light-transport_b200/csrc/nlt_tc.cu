@@ -882,7 +882,15 @@ static TcPlan tc_plan(const GConvK& k) {
   p.o0y = k.ay.o0; p.osy = k.ay.os; p.o0x = k.ax.o0; p.osx = k.ax.os;
   p.d2s = k.d2s; p.d2s_s = k.d2s_s;
   // few output tiles: narrower column tiles so that more SMs get work (A is re-read from L2)
-  while (pl.bn > 32 && (long long)p.N * p.tiles_x * p.tiles_y * (k.Cout / pl.bn) < 148) pl.bn /= 2;
+  // (only while the finer tiling still fits ONE wave of 148 CTAs: every tile pays the ~10 us pipeline fill / drain of
+  // the kernel again, profiles/r2_i_tc_ablation_31.txt; NLT_TC_SPLIT_WAVES=1 restores the round-1 rule "< 148 tiles")
+  static int split_waves = -1;
+  if (split_waves < 0) { const char* e = getenv("NLT_TC_SPLIT_WAVES"); split_waves = (e && e[0] == '1') ? 1 : 0; }
+  while (pl.bn > 32) {
+    const long long tiles = (long long)p.N * p.tiles_x * p.tiles_y * (k.Cout / pl.bn);
+    if (split_waves ? tiles >= 148 : 2 * tiles > 148) break;
+    pl.bn /= 2;
+  }
   p.n_tiles_n = k.Cout / pl.bn;
   const long long tt = (long long)p.N * p.tiles_x * p.tiles_y * p.n_tiles_n;
   if (tt > (1ll << 30)) return pl;

@@ -139,10 +139,13 @@ wop_wgrad_kernel(const __grid_constant__ WopParams p, float* __restrict__ ws) {
     }
 }
 
-int g_opt_wop = -1;     // option "wop" / NLT_WOP: 1 (default) this kernel, 0 the general weight-gradient routes
-static bool wop_enabled() {
-  if (g_opt_wop < 0) { const char* e = getenv("NLT_WOP"); g_opt_wop = (e && e[0] == '0') ? 0 : 1; }
-  return g_opt_wop == 1;
+// option "wop" / NLT_WOP: 0 off; 1 (default) the 4 -> 4 and 8 -> 8 stencils, where it wins (q12.1: 0.262 -> 0.206 ms,
+// q11.1: 0.167 -> 0.156 ms, profiles/r2_q_*); 2 also the 16 -> 16 stencils and the up-convs, which are correct but
+// 1.1-2x SLOWER than the staged-patch / tcgen05 kernels (16 warps/SM at 128 registers cannot hide the load latency)
+int g_opt_wop = -1;
+static int wop_level() {
+  if (g_opt_wop < 0) { const char* e = getenv("NLT_WOP"); g_opt_wop = e ? atoi(e) : 1; }
+  return g_opt_wop;
 }
 
 struct WopPlan {
@@ -158,7 +161,8 @@ static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 static WopPlan wop_plan(const GConvK& k, const float* G) {
   WopPlan pl;
   memset(&pl, 0, sizeof(pl));
-  if (!wop_enabled() || k.M == 0) return pl;
+  if (wop_level() <= 0 || k.M == 0) return pl;
+  if (wop_level() < 2 && (k.d2s || k.Cout > 8)) return pl;
   WopParams& p = pl.p;
   for (int s = 0; s < k.nseg; ++s)
     if (!k.seg[s].vec || k.seg[s].sub != nullptr || k.seg[s].bcast) return pl;

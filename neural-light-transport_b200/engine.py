@@ -97,9 +97,10 @@ class Tape:
         for fn in reversed(self.ops):
             fn()
         if USE_SIDE_STREAM and torch.cuda.is_available():
-            # join the weight-gradient branch BEFORE the closures (and with them the activations the side stream
+            # join the weight-gradient branches BEFORE the closures (and with them the activations the side streams
             # may still be reading) are released
-            torch.cuda.current_stream().wait_stream(side_stream())
+            for i in range(N_SIDE_STREAMS):
+                torch.cuda.current_stream().wait_stream(side_stream(i))
         self.ops = []
         while _PARKED:                      # leaves whose parked contribution nobody took along
             settle(_PARKED.pop())
@@ -110,6 +111,15 @@ class Workspace:
 
     def __init__(self):
         self.buf = None
+        self.subs = {}
+
+    def sub(self, i):
+        """Scratch of the i-th weight-gradient stream (0: this object)."""
+        if i == 0:
+            return self
+        if i not in self.subs:
+            self.subs[i] = Workspace()
+        return self.subs[i]
 
     def get(self, nbytes, device):
         if self.buf is None or self.buf.numel() * 4 < nbytes or self.buf.device != device:
@@ -141,17 +151,27 @@ class use_workspaces:
         global _WS, _WS_SIDE
         _WS, _WS_SIDE = self.saved
         return False
-_SIDE = {}                   # device index -> side stream
+_SIDE = {}                   # (device index, i) -> side stream
+# weight-gradient streams (NLT_SIDE_STREAMS, default 1): with more than one, consecutive layers' weight gradients go
+# round-robin to different streams, so that the latency-bound launches of the deep levels overlap each other too
+N_SIDE_STREAMS = max(1, int(os.environ.get('NLT_SIDE_STREAMS', '1')))
+_side_rr = [0]
 
 
-def side_stream():
+def side_stream(i=0):
     """Weight gradients do not feed the input-gradient chain: they run on a second stream (a parallel
     branch of the captured CUDA graph), which hides the launch/latency-bound deep-level launches behind
     the main chain.  Joined back in Tape.backward()."""
     dev = torch.cuda.current_device()
-    if dev not in _SIDE:
-        _SIDE[dev] = torch.cuda.Stream(device=dev)
-    return _SIDE[dev]
+    if (dev, i) not in _SIDE:
+        _SIDE[(dev, i)] = torch.cuda.Stream(device=dev)
+    return _SIDE[(dev, i)]
+
+
+def join_side_streams():
+    """Orders side stream 0 after everything issued so far on the other weight-gradient streams."""
+    for i in range(1, N_SIDE_STREAMS):
+        side_stream(0).wait_stream(side_stream(i))
 
 
 USE_SIDE_STREAM = os.environ.get('NLT_NO_SIDE_STREAM', '0') != '1'
@@ -371,10 +391,14 @@ class ConvLayer:
         if _SKIP_WGRAD:          # DIAGNOSTIC (NLT_SKIP_WGRAD=1, wrong results): time the forward + input-gradient chain alone
             pass
         elif USE_SIDE_STREAM:
-            main, side = torch.cuda.current_stream(), side_stream()
+            if getattr(self, '_side_idx', None) is None or self._side_idx >= N_SIDE_STREAMS:
+                self._side_idx = _side_rr[0] % N_SIDE_STREAMS      # one stream per layer: repeated (accumulating)
+                _side_rr[0] += 1                                   # launches of a layer stay ordered
+            si = self._side_idx
+            main, side = torch.cuda.current_stream(), side_stream(si)
             side.wait_stream(main)                      # dz (and the inputs) are complete on the main stream
             with torch.cuda.stream(side):
-                ws = _WS_SIDE.get(need, dz.device)
+                ws = _WS_SIDE.sub(si).get(need, dz.device)
                 PROF.run('wgrad ' + self.name, nb, lambda: nat.check(lib.nlt_gconv_wgrad(
                     C.byref(d), nat.ptr(dz), nat.ptr(self.gkernel), nat.ptr(self.gbias), acc, nat.ptr(ws),
                     ws.numel() * 4, nat.stream())))

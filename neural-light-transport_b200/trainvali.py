@@ -159,6 +159,7 @@ class GradReducer:
             return
         head = self.model.bucket.grad[:self.split]
         if engine.USE_SIDE_STREAM:
+            engine.join_side_streams()
             with torch.cuda.stream(engine.side_stream()):      # ordered after the wgrad launches issued so far
                 self.work = self.strategy.all_reduce_sum_async(head)
             head.record_stream(engine.side_stream())

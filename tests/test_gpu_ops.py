@@ -108,6 +108,9 @@ GEOMS = [
     # register-tile outer-product weight gradient (nlt_wop.cu), up-conv into 16 channels: 16 warps per CTA
     ('deconv', 2, 2, 4, 64, [32, 64, 64], 16),
     ('deconv', 2, 2, 5, 48, [16], 16),
+    # ... and the same kernel as the input gradient of up-convs (patch K = 16 / 32 / 64 of the gradient, + beta, mask)
+    ('deconv', 2, 2, 2, 128, [16, 16], 4),
+    ('deconv', 2, 2, 2, 128, [32], 16),
     # depth-to-space forward of the up-convs into 4 / 8 channels (pwx_d2s_fwd_kernel): 128-pixel row tiles
     ('deconv', 2, 2, 3, 128, [8, 32], 4),
     ('deconv', 2, 2, 2, 256, [16, 32, 32], 8),
@@ -157,6 +160,23 @@ def test_gconv_forward_backward(kind, k, s, H, W, segc, cout, act):
         # every input Act was declared as a leakyrelu output: its grad carries the mask of a.t
         want = x.grad * torch.where(x > 0, 1.0, 0.3)
         _close(a.grad, want, rtol=1e-4, atol=1e-4)
+
+
+WOP_ALL_SHAPES = [g for g in GEOMS if g[4] >= 32 and (
+    (g[0] == 'deconv' and g[1] == 2 and g[2] == 2 and g[6] in (4, 8, 16) and all(c % 4 == 0 for c in g[5])) or
+    (g[1] == 2 and g[2] == 1 and g[5] == [16] and g[6] == 16))]
+
+
+@pytest.mark.parametrize('kind,k,s,H,W,segc,cout', WOP_ALL_SHAPES)
+def test_outer_product_wgrad_all_shapes(kind, k, s, H, W, segc, cout):
+    """nlt_wop.cu also serves the up-convs and the 16 -> 16 stencils (option wop = 2; off by default because the
+    staged-patch / tcgen05 kernels are faster there): same oracle check as every other route."""
+    import nlt_native as nat
+    nat.set_option('wop', 2)
+    try:
+        test_gconv_forward_backward(kind, k, s, H, W, segc, cout, 'leakyrelu')
+    finally:
+        nat.set_option('wop', int(os.environ.get('NLT_WOP', '1')))
 
 
 TC_SHAPES = [g for g in GEOMS if all(c % 16 == 0 for c in g[5]) and g[6] % 16 == 0 and g[3] * g[4] >= 256]
