@@ -101,6 +101,17 @@ int64_t nlt_gconv_fwd_workspace_bytes(const nlt_gconv_desc* d);
 int nlt_gconv_fwd_ws(const nlt_gconv_desc* d, const float* bias, int act,
                      float beta, const float* mask_y, int mask_act, float* out,
                      void* workspace, int64_t workspace_bytes, void* stream);
+/* The same op with the weight planes prepared AHEAD of time: the weights of a train step are final when the step
+ * starts (tf.keras optimizers apply at its end, nlt/trainvali.py:279-281), so the caller can run every layer's
+ * nlt_gconv_pack_weights on a separate stream that depends on nothing but the start of the step, and the per-layer
+ * pack kernel leaves the critical path.  nlt_gconv_fwd_pack_bytes: size of the planes, 0 when the op (with this beta /
+ * mask use) is not served by the tensor-core kernel, < 0 on error.  `packed` must stay untouched until the
+ * nlt_gconv_fwd_packed call that reads it has finished. */
+int64_t nlt_gconv_fwd_pack_bytes(const nlt_gconv_desc* d, float beta, int has_mask);
+int nlt_gconv_pack_weights(const nlt_gconv_desc* d, void* packed, int64_t packed_bytes, void* stream);
+int nlt_gconv_fwd_packed(const nlt_gconv_desc* d, const float* bias, int act,
+                         float beta, const float* mask_y, int mask_act, float* out,
+                         const void* packed, int64_t packed_bytes, void* stream);
 
 /* A second, pointwise term fused into the epilogue of a pointwise op (1x1 stride-1 conv, or a
  * k == stride transposed conv in its depth-to-space form):

@@ -202,7 +202,8 @@ extern unsigned long long g_tc_launches;
 bool tc_applicable(const GConvK& k);
 size_t tc_workspace_bytes(const GConvK& k);
 int launch_tc(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act, float* out,
-              void* workspace, size_t workspace_bytes, cudaStream_t st);
+              void* workspace, size_t workspace_bytes, cudaStream_t st, bool prepacked = false);
+int tc_pack(const GConvK& k, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 bool tc_wgrad_applicable(const GConvK& k);
 size_t tc_wgrad_ws_floats(const GConvK& k);

@@ -712,8 +712,49 @@ int64_t nlt_gconv_fwd_workspace_bytes(const nlt_gconv_desc* d) {
   return 0;
 }
 
+// does the forward of `d` run on the tcgen05 kernel (which reads packed hi / lo weight planes)?  Mirrors the routing
+// order of gconv_fwd_impl below.
+static bool fwd_takes_tc(const GConvK* ph, int np, float beta, const float* mask_y, const float* out) {
+  if (np != 1 || ph[0].M == 0) return false;
+  if (tiny_stencil_applicable(ph[0], out, mask_y)) return false;
+  if (pf_enabled() && pf_fwd_applicable(ph[0], mask_y, out)) return false;
+  if (pwx_d2s_fwd_applicable(ph[0], beta, mask_y, out)) return false;
+  return tc_enabled() && tc_applicable(ph[0]);
+}
+
+int64_t nlt_gconv_fwd_pack_bytes(const nlt_gconv_desc* d, float beta, int has_mask) {
+  GConvK ph[16];
+  int np = 0;
+  if (build_phases(d, ph, &np, /*allow_d2s=*/true) != NLT_OK) return -1;
+  const float* aligned = reinterpret_cast<const float*>((uintptr_t)256);     // stands for any 16-byte aligned buffer
+  if (!fwd_takes_tc(ph, np, beta, has_mask ? aligned : nullptr, aligned)) return 0;
+  return (int64_t)tc_workspace_bytes(ph[0]);
+}
+
+int nlt_gconv_pack_weights(const nlt_gconv_desc* d, void* packed, int64_t packed_bytes, void* stream) {
+  GConvK ph[16];
+  int np = 0;
+  int rc = build_phases(d, ph, &np, /*allow_d2s=*/true);
+  if (rc != NLT_OK) return rc;
+  NLT_CHECK_ARG(np == 1 && tc_enabled() && tc_applicable(ph[0]), "this op does not run on the tensor-core kernel");
+  return tc_pack(ph[0], packed, (size_t)packed_bytes, (cudaStream_t)stream);
+}
+
+static int gconv_fwd_impl(const nlt_gconv_desc* d, const float* bias, int act, float beta, const float* mask_y,
+                          int mask_act, float* out, void* workspace, int64_t workspace_bytes, void* stream, bool prepacked);
+
 int nlt_gconv_fwd_ws(const nlt_gconv_desc* d, const float* bias, int act, float beta, const float* mask_y,
                      int mask_act, float* out, void* workspace, int64_t workspace_bytes, void* stream) {
+  return gconv_fwd_impl(d, bias, act, beta, mask_y, mask_act, out, workspace, workspace_bytes, stream, false);
+}
+
+int nlt_gconv_fwd_packed(const nlt_gconv_desc* d, const float* bias, int act, float beta, const float* mask_y,
+                         int mask_act, float* out, const void* packed, int64_t packed_bytes, void* stream) {
+  return gconv_fwd_impl(d, bias, act, beta, mask_y, mask_act, out, const_cast<void*>(packed), packed_bytes, stream, true);
+}
+
+static int gconv_fwd_impl(const nlt_gconv_desc* d, const float* bias, int act, float beta, const float* mask_y,
+                          int mask_act, float* out, void* workspace, int64_t workspace_bytes, void* stream, bool prepacked) {
   GConvK ph[16];
   int np = 0;
   int rc = build_phases(d, ph, &np, /*allow_d2s=*/true);
@@ -731,9 +772,13 @@ int nlt_gconv_fwd_ws(const nlt_gconv_desc* d, const float* bias, int act, float 
     return launch_pf_fwd(ph[0], bias, act, beta, mask_y, mask_act, out, st);
   // up-convs into 4 / 8 channels: depth-to-space pointwise kernel with constant-bank weights (nlt_pwx.cu)
   if (np == 1 && pwx_d2s_fwd_applicable(ph[0], beta, mask_y, out)) return launch_pwx_d2s_fwd(ph[0], bias, act, out, st);
+  if (prepacked)
+    NLT_CHECK_ARG(fwd_takes_tc(ph, np, beta, mask_y, out) && workspace != nullptr &&
+                  (int64_t)tc_workspace_bytes(ph[0]) <= workspace_bytes,
+                  "nlt_gconv_fwd_packed: this op does not run on the tensor-core kernel (nlt_gconv_fwd_pack_bytes == 0)");
   if (np == 1 && workspace != nullptr && tc_enabled() && ph[0].M > 0 && tc_applicable(ph[0]) &&
       (int64_t)tc_workspace_bytes(ph[0]) <= workspace_bytes)
-    return launch_tc(ph[0], bias, act, beta, mask_y, mask_act, out, workspace, (size_t)workspace_bytes, st);
+    return launch_tc(ph[0], bias, act, beta, mask_y, mask_act, out, workspace, (size_t)workspace_bytes, st, prepacked);
   for (int i = 0; i < np; ++i) {
     const GConvK& k = ph[i];
     if (k.M == 0) continue;

@@ -710,8 +710,9 @@ static bool pf_build(const GConvK& k, PfParams* p, int* tp) {
     p->seg_l[s] = sg.C == 4 ? 1 : (sg.C == 8 ? 2 : (sg.C == 16 ? 3 : 4));
     col += 4 * sg.C;
   }
-  if (col != 16 && col != 32 && col != 64 && col != 128) return false;
-  if (col == 16 && k.Cout != 16) return false;
+  // (K = 16 -- the input gradient of the up-conv into 4 channels -- is served better by the wide stencil kernel:
+  //  0.237 vs 0.218 ms on level 12, profiles/r2_r_*)
+  if (col != 32 && col != 64 && col != 128) return false;
   // K = 128 into 32 channels needs 64 float2 accumulators next to a 64-pixel tile: 6 warps per SM, measured 3x slower
   // than the tensor path on level 2 of the 64-channel workload (profiles/r2_p_*)
   if (col == 128 && k.Cout == 32) return false;
@@ -765,7 +766,6 @@ int launch_pf_fwd(const GConvK& k, const float* bias, int act, float beta, const
     e = cudaMemcpyToSymbolAsync(pwx_cw, stage, (size_t)(p.K / 2) * k.Cout * sizeof(float2), 0, cudaMemcpyDeviceToDevice, st);
   if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "pwx weight table: %s", cudaGetErrorString(e));
 #define PF_GO(K4_, N_, TP_) return pf_launch<K4_, N_, TP_>(p, bias, act, out, beta, mask_y, mask_act, st)
-  if (p.K == 16) PF_GO(4, 16, 128);
   if (p.K == 32) { if (k.Cout == 16) PF_GO(8, 16, 128); PF_GO(8, 32, 128); }
   if (p.K == 64) { if (k.Cout == 16) PF_GO(16, 16, 128); PF_GO(16, 32, 128); }
   PF_GO(32, 16, 64);

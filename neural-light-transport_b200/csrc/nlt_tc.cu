@@ -1493,20 +1493,33 @@ static int tc_launch_bn(const TcMaps& maps, const TcPlan& pl, cudaStream_t st) {
   return NLT_OK;
 }
 
-int launch_tc(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act, float* out,
-              void* workspace, size_t workspace_bytes, cudaStream_t st) {
+// hi / lo planes of the weights in K-block layout (what the B tensor maps of the conv kernel read)
+int tc_pack(const GConvK& k, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   TcPlan pl = tc_plan(k);
   if (!pl.ok) return set_err(NLT_ERR_INVALID, "tensor-core path not applicable");
   const size_t need = 2 * pl.pack_floats * sizeof(float) + 256;
   NLT_CHECK_ARG(workspace != nullptr && workspace_bytes >= need, "tc workspace too small: need %zu", need);
   float* bhi = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
   float* blo = bhi + pl.pack_floats;
-  {
-    const size_t total = pl.pack_floats;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    tc_pack_weights_kernel<<<blocks, 256, 0, st>>>(k, pl.kbw, pl.p.kb_total, pl.chunks_per_tap, pl.cout_pad, bhi, blo);
-    NLT_CUDA_LAUNCH_CHECK("tc_pack_weights_kernel");
+  const size_t total = pl.pack_floats;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  tc_pack_weights_kernel<<<blocks, 256, 0, st>>>(k, pl.kbw, pl.p.kb_total, pl.chunks_per_tap, pl.cout_pad, bhi, blo);
+  NLT_CUDA_LAUNCH_CHECK("tc_pack_weights_kernel");
+  return NLT_OK;
+}
+
+int launch_tc(const GConvK& k, const float* bias, int act, float beta, const float* mask_y, int mask_act, float* out,
+              void* workspace, size_t workspace_bytes, cudaStream_t st, bool prepacked) {
+  TcPlan pl = tc_plan(k);
+  if (!pl.ok) return set_err(NLT_ERR_INVALID, "tensor-core path not applicable");
+  const size_t need = 2 * pl.pack_floats * sizeof(float) + 256;
+  NLT_CHECK_ARG(workspace != nullptr && workspace_bytes >= need, "tc workspace too small: need %zu", need);
+  float* bhi = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  float* blo = bhi + pl.pack_floats;
+  if (!prepacked) {
+    const int rc0 = tc_pack(k, workspace, workspace_bytes, st);
+    if (rc0 != NLT_OK) return rc0;
   }
   TcMaps maps;
   int rc = encode_maps(k, pl, bhi, blo, &maps);

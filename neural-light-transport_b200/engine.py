@@ -106,12 +106,43 @@ class Tape:
             settle(_PARKED.pop())
 
 
+class PackArena:
+    """Bump allocator for the packed weight planes of ONE step (hi / lo TF32 planes of every tensor-core layer call):
+    with PACK_AHEAD the planes are produced on the pack stream ahead of the layers that read them, so every call needs
+    its own buffer.  Chunks are kept (addresses stay valid for a captured graph); `reset()` rewinds at step begin."""
+    CHUNK = 256 << 20
+
+    def __init__(self):
+        self.chunks = []
+        self.ci = 0
+        self.off = 0
+
+    def reset(self):
+        self.ci = 0
+        self.off = 0
+
+    def alloc(self, nbytes, device):
+        nbytes = (nbytes + 255) // 256 * 256
+        while True:
+            if self.ci < len(self.chunks):
+                buf = self.chunks[self.ci]
+                if buf.device == device and self.off + nbytes <= buf.numel():
+                    out = buf[self.off:self.off + nbytes]
+                    self.off += nbytes
+                    return out
+                self.ci += 1
+                self.off = 0
+                continue
+            self.chunks.append(torch.empty(max(self.CHUNK, nbytes), dtype=torch.uint8, device=device))
+
+
 class Workspace:
     """Grow-only device scratch shared by all wgrad calls on one stream."""
 
     def __init__(self):
         self.buf = None
         self.subs = {}
+        self.arena = PackArena()
 
     def sub(self, i):
         """Scratch of the i-th weight-gradient stream (0: this object)."""
@@ -152,9 +183,10 @@ class use_workspaces:
         _WS, _WS_SIDE = self.saved
         return False
 _SIDE = {}                   # (device index, i) -> side stream
-# weight-gradient streams (NLT_SIDE_STREAMS, default 1): with more than one, consecutive layers' weight gradients go
-# round-robin to different streams, so that the latency-bound launches of the deep levels overlap each other too
-N_SIDE_STREAMS = max(1, int(os.environ.get('NLT_SIDE_STREAMS', '1')))
+# weight-gradient streams (NLT_SIDE_STREAMS, default 2): consecutive layers' weight gradients go round-robin to
+# different streams, so that the latency-bound launches of the deep levels overlap each other too (cfg4 step 14.83 ->
+# 14.72 ms with 2, no further gain with 3 or 4: profiles/r2_r_*)
+N_SIDE_STREAMS = max(1, int(os.environ.get('NLT_SIDE_STREAMS', '2')))
 _side_rr = [0]
 
 
@@ -184,10 +216,52 @@ WGRAD_HOOK = None
 FWD_TAP = None
 
 
+# NLT_PACK_AHEAD (default 1): weight planes of the tensor-core layers are packed on a stream that hangs off the START of
+# the step (weights are final there), not in front of each layer's kernel on the main stream
+PACK_AHEAD = os.environ.get('NLT_PACK_AHEAD', '1') != '0'
+_PACK = {}                   # device index -> pack stream
+_STEP_ROOT = {}              # device index -> [event recorded on the main stream at step begin, forked?]
+
+
+def pack_stream():
+    dev = torch.cuda.current_device()
+    if dev not in _PACK:
+        _PACK[dev] = torch.cuda.Stream(device=dev)
+    return _PACK[dev]
+
+
+def begin_step():
+    """Marks the start of a forward (+ backward) pass: everything the pack stream does in this step depends on this
+    point only.  Called by the model before its first layer."""
+    if not (PACK_AHEAD and torch.cuda.is_available()):
+        return
+    _WS.arena.reset()
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream())
+    _STEP_ROOT[torch.cuda.current_device()] = [ev, False]
+
+
 def gconv_fwd(d, bias, act, beta, mask, mask_act, out):
     """nlt_gconv_fwd_ws with the shared scratch (tensor-core path where the
     shape allows it, fp32 kernels otherwise)."""
     lib = nat.lib()
+    root = _STEP_ROOT.get(out.device.index) if PACK_AHEAD else None
+    if root is not None:
+        pb = lib.nlt_gconv_fwd_pack_bytes(C.byref(d), beta, 1 if mask is not None else 0)
+        if pb < 0:
+            nat.check(-1)
+        if pb > 0:
+            main, ps = torch.cuda.current_stream(), pack_stream()
+            if not root[1]:
+                ps.wait_event(root[0])                   # fork off the start of the step
+                root[1] = True
+            buf = _WS.arena.alloc(pb, out.device)
+            with torch.cuda.stream(ps):
+                nat.check(lib.nlt_gconv_pack_weights(C.byref(d), nat.ptr(buf), pb, nat.stream()))
+            main.wait_stream(ps)
+            nat.check(lib.nlt_gconv_fwd_packed(C.byref(d), nat.ptr(bias), act, beta, nat.ptr(mask), mask_act,
+                                               nat.ptr(out), nat.ptr(buf), pb, nat.stream()))
+            return
     need = lib.nlt_gconv_fwd_workspace_bytes(C.byref(d))
     if need < 0:
         nat.check(-1)

@@ -201,6 +201,8 @@ class Model(BaseModel):
             nn_base = nn_base.reshape((-1,) + tuple(nn_base.shape[2:]))
         train = mode == 'train'
         tape = Tape() if train else None
+        import engine
+        engine.begin_step()           # start of the step: what the weight-plane pack stream hangs off
         if train:
             self._bucket and self._bucket.begin_step()
         # x = concat(base, cvis, lvis); y_obs = [nn_rgb - nn_base]  (nlt.py:95-96)

@@ -59,6 +59,10 @@ _SIGS = {
     'nlt_gconv_fwd_workspace_bytes': (C.c_int64, [C.POINTER(GConvDesc)]),
     'nlt_gconv_fwd_ws': (C.c_int, [C.POINTER(GConvDesc), C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    'nlt_gconv_fwd_pack_bytes': (C.c_int64, [C.POINTER(GConvDesc), C.c_float, C.c_int]),
+    'nlt_gconv_pack_weights': (C.c_int, [C.POINTER(GConvDesc), C.c_void_p, C.c_int64, C.c_void_p]),
+    'nlt_gconv_fwd_packed': (C.c_int, [C.POINTER(GConvDesc), C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'nlt_gconv_wgrad_workspace_bytes': (C.c_int64, [C.POINTER(GConvDesc)]),
     'nlt_gconv_wgrad': (C.c_int, [C.POINTER(GConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                   C.c_int64, C.c_void_p]),

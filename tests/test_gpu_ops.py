@@ -109,7 +109,6 @@ GEOMS = [
     ('deconv', 2, 2, 4, 64, [32, 64, 64], 16),
     ('deconv', 2, 2, 5, 48, [16], 16),
     # ... and the same kernel as the input gradient of up-convs (patch K = 16 / 32 / 64 of the gradient, + beta, mask)
-    ('deconv', 2, 2, 2, 128, [16, 16], 4),
     ('deconv', 2, 2, 2, 128, [32], 16),
     # depth-to-space forward of the up-convs into 4 / 8 channels (pwx_d2s_fwd_kernel): 128-pixel row tiles
     ('deconv', 2, 2, 3, 128, [8, 32], 4),
