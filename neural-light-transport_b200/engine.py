@@ -122,18 +122,19 @@ class PackArena:
         self.off = 0
 
     def alloc(self, nbytes, device):
-        nbytes = (nbytes + 255) // 256 * 256
+        """A float32 view of at least `nbytes` bytes, 256-byte aligned inside its chunk."""
+        n = (nbytes + 255) // 256 * 64                      # floats
         while True:
             if self.ci < len(self.chunks):
                 buf = self.chunks[self.ci]
-                if buf.device == device and self.off + nbytes <= buf.numel():
-                    out = buf[self.off:self.off + nbytes]
-                    self.off += nbytes
+                if buf.device == device and self.off + n <= buf.numel():
+                    out = buf[self.off:self.off + n]
+                    self.off += n
                     return out
                 self.ci += 1
                 self.off = 0
                 continue
-            self.chunks.append(torch.empty(max(self.CHUNK, nbytes), dtype=torch.uint8, device=device))
+            self.chunks.append(torch.empty(max(self.CHUNK // 4, n), dtype=torch.float32, device=device))
 
 
 class Workspace:
@@ -257,10 +258,10 @@ def gconv_fwd(d, bias, act, beta, mask, mask_act, out):
                 root[1] = True
             buf = _WS.arena.alloc(pb, out.device)
             with torch.cuda.stream(ps):
-                nat.check(lib.nlt_gconv_pack_weights(C.byref(d), nat.ptr(buf), pb, nat.stream()))
+                nat.check(lib.nlt_gconv_pack_weights(C.byref(d), nat.ptr(buf), buf.numel() * 4, nat.stream()))
             main.wait_stream(ps)
             nat.check(lib.nlt_gconv_fwd_packed(C.byref(d), nat.ptr(bias), act, beta, nat.ptr(mask), mask_act,
-                                               nat.ptr(out), nat.ptr(buf), pb, nat.stream()))
+                                               nat.ptr(out), nat.ptr(buf), buf.numel() * 4, nat.stream()))
             return
     need = lib.nlt_gconv_fwd_workspace_bytes(C.byref(d))
     if need < 0:

@@ -300,3 +300,29 @@ def test_uint8_inputs_are_bit_identical_to_float32_inputs():
     b = m(u8, mode='vali')
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
     assert torch.equal(a[3]['pred'], b[3]['pred'])
+
+
+def test_pack_ahead_and_extra_wgrad_streams_do_not_change_results():
+    """Scheduling switches only: weight planes packed on the pack stream (engine.PACK_AHEAD) and weight gradients on
+    1 / 2 / 3 side streams must give bit-identical predictions and gradients (same kernels, same order per buffer)."""
+    import engine
+    from util import synth
+    saved = (engine.PACK_AHEAD, engine.N_SIDE_STREAMS)
+    outs = []
+    try:
+        for pack, nside in ((False, 1), (True, 1), (True, 2), (True, 3)):
+            engine.PACK_AHEAD, engine.N_SIDE_STREAMS = pack, nside
+            m, cfg = make_model(uvh=128, uvw=128, imh=64, imw=64)
+            m.build(5, 3)
+            bt = synth.make_batch(2, 128, 64, seed=11)
+            pred, gt, kw, _ = m(bt, mode='train')
+            m.set_loss_grad_scale(0.5)
+            m.compute_loss(pred, gt, **kw)
+            m.backward()
+            torch.cuda.synchronize()
+            outs.append((pred.clone(), m.bucket.grad.clone()))
+    finally:
+        engine.PACK_AHEAD, engine.N_SIDE_STREAMS = saved
+    for pred, grad in outs[1:]:
+        assert torch.equal(pred, outs[0][0])
+        assert torch.equal(grad, outs[0][1])
