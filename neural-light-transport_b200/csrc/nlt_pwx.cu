@@ -65,7 +65,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __device__ __forceinline__ uint32_t pwx_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // stage the x rows of tile `t` into xs (row stride p.krow floats); rows beyond M are zero-filled by the caller once
-__device__ __forceinline__ void pwx_stage_x(const PwxParams& p, uint32_t t, float* xs) {
+__device__ __forceinline__ void pwx_stage_x(const PwxParams& p, uint32_t t, float* xs, const uint32_t nthr = PWX_THREADS) {
   const uint32_t pix0 = t * PWX_T;
   const uint32_t npx = min((uint32_t)PWX_T, p.M - pix0);
   const uint32_t xs_u = pwx_smem_u32(xs);
@@ -76,7 +76,7 @@ __device__ __forceinline__ void pwx_stage_x(const PwxParams& p, uint32_t t, floa
       const uint32_t c4 = (uint32_t)sg.C >> 2;
       const uint32_t n4 = npx * c4;
       const float4* src = reinterpret_cast<const float4*>(sg.ptr + (size_t)pix0 * sg.C);
-      for (uint32_t i = threadIdx.x; i < n4; i += PWX_THREADS) {
+      for (uint32_t i = threadIdx.x; i < n4; i += nthr) {
         const uint32_t px = fdiv(i, sg.div);
         const uint32_t j = i - px * c4;
         cp_async16(xs_u + (px * p.krow + sg.off + 4 * j) * 4, src + i);
@@ -84,7 +84,7 @@ __device__ __forceinline__ void pwx_stage_x(const PwxParams& p, uint32_t t, floa
     } else {
       const uint32_t n = npx * (uint32_t)sg.C;
       const float* src = sg.ptr + (size_t)pix0 * sg.C;
-      for (uint32_t i = threadIdx.x; i < n; i += PWX_THREADS) {
+      for (uint32_t i = threadIdx.x; i < n; i += nthr) {
         const uint32_t px = fdiv(i, sg.div);
         const uint32_t c = i - px * (uint32_t)sg.C;
         cp_async4(xs_u + (px * p.krow + sg.off + c) * 4, src + i);
@@ -94,8 +94,8 @@ __device__ __forceinline__ void pwx_stage_x(const PwxParams& p, uint32_t t, floa
 }
 
 // zero the rows [from, PWX_T) of an x stage
-__device__ __forceinline__ void pwx_zero_rows(const PwxParams& p, float* xs, uint32_t from) {
-  for (uint32_t i = from * p.krow + threadIdx.x; i < (uint32_t)PWX_T * p.krow; i += PWX_THREADS) xs[i] = 0.f;
+__device__ __forceinline__ void pwx_zero_rows(const PwxParams& p, float* xs, uint32_t from, const uint32_t nthr = PWX_THREADS) {
+  for (uint32_t i = from * p.krow + threadIdx.x; i < (uint32_t)PWX_T * p.krow; i += nthr) xs[i] = 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -122,60 +122,75 @@ __global__ void pwx_pack_w_kernel(const PwxParams p, const float* __restrict__ w
   }
 }
 
-template <int K4>
-__global__ void __launch_bounds__(PWX_THREADS, PWX_CTAS_PER_SM)
+// NS threads per pixel, each owning 16 / NS outputs (warp-uniform split: the constant-bank weights stay uniform
+// operands); the output stage aliases the x stage, so that the CTA needs 35 KB at K = 64 and 4 CTAs x 8 warps fit.
+// One thread per pixel at 45 KB (the round-2 form until profiles/r2_q_*): 14 resident warps, FMA pipe 51 % busy.
+template <int K4, int NS>
+__global__ void __launch_bounds__(PWX_THREADS * NS, NS == 1 ? (K4 <= 16 ? 6 : (K4 <= 24 ? 4 : 3)) : (K4 <= 16 ? 4 : 3))
 pwx_fwd_kernel(const PwxParams p, const float* __restrict__ bias, const int act, float* __restrict__ out) {
   extern __shared__ __align__(16) float smem[];
   constexpr int KROW = K4 * 4 + 4;
+  constexpr int THR = PWX_THREADS * NS, NO = 16 / NS;
   float* xs = smem;
-  float* so = xs + PWX_T * KROW;                               // [PWX_T][PWX_OROW]
+  float* so = smem;                                            // [PWX_T][PWX_OROW], aliases xs (KROW >= PWX_OROW)
   const int tid = threadIdx.x;
+  const int px_t = tid % PWX_T, half = tid / PWX_T;
 
-  pwx_zero_rows(p, xs, 0);
-  float bv[16];
-#pragma unroll
-  for (int n = 0; n < 16; ++n) bv[n] = bias ? __ldg(bias + n) : 0.f;
+  pwx_zero_rows(p, xs, 0, THR);
   __syncthreads();
 
   for (uint32_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-    if (p.M - t * PWX_T < (uint32_t)PWX_T) pwx_zero_rows(p, xs, p.M - t * PWX_T);   // partial last tile
-    pwx_stage_x(p, t, xs);
+    pwx_stage_x(p, t, xs, THR);
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();                                           // tile t has landed for every thread
 
-    float2 acc[16];
+    float2 acc[NO];
 #pragma unroll
-    for (int n = 0; n < 16; ++n) acc[n] = make_float2(bv[n], 0.f);
-    const float4* xrow = reinterpret_cast<const float4*>(xs + tid * KROW);
+    for (int n = 0; n < NO; ++n) acc[n] = make_float2(0.f, 0.f);
+    const float4* xrow = reinterpret_cast<const float4*>(xs + px_t * KROW);
+    const float2* cw = pwx_cw + half * NO;
 #pragma unroll
     for (int q = 0; q < K4; ++q) {
       const float4 xv = xrow[q];
       const float2 xa = make_float2(xv.x, xv.y), xb = make_float2(xv.z, xv.w);
 #pragma unroll
-      for (int n = 0; n < 16; ++n) {
-        acc[n] = __ffma2_rn(xa, pwx_cw[(2 * q) * 16 + n], acc[n]);
-        acc[n] = __ffma2_rn(xb, pwx_cw[(2 * q + 1) * 16 + n], acc[n]);
+      for (int n = 0; n < NO; ++n) {
+        acc[n] = __ffma2_rn(xa, cw[(2 * q) * 16 + n], acc[n]);
+        acc[n] = __ffma2_rn(xb, cw[(2 * q + 1) * 16 + n], acc[n]);
       }
     }
-    float o[16];
+    __syncthreads();                                           // every row of xs has been read
+    float4* srow = reinterpret_cast<float4*>(so + px_t * PWX_OROW + half * NO);
 #pragma unroll
-    for (int n = 0; n < 16; ++n) o[n] = act_fwd(acc[n].x + acc[n].y, act);
-    float4* srow = reinterpret_cast<float4*>(so + tid * PWX_OROW);
+    for (int j = 0; j < NO / 4; ++j) {
+      float o[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) srow[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-    __syncthreads();                                           // outputs staged; every thread is done with xs
+      for (int e = 0; e < 4; ++e) {
+        const int n = 4 * j + e;
+        o[e] = act_fwd(acc[n].x + acc[n].y + (bias ? __ldg(bias + half * NO + n) : 0.f), act);
+      }
+      srow[j] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    __syncthreads();                                           // outputs staged
     // coalesced 16-byte stores: the tile's outputs are one contiguous run of PWX_T*16 floats
     const uint32_t pix0 = t * PWX_T;
     const uint32_t npx = min((uint32_t)PWX_T, p.M - pix0);
     float4* dst = reinterpret_cast<float4*>(out + (size_t)pix0 * 16);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t qi = tid + i * PWX_THREADS;               // float4 index inside the tile
+    for (int i = 0; i < 4 / NS; ++i) {
+      const uint32_t qi = tid + i * THR;                       // float4 index inside the tile
       const uint32_t px = qi >> 2, j = qi & 3;
       if (px < npx) dst[qi] = *reinterpret_cast<const float4*>(so + px * PWX_OROW + 4 * j);
     }
-    // the next iteration rewrites xs before its barrier and so only after it: no further barrier needed here
+    __syncthreads();                                           // so is xs: the next tile's copies wait for these reads
+    // the staged outputs overlay the first PWX_T * PWX_OROW floats of the x stage, zero-pad columns included: re-zero
+    // those (rows beyond M of a partial tile may hold anything: their results are never stored)
+    const int npad = K4 * 4 - p.kpad0;
+    if (npad > 0) {
+      constexpr int DIRTY = (PWX_T * PWX_OROW + KROW - 1) / KROW;
+      for (int i = tid; i < DIRTY * npad; i += THR) xs[(i / npad) * KROW + p.kpad0 + i % npad] = 0.f;
+    }
   }
 }
 
@@ -342,8 +357,8 @@ static bool pwx_build(const GConvK& k, bool for_wgrad, PwxParams* p, int* kd_pad
   return true;
 }
 
-static size_t pwx_fwd_smem(const PwxParams& p) {
-  return ((size_t)PWX_T * p.krow + (size_t)PWX_T * PWX_OROW) * sizeof(float);
+static size_t pwx_fwd_smem(const PwxParams& p) {       // the output stage aliases the x stage (krow >= PWX_OROW)
+  return (size_t)PWX_T * (p.krow > PWX_OROW ? p.krow : PWX_OROW) * sizeof(float);
 }
 static size_t pwx_wgrad_smem(const PwxParams& p) {
   const size_t stage = ((size_t)PWX_T * p.krow + (size_t)PWX_T * 32) * sizeof(float);
@@ -364,18 +379,19 @@ bool pwx_fwd_applicable(const GConvK& k, float beta, const float* mask_y, const 
   return pwx_build(k, false, &p, nullptr, nullptr, nullptr) && pwx_fwd_smem(p) <= PWX_SMEM_MAX;
 }
 
-template <int K4>
+template <int K4, int NS>
 static int pwx_fwd_launch(const PwxParams& p, const float* bias, int act, float* out, size_t smem, cudaStream_t st) {
   int dev = 0;
   cudaGetDevice(&dev);
   static bool attr_set[64] = {false};
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(pwx_fwd_kernel<K4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PWX_SMEM_MAX);
+    cudaError_t e = cudaFuncSetAttribute(pwx_fwd_kernel<K4, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PWX_SMEM_MAX);
     if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  const unsigned grid = p.ntiles < 148u * PWX_CTAS_PER_SM ? p.ntiles : 148u * PWX_CTAS_PER_SM;
-  pwx_fwd_kernel<K4><<<grid, PWX_THREADS, smem, st>>>(p, bias, act, out);
+  const unsigned per_sm = NS == 1 ? (K4 <= 16 ? 6u : (K4 <= 24 ? 4u : 3u)) : (K4 <= 16 ? 4u : 3u);
+  const unsigned grid = p.ntiles < 148u * per_sm ? p.ntiles : 148u * per_sm;
+  pwx_fwd_kernel<K4, NS><<<grid, PWX_THREADS * NS, smem, st>>>(p, bias, act, out);
   NLT_CUDA_LAUNCH_CHECK("pwx_fwd_kernel");
   return NLT_OK;
 }
@@ -393,12 +409,17 @@ int launch_pwx_fwd(const GConvK& k, const float* bias, int act, float* out, cuda
   if (e == cudaSuccess)
     e = cudaMemcpyToSymbolAsync(pwx_cw, stage, (size_t)p.K4 * 2 * 16 * sizeof(float2), 0, cudaMemcpyDeviceToDevice, st);
   if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "pwx weight table: %s", cudaGetErrorString(e));
+  static int ns = -1;      // NLT_PWX_NS: threads per pixel (1 or 2, default 2)
+  if (ns < 0) { const char* e = getenv("NLT_PWX_NS"); ns = (e && e[0] == '1') ? 1 : 2; }
+#define PWX_GO(K4_) do { if (ns == 1) return pwx_fwd_launch<K4_, 1>(p, bias, act, out, smem, st); \
+                         return pwx_fwd_launch<K4_, 2>(p, bias, act, out, smem, st); } while (0)
   switch (p.K4) {
-    case 8: return pwx_fwd_launch<8>(p, bias, act, out, smem, st);
-    case 16: return pwx_fwd_launch<16>(p, bias, act, out, smem, st);
-    case 24: return pwx_fwd_launch<24>(p, bias, act, out, smem, st);
-    default: return pwx_fwd_launch<32>(p, bias, act, out, smem, st);
+    case 8: PWX_GO(8);
+    case 16: PWX_GO(16);
+    case 24: PWX_GO(24);
+    default: PWX_GO(32);
   }
+#undef PWX_GO
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -602,8 +623,23 @@ __global__ void pf_pack_w_kernel(const PfParams p, const float* __restrict__ w, 
   }
 }
 
-template <int K4, int NOUT, int TP>
-__global__ void __launch_bounds__(TP, (K4 * 4 + 4) * TP * 4 <= 36 * 1024 ? (NOUT == 16 ? 6 : 4) : 3)
+// NS threads share a pixel, each owning NOUT / NS outputs (the split is warp-uniform, so the constant-bank weights stay
+// uniform operands): twice the resident warps for the same tile, at the price of every x row being read NS times from
+// shared memory.  (ncu of the one-thread-per-pixel form, profiles/r2_q_ncu_full_*: 12 warps/SM, FMA pipe 40 % busy,
+// warps waiting on the LDS.128 of their row.)
+template <int K4, int NOUT, int TP, int NS>
+struct PfCfg {
+  static constexpr int THR = TP * NS;
+  static constexpr int NO = NOUT / NS;                         // outputs per thread
+  static constexpr int ROW = K4 * 4 + 4 > NOUT + 4 ? K4 * 4 + 4 : NOUT + 4;
+  static constexpr size_t SMEM = (size_t)TP * ROW * sizeof(float);
+  static constexpr int MB_S = (int)((220u * 1024u) / (SMEM + 1024));
+  static constexpr int MB_T = (NO <= 8 ? 1024 : (NO <= 16 ? 768 : 512)) / THR;
+  static constexpr int MB = MB_S < MB_T ? (MB_S < 1 ? 1 : MB_S) : (MB_T < 1 ? 1 : MB_T);
+};
+
+template <int K4, int NOUT, int TP, int NS>
+__global__ void __launch_bounds__(TP * NS, (PfCfg<K4, NOUT, TP, NS>::MB))
 pf_fwd_kernel(const PfParams p, const float* __restrict__ bias, const int act, float* __restrict__ out,
               const float beta, const float* __restrict__ mask_y, const int mask_act) {
   extern __shared__ __align__(16) float smem[];
@@ -611,7 +647,9 @@ pf_fwd_kernel(const PfParams p, const float* __restrict__ bias, const int act, f
   constexpr int OROW = NOUT + 4;
   float* xs = smem;
   float* so = smem;                                            // aliases xs
+  constexpr int THR = TP * NS, NO = NOUT / NS;
   const int tid = threadIdx.x;
+  const int px_t = tid % TP, half = tid / TP;                  // warp-uniform split index
   const uint32_t xs_u = pwx_smem_u32(xs);
 
   for (uint32_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
@@ -626,7 +664,7 @@ pf_fwd_kernel(const PfParams p, const float* __restrict__ bias, const int act, f
       for (int dy = 0; dy < 2; ++dy) {
         const float4* src = reinterpret_cast<const float4*>(p.seg_ptr[s] + ((size_t)(2 * orow + dy) * p.Win + 2 * x0) * C);
         const uint32_t col = p.seg_col[s] + dy * 2 * C;
-        for (int i = tid; i < n4; i += TP) {
+        for (int i = tid; i < n4; i += THR) {
           const uint32_t px = (uint32_t)i >> l, j = (uint32_t)i & ((1u << l) - 1u);
           cp_async16(xs_u + (px * KROW + col + 4 * j) * 4, src + i);
         }
@@ -636,29 +674,30 @@ pf_fwd_kernel(const PfParams p, const float* __restrict__ bias, const int act, f
     cp_async_wait<0>();
     __syncthreads();
 
-    float2 acc[NOUT];
+    float2 acc[NO];
 #pragma unroll
-    for (int n = 0; n < NOUT; ++n) acc[n] = make_float2(0.f, 0.f);
-    const float4* xrow = reinterpret_cast<const float4*>(xs + tid * KROW);
+    for (int n = 0; n < NO; ++n) acc[n] = make_float2(0.f, 0.f);
+    const float4* xrow = reinterpret_cast<const float4*>(xs + px_t * KROW);
+    const float2* cw = pwx_cw + half * NO;
 #pragma unroll
     for (int q = 0; q < K4; ++q) {
       const float4 xv = xrow[q];
       const float2 xa = make_float2(xv.x, xv.y), xb = make_float2(xv.z, xv.w);
 #pragma unroll
-      for (int n = 0; n < NOUT; ++n) {
-        acc[n] = __ffma2_rn(xa, pwx_cw[(2 * q) * NOUT + n], acc[n]);
-        acc[n] = __ffma2_rn(xb, pwx_cw[(2 * q + 1) * NOUT + n], acc[n]);
+      for (int n = 0; n < NO; ++n) {
+        acc[n] = __ffma2_rn(xa, cw[(2 * q) * NOUT + n], acc[n]);
+        acc[n] = __ffma2_rn(xb, cw[(2 * q + 1) * NOUT + n], acc[n]);
       }
     }
     __syncthreads();                                           // every row of xs has been read
-    float4* srow = reinterpret_cast<float4*>(so + tid * OROW);
+    float4* srow = reinterpret_cast<float4*>(so + px_t * OROW + half * NO);
 #pragma unroll
-    for (int j = 0; j < NOUT / 4; ++j) {
+    for (int j = 0; j < NO / 4; ++j) {
       float o[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int n = 4 * j + e;
-        o[e] = act_fwd(acc[n].x + acc[n].y + (bias ? __ldg(bias + n) : 0.f), act);
+        o[e] = act_fwd(acc[n].x + acc[n].y + (bias ? __ldg(bias + half * NO + n) : 0.f), act);
       }
       srow[j] = make_float4(o[0], o[1], o[2], o[3]);
     }
@@ -666,20 +705,21 @@ pf_fwd_kernel(const PfParams p, const float* __restrict__ bias, const int act, f
     const size_t o4 = ((size_t)orow * p.Wout + x0) * (NOUT / 4);
     float4* dst = reinterpret_cast<float4*>(out) + o4;
     constexpr int Q = NOUT / 4;
+    constexpr int QT = Q / NS;                                 // float4 per thread: TP * Q over THR threads
     // input-gradient use: + beta * (what the buffer holds), * activation derivative of the source (from its output y)
-    constexpr int CH = Q < 4 ? Q : 4;                          // float4 in flight per thread
+    constexpr int CH = QT < 4 ? QT : 4;                        // float4 in flight per thread
 #pragma unroll
-    for (int i0 = 0; i0 < Q; i0 += CH) {
+    for (int i0 = 0; i0 < QT; i0 += CH) {
       float4 oldv[CH], yv[CH];
 #pragma unroll
       for (int i = 0; i < CH; ++i) {
-        const uint32_t qi = tid + (i0 + i) * TP;
+        const uint32_t qi = tid + (i0 + i) * THR;
         if (beta != 0.f) oldv[i] = dst[qi];
         if (mask_y != nullptr) yv[i] = __ldg(reinterpret_cast<const float4*>(mask_y) + o4 + qi);
       }
 #pragma unroll
       for (int i = 0; i < CH; ++i) {
-        const uint32_t qi = tid + (i0 + i) * TP;
+        const uint32_t qi = tid + (i0 + i) * THR;
         float4 v = *reinterpret_cast<const float4*>(so + (qi / Q) * OROW + 4 * (qi % Q));
         if (beta != 0.f) { v.x += beta * oldv[i].x; v.y += beta * oldv[i].y; v.z += beta * oldv[i].z; v.w += beta * oldv[i].w; }
         if (mask_y != nullptr) {
@@ -733,21 +773,22 @@ bool pf_fwd_applicable(const GConvK& k, const float* mask_y, const float* out) {
   return aligned16(out) && (mask_y == nullptr || aligned16(mask_y)) && pf_build(k, &p, &tp);
 }
 
-template <int K4, int NOUT, int TP>
+template <int K4, int NOUT, int TP, int NS>
 static int pf_launch(const PfParams& p, const float* bias, int act, float* out, float beta, const float* mask_y,
                      int mask_act, cudaStream_t st) {
-  constexpr size_t smem = (size_t)TP * (K4 * 4 + 4 > NOUT + 4 ? K4 * 4 + 4 : NOUT + 4) * sizeof(float);
-  constexpr unsigned per_sm = smem <= 36 * 1024 ? (NOUT == 16 ? 6u : 4u) : 3u;
+  using Cfg = PfCfg<K4, NOUT, TP, NS>;
+  constexpr size_t smem = Cfg::SMEM;
+  constexpr unsigned per_sm = (unsigned)Cfg::MB;
   int dev = 0;
   cudaGetDevice(&dev);
   static bool attr_set[64] = {false};
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(pf_fwd_kernel<K4, NOUT, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(pf_fwd_kernel<K4, NOUT, TP, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const unsigned grid = p.ntiles < 148u * per_sm ? p.ntiles : 148u * per_sm;
-  pf_fwd_kernel<K4, NOUT, TP><<<grid, TP, smem, st>>>(p, bias, act, out, beta, mask_y, mask_act);
+  pf_fwd_kernel<K4, NOUT, TP, NS><<<grid, TP * NS, smem, st>>>(p, bias, act, out, beta, mask_y, mask_act);
   NLT_CUDA_LAUNCH_CHECK("pf_fwd_kernel");
   return NLT_OK;
 }
@@ -765,7 +806,11 @@ int launch_pf_fwd(const GConvK& k, const float* bias, int act, float beta, const
   if (e == cudaSuccess)
     e = cudaMemcpyToSymbolAsync(pwx_cw, stage, (size_t)(p.K / 2) * k.Cout * sizeof(float2), 0, cudaMemcpyDeviceToDevice, st);
   if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "pwx weight table: %s", cudaGetErrorString(e));
-#define PF_GO(K4_, N_, TP_) return pf_launch<K4_, N_, TP_>(p, bias, act, out, beta, mask_y, mask_act, st)
+  static int ns = -1;      // NLT_PF_NS: threads per pixel (1 or 2, default 2)
+  if (ns < 0) { const char* e = getenv("NLT_PF_NS"); ns = (e && e[0] == '1') ? 1 : 2; }
+#define PF_GO(K4_, N_, TP_) \
+  do { if (ns == 1) return pf_launch<K4_, N_, TP_, 1>(p, bias, act, out, beta, mask_y, mask_act, st); \
+       return pf_launch<K4_, N_, TP_, 2>(p, bias, act, out, beta, mask_y, mask_act, st); } while (0)
   if (p.K == 32) { if (k.Cout == 16) PF_GO(8, 16, 128); PF_GO(8, 32, 128); }
   if (p.K == 64) { if (k.Cout == 16) PF_GO(16, 16, 128); PF_GO(16, 32, 128); }
   PF_GO(32, 16, 64);
