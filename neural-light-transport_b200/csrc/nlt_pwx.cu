@@ -122,6 +122,40 @@ __global__ void pwx_pack_w_kernel(const PwxParams p, const float* __restrict__ w
   }
 }
 
+// K4 x NO FFMA2 block of one thread: x row from shared memory, weights [pair][NOUT] from the constant bank at the
+// COMPILE-TIME column offset H * NO (a thread-derived offset, even a warp-uniform one, turns the LDCU operands into
+// per-thread LDC loads: measured 2.7x slower, profiles/r2_t_*)
+template <int K4, int NOUT, int NO, int H>
+__device__ __forceinline__ void pwx_row_mac(const float4* __restrict__ xrow, float2 (&acc)[NO]) {
+#pragma unroll
+  for (int n = 0; n < NO; ++n) acc[n] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < K4; ++q) {
+    const float4 xv = xrow[q];
+    const float2 xa = make_float2(xv.x, xv.y), xb = make_float2(xv.z, xv.w);
+#pragma unroll
+    for (int n = 0; n < NO; ++n) {
+      acc[n] = __ffma2_rn(xa, pwx_cw[(2 * q) * NOUT + H * NO + n], acc[n]);
+      acc[n] = __ffma2_rn(xb, pwx_cw[(2 * q + 1) * NOUT + H * NO + n], acc[n]);
+    }
+  }
+}
+
+template <int NO>
+__device__ __forceinline__ void pwx_row_out(const float2 (&acc)[NO], const float* __restrict__ bias, const int act,
+                                            float* __restrict__ dst) {
+#pragma unroll
+  for (int j = 0; j < NO / 4; ++j) {
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int n = 4 * j + e;
+      o[e] = act_fwd(acc[n].x + acc[n].y + (bias ? __ldg(bias + n) : 0.f), act);
+    }
+    reinterpret_cast<float4*>(dst)[j] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // NS threads per pixel, each owning 16 / NS outputs (warp-uniform split: the constant-bank weights stay uniform
 // operands); the output stage aliases the x stage, so that the CTA needs 35 KB at K = 64 and 4 CTAs x 8 warps fit.
 // One thread per pixel at 45 KB (the round-2 form until profiles/r2_q_*): 14 resident warps, FMA pipe 51 % busy.
@@ -145,33 +179,12 @@ pwx_fwd_kernel(const PwxParams p, const float* __restrict__ bias, const int act,
     cp_async_wait<0>();
     __syncthreads();                                           // tile t has landed for every thread
 
-    float2 acc[NO];
-#pragma unroll
-    for (int n = 0; n < NO; ++n) acc[n] = make_float2(0.f, 0.f);
     const float4* xrow = reinterpret_cast<const float4*>(xs + px_t * KROW);
-    const float2* cw = pwx_cw + half * NO;
-#pragma unroll
-    for (int q = 0; q < K4; ++q) {
-      const float4 xv = xrow[q];
-      const float2 xa = make_float2(xv.x, xv.y), xb = make_float2(xv.z, xv.w);
-#pragma unroll
-      for (int n = 0; n < NO; ++n) {
-        acc[n] = __ffma2_rn(xa, cw[(2 * q) * 16 + n], acc[n]);
-        acc[n] = __ffma2_rn(xb, cw[(2 * q + 1) * 16 + n], acc[n]);
-      }
-    }
+    float2 acc[NO];
+    if (NS == 1 || half == 0) pwx_row_mac<K4, 16, NO, 0>(xrow, acc);                      // warp-uniform branch
+    else pwx_row_mac<K4, 16, NO, NS - 1>(xrow, acc);
     __syncthreads();                                           // every row of xs has been read
-    float4* srow = reinterpret_cast<float4*>(so + px_t * PWX_OROW + half * NO);
-#pragma unroll
-    for (int j = 0; j < NO / 4; ++j) {
-      float o[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int n = 4 * j + e;
-        o[e] = act_fwd(acc[n].x + acc[n].y + (bias ? __ldg(bias + half * NO + n) : 0.f), act);
-      }
-      srow[j] = make_float4(o[0], o[1], o[2], o[3]);
-    }
+    pwx_row_out<NO>(acc, bias ? bias + half * NO : nullptr, act, so + px_t * PWX_OROW + half * NO);
     __syncthreads();                                           // outputs staged
     // coalesced 16-byte stores: the tile's outputs are one contiguous run of PWX_T*16 floats
     const uint32_t pix0 = t * PWX_T;
@@ -674,33 +687,12 @@ pf_fwd_kernel(const PfParams p, const float* __restrict__ bias, const int act, f
     cp_async_wait<0>();
     __syncthreads();
 
-    float2 acc[NO];
-#pragma unroll
-    for (int n = 0; n < NO; ++n) acc[n] = make_float2(0.f, 0.f);
     const float4* xrow = reinterpret_cast<const float4*>(xs + px_t * KROW);
-    const float2* cw = pwx_cw + half * NO;
-#pragma unroll
-    for (int q = 0; q < K4; ++q) {
-      const float4 xv = xrow[q];
-      const float2 xa = make_float2(xv.x, xv.y), xb = make_float2(xv.z, xv.w);
-#pragma unroll
-      for (int n = 0; n < NO; ++n) {
-        acc[n] = __ffma2_rn(xa, cw[(2 * q) * NOUT + n], acc[n]);
-        acc[n] = __ffma2_rn(xb, cw[(2 * q + 1) * NOUT + n], acc[n]);
-      }
-    }
+    float2 acc[NO];
+    if (NS == 1 || half == 0) pwx_row_mac<K4, NOUT, NO, 0>(xrow, acc);                    // warp-uniform branch
+    else pwx_row_mac<K4, NOUT, NO, NS - 1>(xrow, acc);
     __syncthreads();                                           // every row of xs has been read
-    float4* srow = reinterpret_cast<float4*>(so + px_t * OROW + half * NO);
-#pragma unroll
-    for (int j = 0; j < NO / 4; ++j) {
-      float o[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int n = 4 * j + e;
-        o[e] = act_fwd(acc[n].x + acc[n].y + (bias ? __ldg(bias + half * NO + n) : 0.f), act);
-      }
-      srow[j] = make_float4(o[0], o[1], o[2], o[3]);
-    }
+    pwx_row_out<NO>(acc, bias ? bias + half * NO : nullptr, act, so + px_t * OROW + half * NO);
     __syncthreads();
     const size_t o4 = ((size_t)orow * p.Wout + x0) * (NOUT / 4);
     float4* dst = reinterpret_cast<float4*>(out) + o4;

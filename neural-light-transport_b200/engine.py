@@ -217,9 +217,12 @@ WGRAD_HOOK = None
 FWD_TAP = None
 
 
-# NLT_PACK_AHEAD (default 1): weight planes of the tensor-core layers are packed on a stream that hangs off the START of
-# the step (weights are final there), not in front of each layer's kernel on the main stream
-PACK_AHEAD = os.environ.get('NLT_PACK_AHEAD', '1') != '0'
+# NLT_PACK_AHEAD (default 0): weight planes of the tensor-core layers are packed on a stream that hangs off the START
+# of the step (weights are final there) instead of in front of each layer's kernel on the main stream.  Measured
+# (profiles/r2_s_*, r2_t_*): inside the captured CUDA graph the ~60 pack nodes do not start earlier than before (14.83
+# vs 14.74 ms per step), and eager launches pay the extra stream switches on the host -- so the switch stays off; the
+# C-ABI entry points and the scheduling-invariance test remain.
+PACK_AHEAD = os.environ.get('NLT_PACK_AHEAD', '0') == '1'
 _PACK = {}                   # device index -> pack stream
 _STEP_ROOT = {}              # device index -> [event recorded on the main stream at step begin, forked?]
 
