@@ -693,6 +693,8 @@ int nlt_set_option(const char* name, int value) {
   if (strcmp(name, "wgrad_rows") == 0) { nlt::g_opt_wgrad_rows = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "tcs") == 0) { nlt::g_opt_tcs = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "pwx") == 0) { nlt::g_opt_pwx = value ? 1 : 0; return NLT_OK; }
+  if (strcmp(name, "pf_ns") == 0) { nlt::g_opt_pf_ns = value == 2 ? 2 : 1; return NLT_OK; }
+  if (strcmp(name, "pwx_ns") == 0) { nlt::g_opt_pwx_ns = value == 2 ? 2 : 1; return NLT_OK; }
   if (strcmp(name, "pf") == 0) { g_opt_pf = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "wop") == 0) { nlt::g_opt_wop = value; return NLT_OK; }
   if (strcmp(name, "tiny") == 0) { nlt::g_opt_tiny = value ? 1 : 0; return NLT_OK; }
@@ -849,7 +851,8 @@ int64_t nlt_gconv_wgrad_workspace_bytes(const nlt_gconv_desc* d) {
   GConvK ph[16];
   int np = 0;
   if (build_phases(d, ph, &np, /*allow_d2s=*/true) != NLT_OK) return -1;
-  if (np == 1 && ph[0].d2s && !wop_wgrad_applicable(ph[0], nullptr) && !wgrad_small_applicable(ph[0]) &&
+  if (np == 1 && ph[0].d2s && !pwx_wgrad_applicable(ph[0], nullptr) && !wop_wgrad_applicable(ph[0], nullptr) &&
+      !wgrad_small_applicable(ph[0]) &&
       !use_tc_wgrad(ph[0]) && build_phases(d, ph, &np, false) != NLT_OK) return -1;
   size_t mx = 0;
   for (int i = 0; i < np; ++i) {
@@ -873,7 +876,8 @@ int nlt_gconv_wgrad(const nlt_gconv_desc* d, const float* G, float* dW, float* d
   if (rc != NLT_OK) return rc;
   // a k == stride transposed conv keeps its one-pass depth-to-space form when a kernel takes it (the warp-stream
   // kernel for narrow tiles, the tcgen05 kernel from K_d = 128 up); otherwise s*s phases
-  if (np == 1 && ph[0].d2s && !wop_wgrad_applicable(ph[0], G) && !wgrad_small_applicable(ph[0]) && !use_tc_wgrad(ph[0]))
+  if (np == 1 && ph[0].d2s && !pwx_wgrad_applicable(ph[0], G) && !wop_wgrad_applicable(ph[0], G) &&
+      !wgrad_small_applicable(ph[0]) && !use_tc_wgrad(ph[0]))
     rc = build_phases(d, ph, &np, false);
   if (rc != NLT_OK) return rc;
   NLT_CHECK_ARG(G != nullptr && dW != nullptr && workspace != nullptr, "null pointer");

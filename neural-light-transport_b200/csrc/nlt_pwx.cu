@@ -213,7 +213,7 @@ pwx_fwd_kernel(const PwxParams p, const float* __restrict__ bias, const int act,
 template <int NG>                  // float4 channel groups per lane (K4 <= 8*NG)
 __global__ void __launch_bounds__(PWX_THREADS, PWX_CTAS_PER_SM)
 pwx_wgrad_kernel(const PwxParams p, const float* __restrict__ G, float* __restrict__ ws, const int kd_pad,
-                 const int bias_row) {
+                 const int bias_row, const int ld, const int coff, const int gmode, const int Win, const int gsub) {
   extern __shared__ __align__(16) float smem[];
   float* xs = smem;
   float* gs = xs + PWX_T * p.krow;                             // [PWX_T][32]: dz duplicated (d, d)
@@ -240,18 +240,30 @@ pwx_wgrad_kernel(const PwxParams p, const float* __restrict__ G, float* __restri
       const uint32_t pix0 = t * PWX_T;
       const uint32_t nq = min((uint32_t)PWX_T, p.M - pix0) * 4;
       const float4* src = reinterpret_cast<const float4*>(G + (size_t)pix0 * 16);
-      float4 r[4];
+      // up-convs (gmode 1 / 2): the tile is 128 pixels of input row r; its 16 gradient columns are
+      //   gmode 1 (4 output channels): the pixel's whole 2x2 block, float4 (dy, dx) at G4[(2r + dy) * 2W + 2x + dx]
+      //   gmode 2 (8 output channels), pass gsub = dy: the 16 contiguous floats of pixels (2x, 2x + 1) of row 2r + dy
+      uint32_t r = 0, x0 = 0;
+      if (gmode != 0) { r = pix0 / (uint32_t)Win; x0 = pix0 - r * (uint32_t)Win; }
+      if (gmode == 2) src = reinterpret_cast<const float4*>(G + ((size_t)(2 * r + gsub) * (2 * (size_t)Win) + 2 * x0) * 8);
+      const float4* g4 = reinterpret_cast<const float4*>(G);
+      float4 r4[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const uint32_t qi = tid + i * PWX_THREADS;
-        r[i] = qi < nq ? __ldg(src + qi) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gmode == 1) {
+          const uint32_t px = qi >> 2, dy = (qi >> 1) & 1, dx = qi & 1;
+          r4[i] = __ldg(g4 + (size_t)(2 * r + dy) * (2 * (size_t)Win) + 2 * (x0 + px) + dx);
+        } else {
+          r4[i] = qi < nq ? __ldg(src + qi) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const uint32_t qi = tid + i * PWX_THREADS;             // pixel = qi / 4, output quad = qi % 4
         float4* d = reinterpret_cast<float4*>(gs + (qi >> 2) * 32 + (qi & 3) * 8);
-        d[0] = make_float4(r[i].x, r[i].x, r[i].y, r[i].y);
-        d[1] = make_float4(r[i].z, r[i].z, r[i].w, r[i].w);
+        d[0] = make_float4(r4[i].x, r4[i].x, r4[i].y, r4[i].y);
+        d[1] = make_float4(r4[i].z, r4[i].z, r4[i].w, r4[i].w);
       }
     }
     cp_async_wait<0>();
@@ -295,20 +307,20 @@ pwx_wgrad_kernel(const PwxParams p, const float* __restrict__ G, float* __restri
   float* redb = red + (size_t)PWX_WARPS * ncol * 16;           // [warps][16] bias partials
   if (cg == 0) *reinterpret_cast<float4*>(redb + warp * 16 + ng * 4) = make_float4(bs[0], bs[1], bs[2], bs[3]);
   __syncthreads();
-  float* dst = ws + (size_t)blockIdx.x * kd_pad * 16;
+  float* dst = ws + (size_t)blockIdx.x * kd_pad * ld + coff;
   for (int i = tid; i < ncol * 16; i += PWX_THREADS) {
     const int col = i >> 4, n = i & 15;
     float s = 0.f;
 #pragma unroll
     for (int wv = 0; wv < PWX_WARPS; ++wv) s += red[((size_t)wv * ncol + col) * 16 + n];
     const int row = col < PWX_KMAX ? p.col_row[col] : -1;
-    if (row >= 0) dst[(size_t)row * 16 + n] = s;
+    if (row >= 0) dst[(size_t)row * ld + n] = s;
   }
   if (tid < 16) {
     float s = 0.f;
 #pragma unroll
     for (int wv = 0; wv < PWX_WARPS; ++wv) s += redb[wv * 16 + tid];
-    dst[(size_t)bias_row * 16 + tid] = s;
+    dst[(size_t)bias_row * ld + tid] = s;
   }
 }
 
@@ -380,6 +392,7 @@ static size_t pwx_wgrad_smem(const PwxParams& p) {
 }
 constexpr size_t PWX_SMEM_MAX = 56 * 1024;      // four CTAs per SM
 
+int g_opt_pf_ns = -1, g_opt_pwx_ns = -1;     // options "pf_ns" / "pwx_ns": threads per pixel of the forward kernels
 int g_opt_pwx = -1;     // option "pwx" / NLT_PWX: 1 (default) the kernels of this file, 0 the general routes
 static bool pwx_enabled() {
   if (g_opt_pwx < 0) { const char* e = getenv("NLT_PWX"); g_opt_pwx = (e && e[0] == '0') ? 0 : 1; }
@@ -422,8 +435,9 @@ int launch_pwx_fwd(const GConvK& k, const float* bias, int act, float* out, cuda
   if (e == cudaSuccess)
     e = cudaMemcpyToSymbolAsync(pwx_cw, stage, (size_t)p.K4 * 2 * 16 * sizeof(float2), 0, cudaMemcpyDeviceToDevice, st);
   if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "pwx weight table: %s", cudaGetErrorString(e));
-  static int ns = -1;      // NLT_PWX_NS: threads per pixel (1 or 2, default 2)
-  if (ns < 0) { const char* e = getenv("NLT_PWX_NS"); ns = (e && e[0] == '1') ? 1 : 2; }
+  // NLT_PWX_NS: threads per pixel (default 1; 2 = the output split, not faster: profiles/r2_u_*)
+  if (g_opt_pwx_ns < 0) { const char* e = getenv("NLT_PWX_NS"); g_opt_pwx_ns = (e && e[0] == '2') ? 2 : 1; }
+  const int ns = g_opt_pwx_ns;
 #define PWX_GO(K4_) do { if (ns == 1) return pwx_fwd_launch<K4_, 1>(p, bias, act, out, smem, st); \
                          return pwx_fwd_launch<K4_, 2>(p, bias, act, out, smem, st); } while (0)
   switch (p.K4) {
@@ -798,8 +812,9 @@ int launch_pf_fwd(const GConvK& k, const float* bias, int act, float beta, const
   if (e == cudaSuccess)
     e = cudaMemcpyToSymbolAsync(pwx_cw, stage, (size_t)(p.K / 2) * k.Cout * sizeof(float2), 0, cudaMemcpyDeviceToDevice, st);
   if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "pwx weight table: %s", cudaGetErrorString(e));
-  static int ns = -1;      // NLT_PF_NS: threads per pixel (1 or 2, default 2)
-  if (ns < 0) { const char* e = getenv("NLT_PF_NS"); ns = (e && e[0] == '1') ? 1 : 2; }
+  // NLT_PF_NS: threads per pixel (default 1; 2 = the output split, measured 0.1-0.2 ms per step slower: profiles/r2_u_*)
+  if (g_opt_pf_ns < 0) { const char* e = getenv("NLT_PF_NS"); g_opt_pf_ns = (e && e[0] == '2') ? 2 : 1; }
+  const int ns = g_opt_pf_ns;
 #define PF_GO(K4_, N_, TP_) \
   do { if (ns == 1) return pf_launch<K4_, N_, TP_, 1>(p, bias, act, out, beta, mask_y, mask_act, st); \
        return pf_launch<K4_, N_, TP_, 2>(p, bias, act, out, beta, mask_y, mask_act, st); } while (0)
@@ -809,8 +824,21 @@ int launch_pf_fwd(const GConvK& k, const float* bias, int act, float beta, const
 #undef PF_GO
 }
 
+// up-convs 2x2 / stride 2 into 4 or 8 channels in their depth-to-space form (levels 11-12): the same outer products with
+// the 16 gradient columns gathered from the 2x2 output block (one launch for 4 channels, one per output row for 8)
+static bool pwx_wgrad_d2s_ok(const GConvK& k) {
+  if (!k.d2s || k.d2s_s != 2 || k.M == 0 || (k.cout_true != 4 && k.cout_true != 8) || k.Cout != 4 * k.cout_true) return false;
+  if (k.ay.nt != k.Hin || k.ax.nt != k.Win || k.Hout != 2 * k.Hin || k.Wout != 2 * k.Win || k.Win % PWX_T != 0) return false;
+  int K = 0;
+  for (int s = 0; s < k.nseg; ++s) {
+    if (k.seg[s].sub != nullptr || k.seg[s].bcast) return false;
+    K += k.seg[s].C;
+  }
+  return K > 16 && K <= PWX_KMAX - 8 && k.M >= 4 * PWX_T;
+}
+
 bool pwx_wgrad_applicable(const GConvK& k, const float* G) {
-  if (!pwx_enabled() || !pwx_shape_ok(k) || (G != nullptr && !aligned16(G))) return false;
+  if (!pwx_enabled() || !(pwx_shape_ok(k) || pwx_wgrad_d2s_ok(k)) || (G != nullptr && !aligned16(G))) return false;
   PwxParams p;
   return pwx_build(k, true, &p, nullptr, nullptr, nullptr) && pwx_wgrad_smem(p) <= PWX_SMEM_MAX;
 }
@@ -823,11 +851,12 @@ size_t pwx_wgrad_ws_floats(const GConvK& k) {
   PwxParams p;
   int kd_pad = 0;
   if (!pwx_build(k, true, &p, &kd_pad, nullptr, nullptr)) return 0;
-  return (size_t)pwx_wgrad_grid(p) * kd_pad * 16;
+  return (size_t)pwx_wgrad_grid(p) * kd_pad * (k.d2s ? k.Cout : 16);
 }
 
 template <int NG>
-static int pwx_wgrad_launch(const PwxParams& p, const float* G, float* ws, int kd_pad, int bias_row, cudaStream_t st) {
+static int pwx_wgrad_launch(const PwxParams& p, const float* G, float* ws, int kd_pad, int bias_row, cudaStream_t st,
+                            int ld = 16, int coff = 0, int gmode = 0, int Win = 0, int gsub = 0) {
   int dev = 0;
   cudaGetDevice(&dev);
   static bool attr_set[64] = {false};
@@ -836,7 +865,8 @@ static int pwx_wgrad_launch(const PwxParams& p, const float* G, float* ws, int k
     if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set[dev] = true;
   }
-  pwx_wgrad_kernel<NG><<<pwx_wgrad_grid(p), PWX_THREADS, pwx_wgrad_smem(p), st>>>(p, G, ws, kd_pad, bias_row);
+  pwx_wgrad_kernel<NG><<<pwx_wgrad_grid(p), PWX_THREADS, pwx_wgrad_smem(p), st>>>(p, G, ws, kd_pad, bias_row, ld, coff, gmode,
+                                                                                  Win, gsub);
   NLT_CUDA_LAUNCH_CHECK("pwx_wgrad_kernel");
   return NLT_OK;
 }
@@ -847,14 +877,21 @@ int launch_pwx_wgrad(const GConvK& k, const float* G, float* ws, WgradK* w, size
   if (!pwx_build(k, true, &p, &kd_pad, &bias_row, &GS)) return set_err(NLT_ERR_INVALID, "pwx_wgrad not applicable");
   // rows of pad channels inside a k-group are never read by the reduce stage, but the workspace may hold NaN
   // bit patterns from an earlier use: the reduce stage only touches (c + e < C) rows, so nothing to clear
-  w->g = k; w->GS = GS; w->KG = GS + 1; w->ld = 16; w->nsplit = (int)pwx_wgrad_grid(p); w->pix_per_split = 0;
+  w->g = k; w->GS = GS; w->KG = GS + 1; w->ld = k.d2s ? k.Cout : 16; w->nsplit = (int)pwx_wgrad_grid(p); w->pix_per_split = 0;
   *KD_pad = (size_t)kd_pad;
-  switch (p.K4 / 8) {
-    case 1: return pwx_wgrad_launch<1>(p, G, ws, kd_pad, bias_row, st);
-    case 2: return pwx_wgrad_launch<2>(p, G, ws, kd_pad, bias_row, st);
-    case 3: return pwx_wgrad_launch<3>(p, G, ws, kd_pad, bias_row, st);
-    default: return pwx_wgrad_launch<4>(p, G, ws, kd_pad, bias_row, st);
+  const int passes = k.d2s ? k.Cout / 16 : 1;
+  const int gmode = k.d2s ? (k.cout_true == 4 ? 1 : 2) : 0;
+  for (int ps = 0; ps < passes; ++ps) {
+    int rc;
+    switch (p.K4 / 8) {
+      case 1: rc = pwx_wgrad_launch<1>(p, G, ws, kd_pad, bias_row, st, w->ld, 16 * ps, gmode, k.Win, ps); break;
+      case 2: rc = pwx_wgrad_launch<2>(p, G, ws, kd_pad, bias_row, st, w->ld, 16 * ps, gmode, k.Win, ps); break;
+      case 3: rc = pwx_wgrad_launch<3>(p, G, ws, kd_pad, bias_row, st, w->ld, 16 * ps, gmode, k.Win, ps); break;
+      default: rc = pwx_wgrad_launch<4>(p, G, ws, kd_pad, bias_row, st, w->ld, 16 * ps, gmode, k.Win, ps); break;
+    }
+    if (rc != NLT_OK) return rc;
   }
+  return NLT_OK;
 }
 
 // =============================================================================================

@@ -178,6 +178,24 @@ def test_outer_product_wgrad_all_shapes(kind, k, s, H, W, segc, cout):
         nat.set_option('wop', int(os.environ.get('NLT_WOP', '1')))
 
 
+NS2_SHAPES = [g for g in GEOMS if g[6] in (16, 32) and g[4] >= 128 and (
+    (g[0] == 'conv' and g[1] == 1) or (g[1] == 2 and g[2] == 2))][:12] + [('conv', 1, 1, 32, 32, [64], 16)]
+
+
+@pytest.mark.parametrize('kind,k,s,H,W,segc,cout', NS2_SHAPES)
+def test_two_threads_per_pixel_forward_kernels(kind, k, s, H, W, segc, cout):
+    """The pointwise / staged-patch forward kernels also exist with two threads per pixel (options pwx_ns / pf_ns = 2,
+    off by default: not faster, profiles/r2_u_*): same oracle check."""
+    import nlt_native as nat
+    nat.set_option('pwx_ns', 2)
+    nat.set_option('pf_ns', 2)
+    try:
+        test_gconv_forward_backward(kind, k, s, H, W, segc, cout, 'leakyrelu')
+    finally:
+        nat.set_option('pwx_ns', 1)
+        nat.set_option('pf_ns', 1)
+
+
 TC_SHAPES = [g for g in GEOMS if all(c % 16 == 0 for c in g[5]) and g[6] % 16 == 0 and g[3] * g[4] >= 256]
 
 
