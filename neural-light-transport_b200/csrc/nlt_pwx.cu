@@ -391,6 +391,7 @@ static size_t pwx_wgrad_smem(const PwxParams& p) {
   return stage > red ? stage : red;
 }
 constexpr size_t PWX_SMEM_MAX = 56 * 1024;      // four CTAs per SM
+constexpr size_t PWX_WGRAD_SMEM_MAX = 72 * 1024; // three CTAs per SM (K = 65 .. 96: the level-11 up-conv)
 
 int g_opt_pf_ns = -1, g_opt_pwx_ns = -1;     // options "pf_ns" / "pwx_ns": threads per pixel of the forward kernels
 int g_opt_pwx = -1;     // option "pwx" / NLT_PWX: 1 (default) the kernels of this file, 0 the general routes
@@ -840,11 +841,13 @@ static bool pwx_wgrad_d2s_ok(const GConvK& k) {
 bool pwx_wgrad_applicable(const GConvK& k, const float* G) {
   if (!pwx_enabled() || !(pwx_shape_ok(k) || pwx_wgrad_d2s_ok(k)) || (G != nullptr && !aligned16(G))) return false;
   PwxParams p;
-  return pwx_build(k, true, &p, nullptr, nullptr, nullptr) && pwx_wgrad_smem(p) <= PWX_SMEM_MAX;
+  return pwx_build(k, true, &p, nullptr, nullptr, nullptr) && pwx_wgrad_smem(p) <= PWX_WGRAD_SMEM_MAX;
 }
 
+static size_t pwx_wgrad_smem(const PwxParams& p);
 static unsigned pwx_wgrad_grid(const PwxParams& p) {
-  return p.ntiles < 148u * PWX_CTAS_PER_SM ? p.ntiles : 148u * PWX_CTAS_PER_SM;
+  const unsigned per_sm = pwx_wgrad_smem(p) > PWX_SMEM_MAX ? 3u : (unsigned)PWX_CTAS_PER_SM;      // resident CTAs
+  return p.ntiles < 148u * per_sm ? p.ntiles : 148u * per_sm;
 }
 
 size_t pwx_wgrad_ws_floats(const GConvK& k) {
@@ -861,7 +864,7 @@ static int pwx_wgrad_launch(const PwxParams& p, const float* G, float* ws, int k
   cudaGetDevice(&dev);
   static bool attr_set[64] = {false};
   if (dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(pwx_wgrad_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PWX_SMEM_MAX);
+    cudaError_t e = cudaFuncSetAttribute(pwx_wgrad_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PWX_WGRAD_SMEM_MAX);
     if (e != cudaSuccess) return set_err(NLT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set[dev] = true;
   }

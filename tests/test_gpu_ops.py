@@ -119,6 +119,7 @@ GEOMS = [
     ('conv', 1, 1, 32, 32, [64], 16),
     ('conv', 1, 1, 24, 24, [20, 4], 16),
     ('conv', 1, 1, 40, 40, [3, 40, 1, 2], 16),
+    ('conv', 1, 1, 24, 40, [32, 40, 8], 16),    # K = 80: 24 float4 groups per row (forward at 51 KB, weight gradient at 67 KB)
 ]
 
 
@@ -605,11 +606,12 @@ def test_resize(shape, new):
     _close(dx, x64.grad, atol=1e-5)
 
 
-def test_l2_loss_and_grad():
+@pytest.mark.parametrize('hw', [(20, 24), (5, 7), (256, 192)])      # float4 path / scalar path (105 floats per sample) / many blocks
+def test_l2_loss_and_grad(hw):
     import losses
     dev = torch.device('cuda')
     torch.manual_seed(1)
-    pred, gt = torch.rand(3, 20, 24, 3), torch.rand(3, 20, 24, 3)
+    pred, gt = torch.rand(3, hw[0], hw[1], 3), torch.rand(3, hw[0], hw[1], 3)
     L = losses.L2()
     L.grad_scale = 0.25
     got = L(gt.to(dev), pred.to(dev), keep_batch=True)
