@@ -658,6 +658,11 @@ uint64_t nlt_launch_count(void) { return __atomic_load_n(&nlt::g_launches, __ATO
 uint64_t nlt_tc_launch_count(void) { return __atomic_load_n(&nlt::g_tc_launches, __ATOMIC_RELAXED); }
 
 static int g_opt_tc = -1, g_opt_tc_wgrad = -1;   // -1: take the environment default
+static int g_opt_pwd2s_first = -1;               // option "pwd2s_first" / NLT_PWD2S_FIRST (default 0)
+static bool pwd2s_first() {
+  if (g_opt_pwd2s_first < 0) { const char* e = getenv("NLT_PWD2S_FIRST"); g_opt_pwd2s_first = (e && e[0] == '1') ? 1 : 0; }
+  return g_opt_pwd2s_first == 1;
+}
 static int g_opt_pf = -1;                        // option "pf" / NLT_PF (default 1): staged-patch forward of nlt_pwx.cu
 static bool pf_enabled() {
   if (g_opt_pf < 0) { const char* e = getenv("NLT_PF"); g_opt_pf = (e && e[0] == '0') ? 0 : 1; }
@@ -693,6 +698,7 @@ int nlt_set_option(const char* name, int value) {
   if (strcmp(name, "wgrad_rows") == 0) { nlt::g_opt_wgrad_rows = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "tcs") == 0) { nlt::g_opt_tcs = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "pwx") == 0) { nlt::g_opt_pwx = value ? 1 : 0; return NLT_OK; }
+  if (strcmp(name, "pwd2s_first") == 0) { g_opt_pwd2s_first = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "pf_ns") == 0) { nlt::g_opt_pf_ns = value == 2 ? 2 : 1; return NLT_OK; }
   if (strcmp(name, "pwx_ns") == 0) { nlt::g_opt_pwx_ns = value == 2 ? 2 : 1; return NLT_OK; }
   if (strcmp(name, "pf") == 0) { g_opt_pf = value ? 1 : 0; return NLT_OK; }
@@ -721,6 +727,8 @@ static bool fwd_takes_tc(const GConvK* ph, int np, float beta, const float* mask
   if (tiny_stencil_applicable(ph[0], out, mask_y)) return false;
   if (pf_enabled() && pf_fwd_applicable(ph[0], mask_y, out)) return false;
   if (pwx_d2s_fwd_applicable(ph[0], beta, mask_y, out)) return false;
+  if (pwd2s_first() && ph[0].d2s && ph[0].nseg == 1 && ph[0].seg[0].C == 64 &&
+      pwd2s_applicable(ph[0], nullptr, 0, out, mask_y, nullptr)) return false;
   return tc_enabled() && tc_applicable(ph[0]);
 }
 
@@ -774,6 +782,11 @@ static int gconv_fwd_impl(const nlt_gconv_desc* d, const float* bias, int act, f
     return launch_pf_fwd(ph[0], bias, act, beta, mask_y, mask_act, out, st);
   // up-convs into 4 / 8 channels: depth-to-space pointwise kernel with constant-bank weights (nlt_pwx.cu)
   if (np == 1 && pwx_d2s_fwd_applicable(ph[0], beta, mask_y, out)) return launch_pwx_d2s_fwd(ph[0], bias, act, out, st);
+  // input gradients of the 2x2 / stride-2 convs into 32-channel sources with K = 64 (level 3): depth-to-space FFMA2
+  // kernel ahead of the tensor path (option "pwd2s_first" / NLT_PWD2S_FIRST)
+  if (!prepacked && np == 1 && ph[0].M > 0 && pwd2s_first() && ph[0].d2s && ph[0].nseg == 1 && ph[0].seg[0].C == 64 &&
+      pwd2s_applicable(ph[0], bias, act, out, mask_y, nullptr))
+    return launch_pwd2s(ph[0], beta, mask_y, mask_act, out, st, nullptr);
   if (prepacked)
     NLT_CHECK_ARG(fwd_takes_tc(ph, np, beta, mask_y, out) && workspace != nullptr &&
                   (int64_t)tc_workspace_bytes(ph[0]) <= workspace_bytes,

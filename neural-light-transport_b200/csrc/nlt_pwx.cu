@@ -18,6 +18,7 @@
 //             (d, d) so that x pairs (c, c+1) times a broadcast pair accumulate dW[c..c+1][n] in one FFMA2;
 //             one fp32 partial per CTA goes to the workspace in the k-group layout of WgradK, the fixed-order
 //             reduce kernel of nlt_gconv.cu finishes (deterministic).
+#include <type_traits>
 #include "nlt_common.cuh"
 
 namespace nlt {
@@ -980,19 +981,25 @@ pwd2s_kernel(const PwdParams p) {
     float2 acc[32];
 #pragma unroll
     for (int m = 0; m < 32; ++m) acc[m] = make_float2(0.f, 0.f);
-    const float2* cw = pwd_cw + (TPP == 1 ? 0 : half * 32);        // warp-uniform: a warp lies in one half
     const float4* xrow = reinterpret_cast<const float4*>(p.dz + ((size_t)t * TP + lp) * K);
+    // the tap-row half is warp-uniform, but only a COMPILE-TIME table offset keeps the weights uniform operands
+    // (LDCU -> FFMA2 ..., UR, ...); with `half * 32` as a run-time offset the compiler emitted per-thread LDC loads
+    auto mac = [&](auto hc) {
+      constexpr int H = decltype(hc)::value;
 #pragma unroll
-    for (int q = 0; q < K / 4; ++q) {
-      const float4 xq = PREFETCH ? xcur[q] : __ldg(xrow + q);
-      const float xs[4] = {xq.x, xq.y, xq.z, xq.w};
+      for (int q = 0; q < K / 4; ++q) {
+        const float4 xq = PREFETCH ? xcur[q] : __ldg(xrow + q);
+        const float xs[4] = {xq.x, xq.y, xq.z, xq.w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 xx = make_float2(xs[e], xs[e]);
+        for (int e = 0; e < 4; ++e) {
+          const float2 xx = make_float2(xs[e], xs[e]);
 #pragma unroll
-        for (int m = 0; m < 32; ++m) acc[m] = __ffma2_rn(xx, cw[(4 * q + e) * (NP / 2) + m], acc[m]);
+          for (int m = 0; m < 32; ++m) acc[m] = __ffma2_rn(xx, pwd_cw[(4 * q + e) * (NP / 2) + H * 32 + m], acc[m]);
+        }
       }
-    }
+    };
+    if (TPP == 1 || half == 0) mac(std::integral_constant<int, 0>{});
+    else mac(std::integral_constant<int, TPP - 1>{});
     if (PREFETCH && t + gridDim.x < p.ntiles)                      // next tile's gradient rows: in flight during the write phase
       load_x(t + gridDim.x, reinterpret_cast<float4(&)[K / 4]>(xcur));
     __syncthreads();                                               // the previous tile's staged values have been read
