@@ -168,6 +168,9 @@ extern int g_opt_pwx;
 extern int g_opt_pf_ns, g_opt_pwx_ns;
 extern int g_opt_tiny;
 extern int g_opt_wop;
+bool wopn_wgrad_applicable(const GConvK& k, const float* G);
+size_t wopn_wgrad_ws_floats(const GConvK& k);
+int launch_wopn_wgrad(const GConvK& k, const float* G, float* ws, WgradK* w, size_t* KD_pad, cudaStream_t st);
 bool wop_wgrad_applicable(const GConvK& k, const float* G);
 size_t wop_wgrad_ws_floats(const GConvK& k);
 int launch_wop_wgrad(const GConvK& k, const float* G, float* ws, WgradK* w, size_t* KD_pad, cudaStream_t st);

@@ -874,6 +874,7 @@ int64_t nlt_gconv_wgrad_workspace_bytes(const nlt_gconv_desc* d) {
     if (ph[i].M == 0) continue;
     size_t need = pwx_wgrad_applicable(ph[i], nullptr) ? pwx_wgrad_ws_floats(ph[i])
                   : wop_wgrad_applicable(ph[i], nullptr) ? wop_wgrad_ws_floats(ph[i])
+                  : wopn_wgrad_applicable(ph[i], nullptr) ? wopn_wgrad_ws_floats(ph[i])
                   : pws_wgrad_applicable(ph[i], nullptr) ? pws_wgrad_ws_floats(ph[i])
                   : use_tc_wgrad(ph[i]) ? tc_wgrad_ws_floats(ph[i])
                   : wgrad_tpp_applicable(ph[i]) ? wgrad_tpp_ws_floats(ph[i])
@@ -910,6 +911,10 @@ int nlt_gconv_wgrad(const nlt_gconv_desc* d, const float* G, float* dW, float* d
     } else if (wop_wgrad_applicable(k, G) && (int64_t)(wop_wgrad_ws_floats(k) * sizeof(float)) <= workspace_bytes) {
       // few-channel layers at (near) full resolution: register-tile outer products, one warp per unit kind (nlt_wop.cu)
       rc = launch_wop_wgrad(k, G, ws, &w, &KD_pad, st);
+      if (rc != NLT_OK) return rc;
+    } else if (wopn_wgrad_applicable(k, G) && (int64_t)(wopn_wgrad_ws_floats(k) * sizeof(float)) <= workspace_bytes) {
+      // final 1x1 conv into <= 4 channels: coalesced (pixel, channel quad) lanes (nlt_wop.cu)
+      rc = launch_wopn_wgrad(k, G, ws, &w, &KD_pad, st);
       if (rc != NLT_OK) return rc;
     } else if (pws_wgrad_applicable(k, G) && (int64_t)(pws_wgrad_ws_floats(k) * sizeof(float)) <= workspace_bytes) {
       rc = launch_pws_wgrad(k, G, ws, &w, &KD_pad, st);

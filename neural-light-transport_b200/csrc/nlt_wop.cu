@@ -283,6 +283,161 @@ static WopPlan wop_plan(const GConvK& k, const float* G) {
   return pl;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Weight gradient of a 1x1 conv into <= 4 channels (the final conv, nlt/networks/convnet.py:65-70: 36 -> 3 at full
+// resolution): dW[c, n] = sum_p x[p, c] * dz[p, n] is 108 numbers over 8 M pixels -- a pure stream of 156 B per
+// pixel.  lanes = (pixel slot, channel quad) with the quad fastest, so that a warp's x loads are one contiguous
+// 512-byte run (the thread-per-pixel form read 16 of every 64 bytes per instruction and had three K-split CTAs
+// re-read every line); 12 accumulators per lane; sources get warps in proportion to their width.
+// ---------------------------------------------------------------------------------------------
+constexpr int WOPN_MAX_WARPS = 12;
+
+struct WopnParams {
+  const float* src[NLT_MAX_SEG];
+  int C[NLT_MAX_SEG], lq[NLT_MAX_SEG], row0[NLT_MAX_SEG];       // channels, log2(quads), first partial row
+  int w_seg[WOPN_MAX_WARPS], w_phase[WOPN_MAX_WARPS], w_nphase[WOPN_MAX_WARPS];
+  int nwarp, N, ld, kd_pad, bias_row;
+  uint32_t M;
+};
+
+template <int N>
+__global__ void __launch_bounds__(WOPN_MAX_WARPS * 32, 3)
+wopn_wgrad_kernel(const __grid_constant__ WopnParams p, const float* __restrict__ G, float* __restrict__ ws) {
+  __shared__ float red[WOPN_MAX_WARPS][16 * 4 * N];              // [warp][quad <= 16][4][N]
+  __shared__ float redb[N];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < p.nwarp) {
+    const int sg = p.w_seg[warp];
+    const int lq = p.lq[sg], C = p.C[sg];
+    const int cq = lane & ((1 << lq) - 1), slot = lane >> lq;
+    const uint32_t pw = 32u >> lq;                               // pixels per warp step
+    const uint32_t stride = pw * (uint32_t)p.w_nphase[warp] * gridDim.x;
+    const float* xb = p.src[sg] + 4 * cq;
+    const bool do_bias = (warp == 0) && cq == 0;
+    float acc[4][N], gsum[N];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int n = 0; n < N; ++n) acc[i][n] = 0.f;
+#pragma unroll
+    for (int n = 0; n < N; ++n) gsum[n] = 0.f;
+    uint32_t px = (blockIdx.x * (uint32_t)p.w_nphase[warp] + (uint32_t)p.w_phase[warp]) * pw + slot;
+#pragma unroll 4
+    for (; px < p.M; px += stride) {
+      const float4 xv = ld4(xb + (size_t)px * C);
+      float g[N];
+#pragma unroll
+      for (int n = 0; n < N; ++n) g[n] = __ldg(G + (size_t)px * N + n);
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int n = 0; n < N; ++n) acc[i][n] = fmaf(xs[i], g[n], acc[i][n]);
+      if (do_bias) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) gsum[n] += g[n];
+      }
+    }
+    for (int off = 16; off >= (1 << lq); off >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int n = 0; n < N; ++n) acc[i][n] += __shfl_xor_sync(0xffffffffu, acc[i][n], off);
+    }
+    if (warp == 0) {                                             // the bias lanes are the cq == 0 lanes of warp 0
+      for (int off = 16; off >= (1 << lq); off >>= 1) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) gsum[n] += __shfl_xor_sync(0xffffffffu, gsum[n], off);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) redb[n] = gsum[n];
+      }
+    }
+    if (slot == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int n = 0; n < N; ++n) red[warp][(cq * 4 + i) * N + n] = acc[i][n];
+    }
+  }
+  __syncthreads();
+  // warps of one source in fixed order, one partial per CTA
+  float* part = ws + (size_t)blockIdx.x * p.kd_pad * p.ld;
+  for (int i = threadIdx.x; i < p.kd_pad * p.ld; i += blockDim.x) part[i] = 0.f;
+  __syncthreads();
+  for (int sg = 0; sg < NLT_MAX_SEG; ++sg) {
+    if (p.C[sg] == 0) continue;
+    const int cnt = p.C[sg] * N;                                 // (channel, n) entries of this source
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      float v = 0.f;
+      for (int w = 0; w < p.nwarp; ++w)
+        if (p.w_seg[w] == sg) v += red[w][i];
+      part[(size_t)(p.row0[sg] + i / N) * p.ld + i % N] = v;
+    }
+  }
+  if (threadIdx.x < N) part[(size_t)p.bias_row * p.ld + threadIdx.x] = redb[threadIdx.x];
+}
+
+static bool wopn_plan(const GConvK& k, const float* G, WopnParams* p, unsigned* grid, int* GS_out) {
+  memset(p, 0, sizeof(*p));
+  if (k.d2s || k.M < (1u << 16) || k.Cout != k.cout_true || k.Cout < 1 || k.Cout > 4) return false;
+  if (k.ay.nu != 1 || k.ax.nu != 1 || k.ay.it != 1 || k.ax.it != 1 || k.ay.i0 != 0 || k.ax.i0 != 0) return false;
+  if (k.ay.os != 1 || k.ax.os != 1 || k.ay.o0 != 0 || k.ax.o0 != 0) return false;
+  if (k.Hin != k.Hout || k.Win != k.Wout || k.ay.nt != k.Hout || k.ax.nt != k.Wout) return false;
+  (void)G;
+  int GS = 0, qmin = 32, qsum = 0;
+  for (int s = 0; s < k.nseg; ++s) {
+    const Seg& sg = k.seg[s];
+    if (!sg.vec || sg.sub != nullptr || sg.bcast || sg.C < 4 || sg.C > 64 || !pow2(sg.C / 4)) return false;
+    p->src[s] = sg.ptr; p->C[s] = sg.C; p->lq[s] = ilog2(sg.C / 4); p->row0[s] = GS * 4;
+    GS += sg.C / 4;
+    if (sg.C / 4 < qmin) qmin = sg.C / 4;
+    qsum += sg.C / 4;
+  }
+  int nw = 0;
+  for (int s = 0; s < k.nseg; ++s) {
+    const int cnt = (k.seg[s].C / 4) / qmin;                     // warps in proportion to the source's width
+    for (int ph = 0; ph < cnt; ++ph) {
+      if (nw >= WOPN_MAX_WARPS) return false;
+      p->w_seg[nw] = s; p->w_phase[nw] = ph; p->w_nphase[nw] = cnt; ++nw;
+    }
+  }
+  if (p->w_seg[0] != 0) return false;
+  p->nwarp = nw; p->N = k.Cout; p->ld = (k.Cout + 3) / 4 * 4;
+  p->kd_pad = (GS + 1) * 4; p->bias_row = GS * 4; p->M = k.M;
+  *grid = 148u * (unsigned)(nw <= 4 ? 8 : (nw <= 8 ? 5 : 4));
+  *GS_out = GS;
+  return true;
+}
+
+bool wopn_wgrad_applicable(const GConvK& k, const float* G) {
+  if (wop_level() <= 0) return false;
+  WopnParams p; unsigned grid; int GS;
+  return wopn_plan(k, G, &p, &grid, &GS);
+}
+
+size_t wopn_wgrad_ws_floats(const GConvK& k) {
+  WopnParams p; unsigned grid; int GS;
+  return wopn_plan(k, nullptr, &p, &grid, &GS) ? (size_t)grid * p.kd_pad * p.ld : 0;
+}
+
+int launch_wopn_wgrad(const GConvK& k, const float* G, float* ws, WgradK* w, size_t* KD_pad, cudaStream_t st) {
+  WopnParams p; unsigned grid; int GS;
+  if (!wopn_plan(k, G, &p, &grid, &GS)) return set_err(NLT_ERR_INVALID, "wopn_wgrad not applicable");
+  w->g = k; w->GS = GS; w->KG = GS + 1; w->ld = p.ld; w->nsplit = (int)grid; w->pix_per_split = 0;
+  *KD_pad = (size_t)p.kd_pad;
+  const unsigned thr = (unsigned)p.nwarp * 32u;
+  switch (p.N) {
+    case 1: wopn_wgrad_kernel<1><<<grid, thr, 0, st>>>(p, G, ws); break;
+    case 2: wopn_wgrad_kernel<2><<<grid, thr, 0, st>>>(p, G, ws); break;
+    case 3: wopn_wgrad_kernel<3><<<grid, thr, 0, st>>>(p, G, ws); break;
+    default: wopn_wgrad_kernel<4><<<grid, thr, 0, st>>>(p, G, ws); break;
+  }
+  NLT_CUDA_LAUNCH_CHECK("wopn_wgrad_kernel");
+  return NLT_OK;
+}
+
 bool wop_wgrad_applicable(const GConvK& k, const float* G) { return wop_plan(k, G).ok; }
 
 size_t wop_wgrad_ws_floats(const GConvK& k) {

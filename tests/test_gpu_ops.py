@@ -119,7 +119,10 @@ GEOMS = [
     ('conv', 1, 1, 32, 32, [64], 16),
     ('conv', 1, 1, 24, 24, [20, 4], 16),
     ('conv', 1, 1, 40, 40, [3, 40, 1, 2], 16),
-    ('conv', 1, 1, 24, 40, [32, 40, 8], 16),    # K = 80: 24 float4 groups per row (forward at 51 KB, weight gradient at 67 KB)
+    ('conv', 1, 1, 24, 40, [32, 40, 8], 16),
+    # coalesced weight gradient of a 1x1 conv into <= 4 channels (wopn_wgrad_kernel: >= 64 K pixels)
+    ('conv', 1, 1, 160, 144, [4, 16, 16], 3),
+    ('conv', 1, 1, 128, 192, [8, 32], 2),    # K = 80: 24 float4 groups per row (forward at 51 KB, weight gradient at 67 KB)
 ]
 
 
