@@ -165,7 +165,8 @@ int launch_wgrad_tpp(const GConvK& k, const float* G, float* ws, WgradK* w, size
 
 // wide pointwise conv into 16 channels (nlt_pwx.cu): level 0 of the 64-channel query stack
 extern int g_opt_pwx;
-extern int g_opt_pf_ns, g_opt_pwx_ns;
+extern int g_opt_pf_ns, g_opt_pwx_ns, g_opt_pf_s1;
+int pf_s1_level();
 extern int g_opt_tiny;
 extern int g_opt_wop;
 bool wopn_wgrad_applicable(const GConvK& k, const float* G);

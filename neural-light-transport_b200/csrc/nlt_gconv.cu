@@ -701,6 +701,7 @@ int nlt_set_option(const char* name, int value) {
   if (strcmp(name, "tcs") == 0) { nlt::g_opt_tcs = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "pwx") == 0) { nlt::g_opt_pwx = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "pwd2s_first") == 0) { g_opt_pwd2s_first = value ? 1 : 0; return NLT_OK; }
+  if (strcmp(name, "pf_s1") == 0) { nlt::g_opt_pf_s1 = value ? 1 : 0; return NLT_OK; }
   if (strcmp(name, "pf_ns") == 0) { nlt::g_opt_pf_ns = value == 2 ? 2 : 1; return NLT_OK; }
   if (strcmp(name, "pwx_ns") == 0) { nlt::g_opt_pwx_ns = value == 2 ? 2 : 1; return NLT_OK; }
   if (strcmp(name, "pf") == 0) { g_opt_pf = value ? 1 : 0; return NLT_OK; }
@@ -726,8 +727,8 @@ int64_t nlt_gconv_fwd_workspace_bytes(const nlt_gconv_desc* d) {
 // order of gconv_fwd_impl below.
 static bool fwd_takes_tc(const GConvK* ph, int np, float beta, const float* mask_y, const float* out) {
   if (np != 1 || ph[0].M == 0) return false;
-  if (tiny_stencil_applicable(ph[0], out, mask_y)) return false;
   if (pf_enabled() && pf_fwd_applicable(ph[0], mask_y, out)) return false;
+  if (tiny_stencil_applicable(ph[0], out, mask_y)) return false;
   if (pwx_d2s_fwd_applicable(ph[0], beta, mask_y, out)) return false;
   if (pwd2s_first() && ph[0].d2s && ph[0].nseg == 1 && ph[0].seg[0].C == 64 &&
       pwd2s_applicable(ph[0], nullptr, 0, out, mask_y, nullptr)) return false;
@@ -777,6 +778,8 @@ static int gconv_fwd_impl(const nlt_gconv_desc* d, const float* bias, int act, f
   cudaStream_t st = (cudaStream_t)stream;
   // few-channel stride-1 stencils (4/8/16 -> same): the row-stream kernel of nlt_tiny.cu, ahead of the tensor path
   // (16 -> 16 at 512^2 is a 130 B/pixel stream: the tcgen05 pipeline's fixed costs exceed its 0.5 kFMA/pixel)
+  if (np == 1 && ph[0].M > 0 && pf_enabled() && pf_s1_level() > 0 && ph[0].ay.it == 1 && pf_fwd_applicable(ph[0], mask_y, out))
+    return launch_pf_fwd(ph[0], bias, act, beta, mask_y, mask_act, out, st);
   if (np == 1 && ph[0].M > 0 && tiny_stencil_applicable(ph[0], out, mask_y))
     return launch_tiny_stencil(ph[0], bias, act, beta, mask_y, mask_act, out, st);
   // 2x2 / stride-2 convs of levels 1-2 (K = 64 / 128 into 16 / 32 channels): staged-patch FFMA2 forward (nlt_pwx.cu)

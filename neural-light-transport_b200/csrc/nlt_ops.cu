@@ -181,32 +181,61 @@ __device__ __forceinline__ double fixed_scale(unsigned int gmax_bits) {
   return ldexp(1.0, 37 - e);
 }
 
+// Horizontally adjacent camera pixels usually share a texel column (the right taps of pixel i are the left taps of pixel
+// i + 1 wherever the warp field advances about one texel per pixel): lanes hand their right-tap contributions to the next
+// lane when the target texel is the same, which removes up to half of the 64-bit atomics.  Integer sums: the result
+// does not depend on who adds what, so the gradient stays bit-reproducible (and bit-identical to the unmerged form).
 __global__ void uv2cam_bwd_fixed_kernel(const float* __restrict__ d_pred_c, const float* __restrict__ warp, int B, int H,
                                         int W, int ih, int iw, const unsigned int* __restrict__ gmax_bits,
                                         unsigned long long* __restrict__ acc) {
   const size_t npix = (size_t)B * ih * iw;
   const size_t per_cam = (size_t)ih * iw;
+  const size_t total = (npix + 31) / 32 * 32;                    // whole warps iterate together (shuffles below)
   const double scale = fixed_scale(*gmax_bits);
-  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (size_t)gridDim.x * blockDim.x) {
-    const int b = (int)(p / per_cam);
-    const float2 wv = __ldg(reinterpret_cast<const float2*>(warp) + p);
-    const float x = wv.x * (float)W, y = wv.y * (float)H;
+  const int lane = threadIdx.x & 31;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
+    bool live = p < npix;
     Taps t;
-    if (!resampler_taps(x, y, H, W, t)) continue;
-    float g[3];
+    float g[3] = {0.f, 0.f, 0.f};
+    int b = 0;
+    if (live) {
+      b = (int)(p / per_cam);
+      const float2 wv = __ldg(reinterpret_cast<const float2*>(warp) + p);
+      live = resampler_taps(wv.x * (float)W, wv.y * (float)H, H, W, t);
+    }
+    if (live) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) g[c] = __ldg(d_pred_c + p * 3 + c);
-    if (g[0] == 0.f && g[1] == 0.f && g[2] == 0.f) continue;
-    unsigned long long* du = acc + (size_t)b * H * W * 3;
+      for (int c = 0; c < 3; ++c) g[c] = __ldg(d_pred_c + p * 3 + c);
+      live = !(g[0] == 0.f && g[1] == 0.f && g[2] == 0.f);
+    }
+    int id[4];
+    long long q[4][3];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int id = t.idx[k];
-      if (id <= 0) continue;   // out of range, or texel (0,0) whose mask multiply kills the gradient
+      // id <= 0: out of range, or texel (0,0) whose mask multiply kills the gradient
+      id[k] = (live && t.idx[k] > 0) ? b * H * W + t.idx[k] : -1;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) q[k][c] = id[k] >= 0 ? __double2ll_rn((double)(t.w[k] * g[c]) * scale) : 0ll;
+    }
+    // taps: 0 = (fx,fy), 1 = (cx,cy), 2 = (fx,cy), 3 = (cx,fy): right taps 3 / 1 go to the next lane's left taps 0 / 2
+#pragma unroll
+    for (int pr = 0; pr < 2; ++pr) {
+      const int kr = pr == 0 ? 3 : 1, kl = pr == 0 ? 0 : 2;
+      const int nid = __shfl_down_sync(0xffffffffu, id[kl], 1);
+      const bool give = lane < 31 && id[kr] >= 0 && nid == id[kr];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const long long q = __double2ll_rn((double)(t.w[k] * g[c]) * scale);
-        if (q != 0) atomicAdd(du + (size_t)id * 3 + c, (unsigned long long)q);   // two's complement: signed sum
+        const long long recv = __shfl_up_sync(0xffffffffu, give ? q[kr][c] : 0ll, 1);
+        if (lane > 0) q[kl][c] += recv;
       }
+      if (give) id[kr] = -1;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (id[k] < 0) continue;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        if (q[k][c] != 0) atomicAdd(acc + (size_t)id[k] * 3 + c, (unsigned long long)q[k][c]);   // two's complement: signed sum
     }
   }
 }

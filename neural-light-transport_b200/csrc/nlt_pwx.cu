@@ -632,6 +632,9 @@ struct PfParams {
   int Hin, Win, Wout;
   int tiles_per_row;
   uint32_t ntiles;
+  int s1;                        // 1: stride-1 2x2 stencil (one 16-channel source): input pixel = output pixel + tap offset
+  int iuy, i0y, iux, i0x;        // tap offsets of the stride-1 form: iy = y + uy * iuy + i0y
+  int Hout;
 };
 
 __global__ void pf_pack_w_kernel(const PfParams p, const float* __restrict__ w, long long wt, long long wc, long long wn,
@@ -684,18 +687,43 @@ pf_fwd_kernel(const PfParams p, const float* __restrict__ bias, const int act, f
   for (uint32_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
     const uint32_t orow = t / (uint32_t)p.tiles_per_row;       // n * Hout + y; input rows 2 * orow + dy (Hin = 2 Hout)
     const uint32_t x0 = (t - orow * (uint32_t)p.tiles_per_row) * TP;
+    if (p.s1) {
+      // stride-1 stencil: every input pixel of the two tap rows lands in the K-rows of the (up to) two output pixels
+      // that see it; rows / columns outside the image (SAME padding) are stored as zeros
+      const int C = p.seg_C[0], c4 = C >> 2, l = p.seg_l[0] - 1;         // l = log2(C / 4)
+      const uint32_t n = orow / (uint32_t)p.Hout, y = orow - n * (uint32_t)p.Hout;
 #pragma unroll
-    for (int s = 0; s < NLT_MAX_SEG; ++s) {
-      if (s >= p.nseg) break;
-      const int C = p.seg_C[s], l = p.seg_l[s];
-      const int n4 = TP << l;                                  // float4 per patch row of the tile: TP * 2C / 4
+      for (int uy = 0; uy < 2; ++uy) {
+        const int iy = (int)y + uy * p.iuy + p.i0y;
+        const bool rowok = (unsigned)iy < (unsigned)p.Hin;
+        const float4* src = reinterpret_cast<const float4*>(p.seg_ptr[0] + ((size_t)n * p.Hin + (rowok ? iy : 0)) * p.Win * C);
 #pragma unroll
-      for (int dy = 0; dy < 2; ++dy) {
-        const float4* src = reinterpret_cast<const float4*>(p.seg_ptr[s] + ((size_t)(2 * orow + dy) * p.Win + 2 * x0) * C);
-        const uint32_t col = p.seg_col[s] + dy * 2 * C;
-        for (int i = tid; i < n4; i += THR) {
-          const uint32_t px = (uint32_t)i >> l, j = (uint32_t)i & ((1u << l) - 1u);
-          cp_async16(xs_u + (px * KROW + col + 4 * j) * 4, src + i);
+        for (int ux = 0; ux < 2; ++ux) {
+          const int xoff = (int)x0 + ux * p.iux + p.i0x;
+          const uint32_t col = (uint32_t)(uy * 2 + ux) * C;
+          for (int i = tid; i < TP * c4; i += THR) {
+            const uint32_t px = (uint32_t)i >> l, j = (uint32_t)i & ((uint32_t)c4 - 1u);
+            const int ix = xoff + (int)px;
+            const uint32_t dst = px * KROW + col + 4 * j;
+            if (rowok && (unsigned)ix < (unsigned)p.Win) cp_async16(xs_u + dst * 4, src + (size_t)ix * c4 + j);
+            else *reinterpret_cast<float4*>(xs + dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < NLT_MAX_SEG; ++s) {
+        if (s >= p.nseg) break;
+        const int C = p.seg_C[s], l = p.seg_l[s];
+        const int n4 = TP << l;                                  // float4 per patch row of the tile: TP * 2C / 4
+  #pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+          const float4* src = reinterpret_cast<const float4*>(p.seg_ptr[s] + ((size_t)(2 * orow + dy) * p.Win + 2 * x0) * C);
+          const uint32_t col = p.seg_col[s] + dy * 2 * C;
+          for (int i = tid; i < n4; i += THR) {
+            const uint32_t px = (uint32_t)i >> l, j = (uint32_t)i & ((1u << l) - 1u);
+            cp_async16(xs_u + (px * KROW + col + 4 * j) * 4, src + i);
+          }
         }
       }
     }
@@ -741,15 +769,29 @@ pf_fwd_kernel(const PfParams p, const float* __restrict__ bias, const int act, f
   }
 }
 
+int g_opt_pf_s1 = -1;    // option "pf_s1" / NLT_PF_S1: the staged kernel also for the stride-1 16 -> 16 stencils (ahead of nlt_tiny.cu)
+int pf_s1_level() {
+  if (g_opt_pf_s1 < 0) { const char* e = getenv("NLT_PF_S1"); g_opt_pf_s1 = (e && e[0] == '1') ? 1 : 0; }
+  return g_opt_pf_s1;
+}
+
 static bool pf_build(const GConvK& k, PfParams* p, int* tp) {
   memset(p, 0, sizeof(*p));
   if (!pwx_enabled() || k.d2s || k.M == 0) return false;
   if (k.Cout != k.cout_true || (k.Cout != 16 && k.Cout != 32)) return false;
-  if (k.ay.nu != 2 || k.ax.nu != 2 || k.ay.iu != 1 || k.ax.iu != 1 || k.ay.i0 != 0 || k.ax.i0 != 0) return false;
-  if (k.ay.it != 2 || k.ax.it != 2 || k.ay.os != 1 || k.ax.os != 1 || k.ay.o0 != 0 || k.ax.o0 != 0) return false;
+  if (k.ay.nu != 2 || k.ax.nu != 2 || k.ay.os != 1 || k.ax.os != 1 || k.ay.o0 != 0 || k.ax.o0 != 0) return false;
+  const bool s1 = k.ay.it == 1 && k.ax.it == 1;
+  if (s1) {
+    // stride-1 2x2 stencil 16 -> 16 (second convs of level 1 / 10 and their adjoints), option "pf_s1"
+    if (pf_s1_level() <= 0 || k.nseg != 1 || k.seg[0].C != 16 || k.Cout != 16) return false;
+    if (k.Hin != k.Hout || k.Win != k.Wout || k.ay.nt != k.Hout || k.ax.nt != k.Wout) return false;
+    if ((k.ay.iu != 1 && k.ay.iu != -1) || (k.ax.iu != 1 && k.ax.iu != -1)) return false;
+  } else {
+    if (k.ay.iu != 1 || k.ax.iu != 1 || k.ay.i0 != 0 || k.ax.i0 != 0 || k.ay.it != 2 || k.ax.it != 2) return false;
+    if (k.ay.nt != k.Hout || k.ax.nt != k.Wout || k.Hin != 2 * k.Hout || k.Win != 2 * k.Wout) return false;
+  }
   if (k.kw != 2 || (k.ay.d0 + k.ay.ds) < 0 || (k.ay.d0 + k.ay.ds) > 1 || (k.ax.d0 + k.ax.ds) < 0 || (k.ax.d0 + k.ax.ds) > 1 ||
       k.ay.d0 < 0 || k.ay.d0 > 1 || k.ax.d0 < 0 || k.ax.d0 > 1) return false;
-  if (k.ay.nt != k.Hout || k.ax.nt != k.Wout || k.Hin != 2 * k.Hout || k.Win != 2 * k.Wout) return false;
   int col = 0;
   for (int s = 0; s < k.nseg; ++s) {
     const Seg& sg = k.seg[s];
@@ -767,7 +809,8 @@ static bool pf_build(const GConvK& k, PfParams* p, int* tp) {
   p->nseg = k.nseg; p->K = col;
   *tp = col <= 64 ? 128 : 64;
   if (k.Wout % *tp != 0) return false;
-  p->Hin = k.Hin; p->Win = k.Win; p->Wout = k.Wout;
+  p->Hin = k.Hin; p->Win = k.Win; p->Wout = k.Wout; p->Hout = k.Hout;
+  p->s1 = s1 ? 1 : 0; p->iuy = k.ay.iu; p->i0y = k.ay.i0; p->iux = k.ax.iu; p->i0x = k.ax.i0;
   p->tiles_per_row = k.Wout / *tp;
   const long long nt = (long long)k.N * k.Hout * p->tiles_per_row;
   if (nt < 4 || nt > (1ll << 31)) return false;

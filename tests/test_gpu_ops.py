@@ -200,6 +200,20 @@ def test_two_threads_per_pixel_forward_kernels(kind, k, s, H, W, segc, cout):
         nat.set_option('pf_ns', 1)
 
 
+@pytest.mark.parametrize('kind,k,s,H,W,segc,cout', [('conv', 2, 1, 5, 128, [16], 16), ('deconv', 2, 1, 5, 256, [16], 16),
+                                                    ('conv', 2, 1, 256, 256, [16], 16)])
+def test_staged_patch_kernel_on_stride1_stencils(kind, k, s, H, W, segc, cout):
+    """pf_fwd_kernel in its stride-1 form (option pf_s1): forward and input gradient of the 16 -> 16 2x2 stencils,
+    SAME padding on either side (conv / deconv flavour)."""
+    import nlt_native as nat
+    nat.set_option('pf_s1', 1)
+    try:
+        for act in ('leakyrelu', None):
+            test_gconv_forward_backward(kind, k, s, H, W, segc, cout, act)
+    finally:
+        nat.set_option('pf_s1', int(os.environ.get('NLT_PF_S1', '0')))
+
+
 TC_SHAPES = [g for g in GEOMS if all(c % 16 == 0 for c in g[5]) and g[6] % 16 == 0 and g[3] * g[4] >= 256]
 
 
