@@ -53,6 +53,10 @@ struct TcParams {
   int Hout, Wout, cout_true, Cout;   // Cout = GEMM columns (d2s: s*s*cout_true)
   int o0y, osy, o0x, osx;            // output pixel = o0 + os * lattice coordinate (non-d2s)
   int d2s, d2s_s;
+  // exact multiply-shift division by the run-time tile / channel counts: the per-tile coordinate decode of the producer
+  // and the per-pass address arithmetic of the epilogue warps were chains of 32-bit integer divisions (~150 cycles
+  // each); with everything else ablated a tile still cost 4 us (profiles/r2_z_*)
+  FastDiv div_ntn, div_tpi, div_tx, div_tw, div_ct, div_s;
   int act, mask_act;
   int stages;               // smem ring depth
   int ablate;               // DIAGNOSTIC (NLT_TC_ABLATE, wrong results!): 1 no B loads, 2 no transform, 4 no MMA, 8 no epilogue memory traffic, 16 no A loads
@@ -290,11 +294,12 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles_n;
-        const int mt = tile / p.n_tiles_n;
-        const int n = mt / tiles_per_img;
+        const int mt = (int)fdiv((uint32_t)tile, p.div_ntn);
+        const int nt = tile - mt * p.n_tiles_n;
+        const int n = (int)fdiv((uint32_t)mt, p.div_tpi);
         const int r = mt - n * tiles_per_img;
-        const int ty0 = (r / p.tiles_x) * p.TH, tx0 = (r % p.tiles_x) * p.TW;
+        const int rq = (int)fdiv((uint32_t)r, p.div_tx);
+        const int ty0 = rq * p.TH, tx0 = (r - rq * p.tiles_x) * p.TW;
         int kb = 0;
         for (int uy = 0; uy < p.ntap_y; ++uy)
           for (int ux = 0; ux < p.ntap_x; ++ux)
@@ -391,21 +396,23 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     struct Coord { int n, ty0, tx0, nt; };
     auto tile_coord = [&](int tile) {
       Coord c;
-      c.nt = tile % p.n_tiles_n;
-      const int mt = tile / p.n_tiles_n;
-      c.n = mt / tiles_per_img;
+      const int mt = (int)fdiv((uint32_t)tile, p.div_ntn);
+      c.nt = tile - mt * p.n_tiles_n;
+      c.n = (int)fdiv((uint32_t)mt, p.div_tpi);
       const int r = mt - c.n * tiles_per_img;
-      c.ty0 = (r / p.tiles_x) * p.TH; c.tx0 = (r % p.tiles_x) * p.TW;
+      const int rq = (int)fdiv((uint32_t)r, p.div_tx);
+      c.ty0 = rq * p.TH; c.tx0 = (r - rq * p.tiles_x) * p.TW;
       return c;
     };
     // element offset of (tile row, GEMM column) in the output tensor
     auto out_off = [&](const Coord& c, int row, int nb) -> size_t {
-      const int ty = c.ty0 + row / p.TW, tx = c.tx0 + row % p.TW;
+      const int rty = (int)fdiv((uint32_t)row, p.div_tw);
+      const int ty = c.ty0 + rty, tx = c.tx0 + row - rty * p.TW;
       int cb = nb, oy, ox;
       if (p.d2s) {
-        const int tap = nb / p.cout_true;
+        const int tap = (int)fdiv((uint32_t)nb, p.div_ct);
         cb = nb - tap * p.cout_true;
-        const int dy = tap / p.d2s_s;
+        const int dy = (int)fdiv((uint32_t)tap, p.div_s);
         oy = ty * p.d2s_s + dy; ox = tx * p.d2s_s + (tap - dy * p.d2s_s);
       } else {
         oy = p.o0y + p.osy * ty; ox = p.o0x + p.osx * tx;
@@ -443,7 +450,7 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
             int cb = col0 + h * 16 + q4 * 4;
-            if (p.d2s) cb -= (cb / p.cout_true) * p.cout_true;
+            if (p.d2s) cb -= (int)fdiv((uint32_t)cb, p.div_ct) * p.cout_true;
             float o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -554,11 +561,12 @@ tcs_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles_n;
-        const int mt = tile / p.n_tiles_n;
-        const int n = mt / tiles_per_img;
+        const int mt = (int)fdiv((uint32_t)tile, p.div_ntn);
+        const int nt = tile - mt * p.n_tiles_n;
+        const int n = (int)fdiv((uint32_t)mt, p.div_tpi);
         const int r = mt - n * tiles_per_img;
-        const int ty0 = (r / p.tiles_x) * p.TH, tx0 = (r % p.tiles_x) * p.TW;
+        const int rq = (int)fdiv((uint32_t)r, p.div_tx);
+        const int ty0 = rq * p.TH, tx0 = (r - rq * p.tiles_x) * p.TW;
         int kb = 0;
         for (int uy = 0; uy < p.ntap_y; ++uy)
           for (int ux = 0; ux < p.ntap_x; ++ux)
@@ -677,21 +685,23 @@ tcs_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     struct Coord { int n, ty0, tx0, nt; };
     auto tile_coord = [&](int tile) {
       Coord c;
-      c.nt = tile % p.n_tiles_n;
-      const int mt = tile / p.n_tiles_n;
-      c.n = mt / tiles_per_img;
+      const int mt = (int)fdiv((uint32_t)tile, p.div_ntn);
+      c.nt = tile - mt * p.n_tiles_n;
+      c.n = (int)fdiv((uint32_t)mt, p.div_tpi);
       const int r = mt - c.n * tiles_per_img;
-      c.ty0 = (r / p.tiles_x) * p.TH; c.tx0 = (r % p.tiles_x) * p.TW;
+      const int rq = (int)fdiv((uint32_t)r, p.div_tx);
+      c.ty0 = rq * p.TH; c.tx0 = (r - rq * p.tiles_x) * p.TW;
       return c;
     };
     // element offset of (tile row, GEMM column) in the output tensor
     auto out_off = [&](const Coord& c, int row, int nb) -> size_t {
-      const int ty = c.ty0 + row / p.TW, tx = c.tx0 + row % p.TW;
+      const int rty = (int)fdiv((uint32_t)row, p.div_tw);
+      const int ty = c.ty0 + rty, tx = c.tx0 + row - rty * p.TW;
       int cb = nb, oy, ox;
       if (p.d2s) {
-        const int tap = nb / p.cout_true;
+        const int tap = (int)fdiv((uint32_t)nb, p.div_ct);
         cb = nb - tap * p.cout_true;
-        const int dy = tap / p.d2s_s;
+        const int dy = (int)fdiv((uint32_t)tap, p.div_s);
         oy = ty * p.d2s_s + dy; ox = tx * p.d2s_s + (tap - dy * p.d2s_s);
       } else {
         oy = p.o0y + p.osy * ty; ox = p.o0x + p.osx * tx;
@@ -729,7 +739,7 @@ tcs_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
             int cb = col0 + h * 16 + q4 * 4;
-            if (p.d2s) cb -= (cb / p.cout_true) * p.cout_true;
+            if (p.d2s) cb -= (int)fdiv((uint32_t)cb, p.div_ct) * p.cout_true;
             float o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -892,6 +902,9 @@ static TcPlan tc_plan(const GConvK& k) {
     pl.bn /= 2;
   }
   p.n_tiles_n = k.Cout / pl.bn;
+  p.div_ntn = make_fastdiv((uint32_t)p.n_tiles_n); p.div_tpi = make_fastdiv((uint32_t)(p.tiles_x * p.tiles_y));
+  p.div_tx = make_fastdiv((uint32_t)p.tiles_x); p.div_tw = make_fastdiv((uint32_t)p.TW);
+  p.div_ct = make_fastdiv((uint32_t)p.cout_true); p.div_s = make_fastdiv((uint32_t)(p.d2s ? p.d2s_s : 1));
   const long long tt = (long long)p.N * p.tiles_x * p.tiles_y * p.n_tiles_n;
   if (tt > (1ll << 30)) return pl;
   p.total_tiles = (int)tt;
@@ -996,6 +1009,7 @@ struct WgParams {
   int ntap_x, nseg, ctot, Kd;
   int seg_C[NLT_MAX_SEG], seg_coff[NLT_MAX_SEG];
   int n_mtiles, n_ntiles;
+  FastDiv div_tpi, div_tx;                                // multiply-shift division by tiles per image / per row
   int raw_stages, raw_stage_bytes;
   int Cout, ld, KD_pad, bias_row;
   float* ws;
@@ -1117,9 +1131,10 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < p.total_ptiles; t += gridDim.x) {
-        const int n = t / tiles_per_img;
+        const int n = (int)fdiv((uint32_t)t, p.div_tpi);
         const int r = t - n * tiles_per_img;
-        const int ty0 = (r / p.tiles_x) * p.TH, tx0 = (r % p.tiles_x) * p.TW;
+        const int rq = (int)fdiv((uint32_t)r, p.div_tx);
+        const int ty0 = rq * p.TH, tx0 = (r - rq * p.tiles_x) * p.TW;
         mbar_wait(bar_rempty(stage), phase ^ 1);
         mbar_expect_tx(bar_rfull(stage), (uint32_t)raw_bytes_s);
         const uint32_t base = raw_u32 + (uint32_t)stage * p.raw_stage_bytes;
@@ -1303,6 +1318,7 @@ static WgPlan wg_plan(const GConvK& k) {
     if (p.Hl % p.TH) return pl;
   }
   p.tiles_x = p.Wl / p.TW; p.tiles_y = p.Hl / p.TH;
+  p.div_tpi = make_fastdiv((uint32_t)(p.tiles_x * p.tiles_y)); p.div_tx = make_fastdiv((uint32_t)p.tiles_x);
   const long long tt = (long long)p.N * p.tiles_x * p.tiles_y;
   if (tt > (1ll << 30) || tt < 4) return pl;
   p.total_ptiles = (int)tt;
