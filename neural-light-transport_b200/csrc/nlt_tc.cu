@@ -266,12 +266,12 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(bar_full(s), 1);
-      mbar_init(bar_ready(s), 256);
+      mbar_init(bar_ready(s), 8);                  // one arrival per transform warp (see the transform role)
       mbar_init(bar_empty(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_accf(b), 1);
-      mbar_init(bar_acce(b), 128);
+      mbar_init(bar_acce(b), 4);                   // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -372,8 +372,11 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           ah[q] = h;
           al[q] = l;
         }
+        // every thread makes its writes visible to the async proxy; ONE arrival per warp: 256 single-thread arrivals
+        // on the same mbarrier word serialise (they were the largest part of the kernel's per-k-block fixed cost)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(bar_ready(stage));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_ready(stage));
         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -479,7 +482,8 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         __syncwarp();
       }
       tc_fence_before();
-      mbar_arrive(bar_acce(buf));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acce(buf));
     }
   }
 
@@ -1102,8 +1106,8 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
     }
     n_items_s = ni;
     raw_bytes_s = bytes;
-    for (int s = 0; s < S; ++s) { mbar_init(bar_rfull(s), 1); mbar_init(bar_rempty(s), 256); }
-    for (int b = 0; b < 2; ++b) { mbar_init(bar_tready(b), 256); mbar_init(bar_tempty(b), 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(bar_rfull(s), 1); mbar_init(bar_rempty(s), 8); }      // one arrival per transform warp
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_tready(b), 8); mbar_init(bar_tempty(b), 1); }
     mbar_init(bar_accf, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1225,8 +1229,11 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(bar_tready(b));
-      mbar_arrive(bar_rempty(stage));
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_tready(b));
+        mbar_arrive(bar_rempty(stage));
+      }
       if (++stage == S) { stage = 0; phase ^= 1; }
     }
     // bias partial: reduce the 32 pixel lanes of each warp in a fixed butterfly order
