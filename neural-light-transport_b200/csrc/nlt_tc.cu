@@ -396,37 +396,44 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     constexpr int NPASS = 32 / RPI;               // passes per chunk (== QPR)
     const int lq = lane % QPR, lr = lane / QPR;
 
-    struct Coord { int n, ty0, tx0, nt; };
-    auto tile_coord = [&](int tile) {
-      Coord c;
+    // Output addressing without per-pass arithmetic: offset(tile, pass i, column) = tile base + row_off[i] + col_off, where
+    // row_off depends only on the lane (computed once per kernel) and col_off only on (column tile, chunk).  The
+    // epilogue warps are the busiest role of this kernel on the many-tile levels (ncu source view, profiles/r2_af_*:
+    // ~85 % of their samples are not waits) -- every instruction here is on the critical path of a tile.
+    const int sxy = p.d2s ? p.d2s_s : 1;
+    int row_off[NPASS];
+#pragma unroll
+    for (int i = 0; i < NPASS; ++i) {
+      const int row = quarter * 32 + i * RPI + lr;
+      const int rty = (int)fdiv((uint32_t)row, p.div_tw), rtx = row - rty * p.TW;
+      row_off[i] = p.d2s ? (rty * sxy * p.Wout + rtx * sxy) * p.cout_true
+                         : (p.osy * rty * p.Wout + p.osx * rtx) * p.cout_true;
+    }
+    auto tile_base = [&](int tile, int& nt) -> size_t {
       const int mt = (int)fdiv((uint32_t)tile, p.div_ntn);
-      c.nt = tile - mt * p.n_tiles_n;
-      c.n = (int)fdiv((uint32_t)mt, p.div_tpi);
-      const int r = mt - c.n * tiles_per_img;
+      nt = tile - mt * p.n_tiles_n;
+      const int n = (int)fdiv((uint32_t)mt, p.div_tpi);
+      const int r = mt - n * tiles_per_img;
       const int rq = (int)fdiv((uint32_t)r, p.div_tx);
-      c.ty0 = rq * p.TH; c.tx0 = (r - rq * p.tiles_x) * p.TW;
-      return c;
+      const int ty0 = rq * p.TH, tx0 = (r - rq * p.tiles_x) * p.TW;
+      const int oy = p.d2s ? ty0 * sxy : p.o0y + p.osy * ty0, ox = p.d2s ? tx0 * sxy : p.o0x + p.osx * tx0;
+      return (((size_t)n * p.Hout + oy) * p.Wout + ox) * p.cout_true;
     };
-    // element offset of (tile row, GEMM column) in the output tensor
-    auto out_off = [&](const Coord& c, int row, int nb) -> size_t {
-      const int rty = (int)fdiv((uint32_t)row, p.div_tw);
-      const int ty = c.ty0 + rty, tx = c.tx0 + row - rty * p.TW;
-      int cb = nb, oy, ox;
-      if (p.d2s) {
-        const int tap = (int)fdiv((uint32_t)nb, p.div_ct);
-        cb = nb - tap * p.cout_true;
-        const int dy = (int)fdiv((uint32_t)tap, p.div_s);
-        oy = ty * p.d2s_s + dy; ox = tx * p.d2s_s + (tap - dy * p.d2s_s);
-      } else {
-        oy = p.o0y + p.osy * ty; ox = p.o0x + p.osx * tx;
-      }
-      return (((size_t)c.n * p.Hout + oy) * p.Wout + ox) * p.cout_true + cb;
+    // offset of GEMM column nb inside an output pixel group (d2s: which of the s x s pixels, which channel)
+    auto col_off = [&](int nb) -> int {
+      if (!p.d2s) return nb;
+      const int tap = (int)fdiv((uint32_t)nb, p.div_ct);
+      const int dy = (int)fdiv((uint32_t)tap, p.div_s);
+      return (dy * p.Wout + (tap - dy * p.d2s_s)) * p.cout_true + (nb - tap * p.cout_true);
     };
+    const bool bias_vec = p.bias != nullptr && aligned16(p.bias);
+    const int act = p.act;
+    const float neg = act == NLT_ACT_LEAKYRELU ? 0.3f : (act == NLT_ACT_RELU ? 0.f : 1.f);
     float4 rm_old[NPASS], rm_y[NPASS];
-    auto prefetch = [&](const Coord& c, int ch) {
+    auto prefetch = [&](size_t base) {
 #pragma unroll
       for (int i = 0; i < NPASS; ++i) {
-        const size_t ob = out_off(c, quarter * 32 + i * RPI + lr, c.nt * BN + ch * 32 + lq * 4);
+        const size_t ob = base + (size_t)row_off[i];
         rm_old[i] = (p.beta != 0.f) ? *reinterpret_cast<const float4*>(p.out + ob) : make_float4(0.f, 0.f, 0.f, 0.f);
         rm_y[i] = (p.mask_y != nullptr) ? ld4(p.mask_y + ob) : make_float4(1.f, 1.f, 1.f, 1.f);
       }
@@ -435,17 +442,19 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1;
-      const Coord tc = tile_coord(tile);
+      int nt;
+      const size_t tbase = tile_base(tile, nt);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN);
 #pragma unroll 1
       for (int ch = 0; ch < NCH; ++ch) {
+        const int col0 = nt * BN + ch * 32;       // GEMM column of this chunk
+        const size_t cbase = tbase + (size_t)col_off(col0 + lq * 4);
         // read-modify-write operands first: their latency overlaps the accumulator wait / TMEM drain
-        if (rmw) prefetch(tc, ch);
+        if (rmw) prefetch(cbase);
         if (ch == 0) {
           mbar_wait(bar_accf(buf), acc_phase);
           tc_fence_after();
         }
-        const int col0 = tc.nt * BN + ch * 32;    // GEMM column of this chunk
 #pragma unroll
         for (int h = 0; h < CW / 16; ++h) {
           uint32_t v[16];
@@ -454,12 +463,17 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           for (int q4 = 0; q4 < 4; ++q4) {
             int cb = col0 + h * 16 + q4 * 4;
             if (p.d2s) cb -= (int)fdiv((uint32_t)cb, p.div_ct) * p.cout_true;
-            float o[4];
+            float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bias_vec) bq = ld4(p.bias + cb);
+            else if (p.bias != nullptr) bq = make_float4(__ldg(p.bias + cb), __ldg(p.bias + cb + 1), __ldg(p.bias + cb + 2), __ldg(p.bias + cb + 3));
+            float o[4] = {__uint_as_float(v[q4 * 4 + 0]) + bq.x, __uint_as_float(v[q4 * 4 + 1]) + bq.y,
+                          __uint_as_float(v[q4 * 4 + 2]) + bq.z, __uint_as_float(v[q4 * 4 + 3]) + bq.w};
+            if (act == NLT_ACT_ELU) {             // warp-uniform
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float x = __uint_as_float(v[q4 * 4 + e]);
-              if (p.bias != nullptr) x += __ldg(p.bias + cb + e);
-              o[e] = act_fwd(x, p.act);
+              for (int e = 0; e < 4; ++e) o[e] = elu_slow(o[e]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) o[e] = o[e] > 0.f ? o[e] : neg * o[e];
             }
             *reinterpret_cast<float4*>(stg + lane * TC_EPI_PAD + h * 16 + q4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
           }
@@ -476,7 +490,7 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
               o.z *= act_bwd_from_y(rm_y[i].z, p.mask_act); o.w *= act_bwd_from_y(rm_y[i].w, p.mask_act);
             }
           }
-          const size_t ob = out_off(tc, quarter * 32 + row, col0 + lq * 4);
+          const size_t ob = cbase + (size_t)row_off[i];
           if (!(p.ablate & 8) || o.x == 123456.f) *reinterpret_cast<float4*>(p.out + ob) = o;
         }
         __syncwarp();
