@@ -168,6 +168,7 @@ extern int g_opt_pwx;
 extern int g_opt_pf_ns, g_opt_pwx_ns, g_opt_pf_s1;
 int pf_s1_level();
 extern int g_opt_tiny;
+extern int g_opt_tc_rawhi;
 extern int g_opt_wop;
 bool wopn_wgrad_applicable(const GConvK& k, const float* G);
 size_t wopn_wgrad_ws_floats(const GConvK& k);

@@ -33,6 +33,8 @@ constexpr int TCF_THREADS = 448;              // forward kernel: TMA + MMA + 4 t
 constexpr uint32_t TC_SPIN_LIMIT = 1u << 28;    // watchdog: trap instead of hanging the GPU
 unsigned long long g_tc_launches = 0;           // tensor-core kernel launches (diagnostic)
 
+int g_opt_tc_rawhi = -1;
+
 struct TcParams {
   // lattice / tiling
   int N, Hl, Wl;            // lattice size (pixels this kernel enumerates)
@@ -59,6 +61,7 @@ struct TcParams {
   FastDiv div_ntn, div_tpi, div_tx, div_tw, div_ct, div_s;
   int act, mask_act;
   int stages;               // smem ring depth
+  int rawhi;                // option "tc_rawhi" / NLT_TC_RAWHI: A-hi operand = the raw fp32 tile (no hi plane write)
   int ablate;               // DIAGNOSTIC (NLT_TC_ABLATE, wrong results!): 1 no B loads, 2 no transform, 4 no MMA, 8 no epilogue memory traffic, 16 no A loads
   float beta;
   const float* bias;
@@ -367,10 +370,19 @@ tc_gconv_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           const int q = t + i * 256;              // physical 16-byte chunk: elementwise, swizzle-agnostic
           const float4 v = ah[q];
           float4 h, l;
-          h.x = tf32_round(v.x); h.y = tf32_round(v.y); h.z = tf32_round(v.z); h.w = tf32_round(v.w);
-          l.x = tf32_round(v.x - h.x); l.y = tf32_round(v.y - h.y); l.z = tf32_round(v.z - h.z); l.w = tf32_round(v.w - h.w);
-          ah[q] = h;
-          al[q] = l;
+          if (p.rawhi) {
+            // the tensor core reads the upper 19 bits of an fp32 word (measured: tests/test_gpu_tcts.py): the raw tile IS
+            // the hi operand, only lo = x - trunc(x) (exact in fp32, then rounded to TF32) has to be written
+            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+            l.x = tf32_round(v.x - h.x); l.y = tf32_round(v.y - h.y); l.z = tf32_round(v.z - h.z); l.w = tf32_round(v.w - h.w);
+            al[q] = l;
+          } else {
+            h.x = tf32_round(v.x); h.y = tf32_round(v.y); h.z = tf32_round(v.z); h.w = tf32_round(v.w);
+            l.x = tf32_round(v.x - h.x); l.y = tf32_round(v.y - h.y); l.z = tf32_round(v.z - h.z); l.w = tf32_round(v.w - h.w);
+            ah[q] = h;
+            al[q] = l;
+          }
         }
         // every thread makes its writes visible to the async proxy; ONE arrival per warp: 256 single-thread arrivals
         // on the same mbarrier word serialise (they were the largest part of the kernel's per-k-block fixed cost)
@@ -945,6 +957,8 @@ static TcPlan tc_plan(const GConvK& k) {
       if (ablate & 32) { const int one = 1; cudaMemcpyToSymbol(g_tc_poll, &one, sizeof(int)); }
     }
     p.ablate = ablate;
+    if (g_opt_tc_rawhi < 0) { const char* e = getenv("NLT_TC_RAWHI"); g_opt_tc_rawhi = (e && e[0] == '1') ? 1 : 0; }
+    p.rawhi = g_opt_tc_rawhi;
   }
   pl.ok = true;
   return pl;

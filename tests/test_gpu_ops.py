@@ -217,6 +217,20 @@ def test_staged_patch_kernel_on_stride1_stencils(kind, k, s, H, W, segc, cout):
 TC_SHAPES = [g for g in GEOMS if all(c % 16 == 0 for c in g[5]) and g[6] % 16 == 0 and g[3] * g[4] >= 256]
 
 
+@pytest.mark.parametrize('kind,k,s,H,W,segc,cout', [g for g in GEOMS if all(c % 16 == 0 for c in g[5]) and g[6] % 16 == 0
+                                                    and g[3] * g[4] >= 256][:14])
+def test_tensor_core_raw_hi_operand(kind, k, s, H, W, segc, cout):
+    """Option tc_rawhi: the activation tile as TMA delivered it is the hi operand (the tensor core ignores the low 13
+    bits), only lo = x - trunc(x) is written by the transform warps.  Same oracle check, same tolerance (a core that
+    ROUNDED its operands would be 1e-3 off here)."""
+    import nlt_native as nat
+    nat.set_option('tc_rawhi', 1)
+    try:
+        test_gconv_forward_backward(kind, k, s, H, W, segc, cout, 'leakyrelu')
+    finally:
+        nat.set_option('tc_rawhi', int(os.environ.get('NLT_TC_RAWHI', '0')))
+
+
 @pytest.fixture(params=['ss', 'ts'])
 def tc_form(request):
     """Both forms of the tcgen05 forward / input-gradient kernel: 'ss' = operands in shared memory after an smem -> smem
