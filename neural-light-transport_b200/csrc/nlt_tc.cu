@@ -61,7 +61,7 @@ struct TcParams {
   FastDiv div_ntn, div_tpi, div_tx, div_tw, div_ct, div_s;
   int act, mask_act;
   int stages;               // smem ring depth
-  int rawhi;                // option "tc_rawhi" / NLT_TC_RAWHI: A-hi operand = the raw fp32 tile (no hi plane write)
+  int rawhi;                // option "tc_rawhi" / NLT_TC_RAWHI (default 1): A-hi operand = the raw fp32 tile (no hi plane write)
   int ablate;               // DIAGNOSTIC (NLT_TC_ABLATE, wrong results!): 1 no B loads, 2 no transform, 4 no MMA, 8 no epilogue memory traffic, 16 no A loads
   float beta;
   const float* bias;
@@ -957,7 +957,7 @@ static TcPlan tc_plan(const GConvK& k) {
       if (ablate & 32) { const int one = 1; cudaMemcpyToSymbol(g_tc_poll, &one, sizeof(int)); }
     }
     p.ablate = ablate;
-    if (g_opt_tc_rawhi < 0) { const char* e = getenv("NLT_TC_RAWHI"); g_opt_tc_rawhi = (e && e[0] == '1') ? 1 : 0; }
+    if (g_opt_tc_rawhi < 0) { const char* e = getenv("NLT_TC_RAWHI"); g_opt_tc_rawhi = (e && e[0] == '0') ? 0 : 1; }
     p.rawhi = g_opt_tc_rawhi;
   }
   pl.ok = true;

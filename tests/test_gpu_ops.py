@@ -224,11 +224,12 @@ def test_tensor_core_raw_hi_operand(kind, k, s, H, W, segc, cout):
     bits), only lo = x - trunc(x) is written by the transform warps.  Same oracle check, same tolerance (a core that
     ROUNDED its operands would be 1e-3 off here)."""
     import nlt_native as nat
-    nat.set_option('tc_rawhi', 1)
     try:
-        test_gconv_forward_backward(kind, k, s, H, W, segc, cout, 'leakyrelu')
+        for v in (1, 0):         # default form, and the one that writes a rounded hi plane
+            nat.set_option('tc_rawhi', v)
+            test_gconv_forward_backward(kind, k, s, H, W, segc, cout, 'leakyrelu')
     finally:
-        nat.set_option('tc_rawhi', int(os.environ.get('NLT_TC_RAWHI', '0')))
+        nat.set_option('tc_rawhi', int(os.environ.get('NLT_TC_RAWHI', '1')))
 
 
 @pytest.fixture(params=['ss', 'ts'])
