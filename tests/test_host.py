@@ -315,3 +315,43 @@ def test_opbench_layer_table_matches_the_network_wiring():
     assert [cin['query.%d.0' % i] for i in range(7, 14)] == [1024, 640, 320, 160, 80, 40, 36]
     assert cin['query.1.0'] == 32 and cin['obs.1.0'] == 16 and cin['query.6.0'] == 512
     assert rows['query.7.0'][4] == 8 and rows['query.13.0'][4] == 512 and rows['query.13.0'][6] == 3
+
+
+def test_pack_arena_bump_allocation_and_rewind():
+    """engine.PackArena: 256-byte aligned float32 views out of kept chunks, rewound (same addresses) at step begin;
+    a request larger than a chunk gets its own chunk."""
+    import torch
+    import engine
+    a = engine.PackArena()
+    a.CHUNK = 4096
+    dev = torch.device('cpu')
+    x = a.alloc(1000, dev)
+    y = a.alloc(300, dev)
+    assert x.dtype == torch.float32 and x.numel() * 4 >= 1000 and y.numel() * 4 >= 300
+    assert y.data_ptr() - x.data_ptr() == 1024 and (y.data_ptr() - x.data_ptr()) % 256 == 0
+    big = a.alloc(3 * 4096, dev)                     # does not fit the first chunk: a chunk of its own
+    assert big.numel() * 4 >= 3 * 4096 and len(a.chunks) == 2
+    z = a.alloc(3000, dev)                           # fits neither what is left of chunk 0 nor chunk 1
+    assert len(a.chunks) == 3 and z.numel() * 4 >= 3000
+    a.reset()
+    assert a.alloc(1000, dev).data_ptr() == x.data_ptr()      # a captured graph may keep the addresses
+    assert a.alloc(300, dev).data_ptr() == y.data_ptr()
+
+
+def test_scheduling_switches_have_the_documented_defaults():
+    """NLT_SIDE_STREAMS = 2 weight-gradient streams, NLT_PACK_AHEAD off, side stream on; read in a fresh
+    interpreter so that this process's engine module is left alone."""
+    import os
+    import subprocess
+    import sys
+    import engine
+    env = {k: v for k, v in os.environ.items() if k not in ('NLT_SIDE_STREAMS', 'NLT_PACK_AHEAD', 'NLT_NO_SIDE_STREAM')}
+    pkg = os.path.dirname(os.path.abspath(engine.__file__))
+    out = subprocess.run([sys.executable, '-c',
+                          'import sys; sys.path.insert(0, %r); import engine as e; '
+                          'print(e.N_SIDE_STREAMS, e.PACK_AHEAD, e.USE_SIDE_STREAM)' % pkg],
+                         env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split() == ['2', 'False', 'True']
+    ws = engine.Workspace()
+    assert ws.sub(0) is ws and ws.sub(1) is ws.sub(1) and ws.sub(1) is not ws
